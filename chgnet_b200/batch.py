@@ -1,0 +1,242 @@
+"""Batch descriptor: list[CrystalGraph] -> one SoA on the device.
+
+Replaces the per-graph Python loop of the reference's
+``BatchedGraph.from_graphs`` (reference chgnet/model/model.py:792-913): the
+host concatenates every field of every graph into ONE int32 and ONE fp32 pinned
+staging buffer (two H2D copies per batch, instead of 8 per graph,
+crystalgraph.py:102-118), index offsets are applied on the device, and the
+CSR row pointers / gather permutations that make every scatter-add of the model
+an atomics-free segmented reduction are built with a handful of device sorts.
+
+Segment structures (all int32, device):
+  ptr_c   [N+1]   directed edges grouped by center (edges are center-sorted)
+  perm_n  [Ed], ptr_n [N+1]     directed edges grouped by NEIGHBOUR
+  perm_u  [Ed]    directed edges grouped by undirected bond (2 per bond)
+  ptr_u   [Eu+1]  = 2*arange
+  ptr_i   [Eu+1]  angles grouped by bond i (angles are i-sorted)
+  perm_j  [A], ptr_j [Eu+1]     angles grouped by bond j
+  perm_x  [A], ptr_x [N+1]      angles grouped by center atom
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+import torch
+from torch import Tensor
+
+
+@dataclass
+class DeviceBatch:
+    n_graphs: int
+    n_atoms: int
+    n_edges: int  # directed
+    n_bonds: int  # undirected
+    n_angles: int
+    atoms_per_graph: list[int]
+    # atoms
+    z: Tensor
+    frac: Tensor
+    owner: Tensor
+    lattice: Tensor  # [B, 9]
+    volume: Tensor  # [B]
+    # directed edges (center-sorted)
+    center: Tensor
+    nbr: Tensor
+    image: Tensor
+    d2u: Tensor
+    u2d: Tensor
+    ptr_c: Tensor
+    perm_n: Tensor
+    ptr_n: Tensor
+    perm_u: Tensor
+    ptr_u: Tensor
+    # angles (bond-i sorted)
+    ang_atom: Tensor
+    ang_i: Tensor
+    ang_j: Tensor
+    ang_di: Tensor
+    ang_dj: Tensor
+    ptr_i: Tensor
+    perm_j: Tensor
+    ptr_j: Tensor
+    perm_x: Tensor
+    ptr_x: Tensor
+    h2d_bytes: int = 0
+
+
+def _is_sorted(t: Tensor) -> bool:
+    if t.numel() < 2:
+        return True
+    if t.device.type == "cpu":
+        a = t.numpy()
+        return bool(np.all(a[1:] >= a[:-1]))
+    return bool((t[1:] >= t[:-1]).all())
+
+
+def _csr_ptr(sorted_keys: Tensor, n_rows: int) -> Tensor:
+    edges = torch.arange(n_rows + 1, device=sorted_keys.device, dtype=sorted_keys.dtype)
+    return torch.searchsorted(sorted_keys.contiguous(), edges).to(torch.int32)
+
+
+def _group(keys: Tensor, n_rows: int) -> tuple[Tensor, Tensor]:
+    """(perm, ptr) such that rows perm[ptr[r]:ptr[r+1]] are the items with key r."""
+    if keys.numel() == 0:
+        z = torch.zeros(n_rows + 1, dtype=torch.int32, device=keys.device)
+        return keys.to(torch.int32), z
+    sk, perm = torch.sort(keys, stable=True)
+    return perm.to(torch.int32), _csr_ptr(sk, n_rows)
+
+
+def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True) -> DeviceBatch:
+    device = torch.device(device)
+    B = len(graphs)
+    n_at = [int(g.atomic_number.shape[0]) for g in graphs]
+    ag_l = [g.atom_graph.reshape(-1, 2) for g in graphs]  # model.py:841-843
+    n_ed = [int(a.shape[0]) for a in ag_l]
+    n_eu = [int(g.undirected2directed.shape[0]) for g in graphs]
+    bg_l = [g.bond_graph.reshape(-1, 5) for g in graphs]
+    n_an = [int(b.shape[0]) for b in bg_l]
+    N, Ed, Eu, A = sum(n_at), sum(n_ed), sum(n_eu), sum(n_an)
+    for g, e_d, e_u in zip(graphs, n_ed, n_eu):
+        if e_d != 2 * e_u or int(g.directed2undirected.shape[0]) != e_d:
+            raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
+
+    # host-side sortedness checks (cheap; decide whether the device has to reorder)
+    edges_sorted = all(_is_sorted(a[:, 0]) for a in ag_l)
+    angles_sorted = all(_is_sorted(b[:, 1]) for b in bg_l)
+
+    src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
+    pin = src_dev.type == "cpu" and device.type == "cuda"
+
+    # ---- one int32 staging buffer ----
+    int_fields = [
+        ("z", [g.atomic_number.reshape(-1) for g in graphs], N),
+        ("ag", [a.reshape(-1) for a in ag_l], 2 * Ed),
+        ("d2u", [g.directed2undirected.reshape(-1) for g in graphs], Ed),
+        ("u2d", [g.undirected2directed.reshape(-1) for g in graphs], Eu),
+        ("bg", [b.reshape(-1) for b in bg_l], 5 * A),
+    ]
+    flt_fields = [
+        ("frac", [g.atom_frac_coord.detach().reshape(-1) for g in graphs], 3 * N),
+        ("image", [g.neighbor_image.detach().reshape(-1) for g in graphs], 3 * Ed),
+        ("lattice", [g.lattice.detach().reshape(-1) for g in graphs], 9 * B),
+    ]
+    counts_host = np.array([n_at, n_ed, n_eu, n_an], dtype=np.int32).reshape(-1)  # [4*B]
+    n_int = sum(f[2] for f in int_fields) + counts_host.size
+    n_flt = sum(f[2] for f in flt_fields)
+
+    def stage(fields, total, dtype, tail=None):
+        buf = torch.empty(total, dtype=dtype, device=src_dev, pin_memory=pin)
+        off, views = 0, {}
+        for name, parts, size in fields:
+            if size:
+                torch.cat([p.to(dtype) if p.dtype != dtype else p for p in parts], out=buf[off : off + size])
+            views[name] = (off, size)
+            off += size
+        if tail is not None:
+            buf[off : off + tail.numel()] = tail
+            views["_tail"] = (off, tail.numel())
+        dbuf = buf.to(device, non_blocking=True)
+        return dbuf, views
+
+    ibuf, iv = stage(int_fields, n_int, torch.int32, torch.from_numpy(counts_host))
+    fbuf, fv = stage(flt_fields, n_flt, torch.float32)
+    h2d = (n_int + n_flt) * 4 if src_dev != device else 0
+
+    def iview(name):
+        o, s = iv[name]
+        return ibuf[o : o + s]
+
+    def fview(name):
+        o, s = fv[name]
+        return fbuf[o : o + s]
+
+    cnt = iview("_tail").view(4, B).long()  # device copies of the per-graph counts
+    # exclusive prefix sums = per-graph offsets
+    offs = torch.cumsum(cnt, dim=1) - cnt
+    atom_off, ed_off, eu_off = offs[0], offs[1], offs[2]
+
+    def rep(vals: Tensor, which: int, total: int) -> Tensor:
+        return torch.repeat_interleave(vals, cnt[which], output_size=total).to(torch.int32)
+
+    z = iview("z")
+    owner = rep(torch.arange(B, device=device), 0, N)
+    ag = iview("ag").view(Ed, 2)
+    e_atom_off = rep(atom_off, 1, Ed)
+    center = (ag[:, 0] + e_atom_off).contiguous()
+    nbr = (ag[:, 1] + e_atom_off).contiguous()
+    d2u = iview("d2u") + rep(eu_off, 1, Ed)
+    u2d = iview("u2d") + rep(ed_off, 2, Eu)
+    image = fview("image").view(Ed, 3)
+    bg = iview("bg").view(A, 5)
+    a_atom_off, a_eu_off, a_ed_off = rep(atom_off, 3, A), rep(eu_off, 3, A), rep(ed_off, 3, A)
+    ang_atom = bg[:, 0] + a_atom_off
+    ang_i = bg[:, 1] + a_eu_off
+    ang_di = bg[:, 2] + a_ed_off
+    ang_j = bg[:, 3] + a_eu_off
+    ang_dj = bg[:, 4] + a_ed_off
+
+    if not edges_sorted and Ed:
+        # stable sort by center; remap everything that stores a directed index
+        _, perm = torch.sort(center, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(Ed, device=device)
+        center, nbr, d2u, image = center[perm], nbr[perm], d2u[perm], image[perm]
+        u2d = inv[u2d.long()].to(torch.int32)
+        if A:
+            ang_di = inv[ang_di.long()].to(torch.int32)
+            ang_dj = inv[ang_dj.long()].to(torch.int32)
+    if not angles_sorted and A:
+        _, perm = torch.sort(ang_i, stable=True)
+        ang_atom, ang_i, ang_j, ang_di, ang_dj = (t[perm] for t in (ang_atom, ang_i, ang_j, ang_di, ang_dj))
+
+    ptr_c = _csr_ptr(center, N)
+    ptr_i = _csr_ptr(ang_i, Eu)
+    i32 = dict(dtype=torch.int32, device=device)
+    if with_reverse:
+        perm_n, ptr_n = _group(nbr, N)
+        perm_u, _ = _group(d2u, Eu)
+        ptr_u = torch.arange(Eu + 1, **i32) * 2
+        perm_j, ptr_j = _group(ang_j, Eu)
+        perm_x, ptr_x = _group(ang_atom, N)
+    else:
+        empty = torch.zeros(0, **i32)
+        perm_n = perm_u = perm_j = perm_x = empty
+        ptr_n = ptr_x = torch.zeros(N + 1, **i32)
+        ptr_u = ptr_j = torch.zeros(Eu + 1, **i32)
+
+    lattice = fview("lattice").view(B, 9)
+    L = lattice.view(B, 3, 3)
+    volume = (L[:, 0] * torch.linalg.cross(L[:, 1], L[:, 2])).sum(dim=1)  # model.py:834-836
+
+    c = lambda t: t.contiguous()  # noqa: E731
+    return DeviceBatch(
+        n_graphs=B, n_atoms=N, n_edges=Ed, n_bonds=Eu, n_angles=A, atoms_per_graph=n_at,
+        z=c(z), frac=c(fview("frac").view(N, 3)), owner=c(owner), lattice=c(lattice), volume=volume,
+        center=c(center), nbr=c(nbr), image=c(image), d2u=c(d2u), u2d=c(u2d),
+        ptr_c=ptr_c, perm_n=perm_n, ptr_n=ptr_n, perm_u=perm_u, ptr_u=ptr_u,
+        ang_atom=c(ang_atom), ang_i=c(ang_i), ang_j=c(ang_j), ang_di=c(ang_di), ang_dj=c(ang_dj),
+        ptr_i=ptr_i, perm_j=perm_j, ptr_j=ptr_j, perm_x=perm_x, ptr_x=ptr_x, h2d_bytes=h2d,
+    )
+
+
+def partition_graphs(costs: Sequence[float], n_ranks: int) -> list[list[int]]:
+    """Greedy longest-processing-time partition of graph indices over ranks
+    (SURVEY.md §8e): whole graphs per rank, no device-path collective."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * n_ranks
+    parts: list[list[int]] = [[] for _ in range(n_ranks)]
+    for i in order:
+        r = min(range(n_ranks), key=lambda k: loads[k])
+        parts[r].append(i)
+        loads[r] += costs[i]
+    for p in parts:
+        p.sort()
+    return parts
+
+
+def graph_cost(g) -> float:
+    """Work estimate of one graph: message rows (edges + 2.5 x angles)."""
+    return float(g.atom_graph.reshape(-1, 2).shape[0]) + 2.5 * float(g.bond_graph.reshape(-1, 5).shape[0])

@@ -1,0 +1,247 @@
+"""Kernel schedule of the hot path: forward, then ONE reverse pass for F and sigma.
+
+Restates what ``CHGNet._compute`` does (reference chgnet/model/model.py:389-542)
+as a fixed sequence of C-ABI kernel calls on a :class:`DeviceBatch`:
+
+    geometry/basis/embeddings -> 3 x (AtomConv, BondConv, AngleUpdate) -> AtomConv
+    -> readout  [-> reverse of all of it -> force / virial]
+
+Differences from the reference that are deliberate:
+* the dead third AngleUpdate (its output is never read, model.py:470-496) is skipped;
+* forces and stress come from one reverse pass producing dE/dr per directed
+  edge (the reference runs autograd twice, model.py:521-535);
+* no ``create_graph=True`` in inference;
+* every scatter-add is a segmented reduction over the batch's CSR structures.
+
+``kernels`` is the binding object (``chgnet_b200._lib.CudaKernels``).  There is no
+CPU implementation in the product: constructing the engine without the CUDA
+library raises.  Tests inject ``oracle.kernel_specs.SpecKernels`` to check this
+schedule on the CPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+from torch import Tensor
+
+from chgnet_b200.batch import DeviceBatch
+from chgnet_b200.weights import PackedWeights
+
+EV_A3_TO_GPA = 160.21766208  # reference model.py:533
+
+
+@dataclass
+class EngineOutput:
+    energy: Tensor  # [B] fp64 model energy (extensive, eV)
+    e_ref: Tensor  # [B] fp64 AtomRef energy (extensive)
+    site_e: Tensor  # [N]
+    magmom: Tensor | None = None
+    atom_fea: Tensor | None = None
+    crystal_fea: Tensor | None = None
+    force: Tensor | None = None  # [N,3] fp64
+    virial: Tensor | None = None  # [B,9] fp64, sum_e r (x) dE/dr
+    extras: dict = field(default_factory=dict)
+
+
+class Engine:
+    def __init__(self, pw: PackedWeights, kernels) -> None:
+        if kernels is None:
+            raise RuntimeError("chgnet_b200 Engine needs the CUDA kernel library (no CPU path exists)")
+        self.pw = pw
+        self.K = kernels
+
+    # ------------------------------------------------------------------ helpers
+    def _new(self, b: DeviceBatch, *shape, dtype=None) -> Tensor:
+        return torch.empty(*shape, dtype=dtype or self.pw.emb.dtype, device=b.z.device)
+
+    def _zeros(self, b: DeviceBatch, *shape, dtype=None) -> Tensor:
+        return torch.zeros(*shape, dtype=dtype or self.pw.emb.dtype, device=b.z.device)
+
+    def _lin(self, b, x, wt, bias=None, residual=None) -> Tensor:
+        y = self._new(b, x.shape[0], wt.shape[1])
+        self.K.linear(x, wt, bias, residual, y)
+        return y
+
+    def _seg(self, b, data, perm, ptr, n_rows) -> Tensor:
+        out = self._new(b, n_rows, data.shape[1])
+        self.K.segment_sum(data, perm, ptr, 0, out)
+        return out
+
+    # ------------------------------------------------------------------ forward (+ reverse)
+    def run(
+        self,
+        b: DeviceBatch,
+        *,
+        need_grad: bool,
+        need_magmom: bool = False,
+        need_atom_fea: bool = False,
+        need_crystal_fea: bool = False,
+        keep_intermediates: bool = False,
+    ) -> EngineOutput:
+        pw, K, hp = self.pw, self.K, self.pw.hp
+        N, Ed, Eu, A, B = b.n_atoms, b.n_edges, b.n_bonds, b.n_angles, b.n_graphs
+        has_ang = A > 0
+        n_conv = hp.n_conv
+        inter: dict = {}
+
+        # ---- geometry, bases, embeddings -------------------------------------
+        x = self._new(b, N, 64)
+        K.embed_atoms(b.z, pw.emb, x)
+        rvec, dist, rhat = self._new(b, Ed, 3), self._new(b, Ed), self._new(b, Ed, 3)
+        K.edge_geometry(b.frac, b.lattice, b.owner, b.center, b.nbr, b.image, rvec, dist, rhat)
+        e, wag, wbg = self._new(b, Eu, 64), self._new(b, Eu, 64), self._new(b, Eu, 64)
+        K.bond_basis_embed(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                           hp.cutoff_coeff, pw.w3t, e, wag, wbg)
+        ang = None
+        if has_ang:
+            ang = self._new(b, A, 64)
+            K.angle_basis_embed(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang_t, ang)
+        if keep_intermediates:
+            inter.update(x0=x, e0=e, w_ag=wag, w_bg=wbg, a0=ang)
+
+        saved_atom: list[dict] = []
+        saved_bond: list[dict] = []
+        saved_angle: list[dict] = []
+
+        def atom_conv(t: int, x: Tensor, e: Tensor) -> Tensor:
+            gp = pw.atom[t]
+            pcn = self._lin(b, x, gp.extra["wcn_t"])
+            pe = self._lin(b, e, gp.extra["we_t"], bias=gp.extra["b1"])
+            msg = self._new(b, Ed, 64)
+            save_p = self._new(b, Ed, 128) if need_grad else None
+            K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p)
+            agg = self._seg(b, msg, None, b.ptr_c, N)
+            if need_grad:
+                saved_atom.append(dict(pcn=pcn, pe=pe, p=save_p))
+            return self._lin(b, agg, gp.extra["wo_t"], bias=gp.extra["bo"], residual=x)
+
+        magmom = atom_fea = None
+        for t in range(n_conv - 1):
+            x = atom_conv(t, x, e)
+            if has_ang:
+                gp = pw.bond[t]
+                pij = self._lin(b, e, gp.extra["wij_t"], bias=gp.extra["bij"])
+                px = self._lin(b, x, gp.extra["wx_t"])
+                upd = self._new(b, A, 64)
+                s_pre = self._new(b, A, 128) if need_grad else None
+                s_p = self._new(b, A, 128) if need_grad else None
+                K.bond_conv_fwd(pij, px, ang, wbg, b.ang_atom, b.ang_i, b.ang_j, gp.extra["w1a_t"],
+                                gp.w2t, gp.b2, gp.ln, upd, s_pre, s_p)
+                agg = self._seg(b, upd, None, b.ptr_i, Eu)
+                e = self._lin(b, agg, gp.extra["wo_t"], bias=gp.extra["bo"], residual=e)
+                if need_grad:
+                    saved_bond.append(dict(pre=s_pre, p=s_p))
+                if t < n_conv - 2:  # the last AngleUpdate is dead compute
+                    ga = pw.angle[t]
+                    pij = self._lin(b, e, ga.extra["wij_t"], bias=ga.extra["bij"])
+                    px = self._lin(b, x, ga.extra["wx_t"])
+                    ang_new = self._new(b, A, 64)
+                    s_p = self._new(b, A, 128) if need_grad else None
+                    K.angle_update_fwd(pij, px, ang, b.ang_atom, b.ang_i, b.ang_j, ga.extra["w1a_t"], ga.ln,
+                                       ang_new, s_p)
+                    ang = ang_new
+                    if need_grad:
+                        saved_angle.append(dict(p=s_p))
+            if keep_intermediates:
+                inter[f"x{t + 1}"], inter[f"e{t + 1}"] = x, e
+                if t < n_conv - 2:
+                    inter[f"a{t + 1}"] = ang
+            if t == n_conv - 2:  # model.py:477-487
+                if need_atom_fea:
+                    atom_fea = x
+                if need_magmom:
+                    magmom = self._new(b, N)
+                    K.magmom(x, pw.w_mag, pw.b_mag, magmom)
+        x = atom_conv(n_conv - 1, x, e)
+
+        # ---- readout -----------------------------------------------------------
+        site_e = self._new(b, N)
+        h_out = self._new(b, N, 64) if (need_crystal_fea or keep_intermediates) else None
+        energy = self._zeros(b, B, dtype=torch.float64)
+        e_ref = self._zeros(b, B, dtype=torch.float64)
+        g_x = self._new(b, N, 64) if need_grad else None
+        K.readout(x, b.z, b.owner, pw.readout_ln, pw.mlp_wt, pw.mlp_w, pw.mlp_b, pw.w_last, pw.b_last,
+                  pw.atom_ref, site_e, h_out, energy, e_ref, g_x)
+        crystal_fea = None
+        if need_crystal_fea:
+            gptr = torch.zeros(B + 1, dtype=torch.int32, device=b.z.device)
+            gptr[1:] = torch.cumsum(torch.tensor(b.atoms_per_graph, device=b.z.device), 0)
+            crystal_fea = self._seg(b, h_out, None, gptr, B)
+        if keep_intermediates:
+            inter["x_readout"], inter["site_e_model"] = h_out, site_e
+        out = EngineOutput(energy=energy, e_ref=e_ref, site_e=site_e, magmom=magmom, atom_fea=atom_fea,
+                           crystal_fea=crystal_fea, extras=inter)
+        if not need_grad:
+            return out
+
+        # ======================= reverse pass (inputs only) ======================
+        g_e = None  # d(sum E)/d e at the current level
+        g_wag = self._zeros(b, Eu, 64)
+        g_wbg = self._zeros(b, Eu, 64) if has_ang else None
+        g_a = None
+
+        def acc(dst: Tensor | None, x_in: Tensor, wt: Tensor) -> Tensor:
+            """dst + x_in @ wt (dst None -> plain product)."""
+            return self._lin(b, x_in, wt, residual=dst)
+
+        def atom_conv_bwd(t: int, g_xout: Tensor, g_e: Tensor | None) -> tuple[Tensor, Tensor]:
+            gp, sv = pw.atom[t], saved_atom[t]
+            g_agg = self._lin(b, g_xout, gp.extra["wo"])
+            g_pre, g_w = self._new(b, Ed, 128), self._new(b, Ed, 64)
+            K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
+                            g_pre, g_w)
+            sp = self._new(b, N, 256)
+            K.segment_sum(g_pre, None, b.ptr_c, 0, sp[:, :128])
+            K.segment_sum(g_pre, b.perm_n, b.ptr_n, 0, sp[:, 128:])
+            g_xin = acc(g_xout, sp, gp.extra["wcn_b"])
+            spe = self._seg(b, g_pre, b.perm_u, b.ptr_u, Eu)
+            g_e = acc(g_e, spe, gp.extra["we_b"])
+            K.segment_sum(g_w, b.perm_u, b.ptr_u, 1, g_wag)
+            return g_xin, g_e
+
+        def angle_scatter(g_pre: Tensor, g_x: Tensor, g_e: Tensor | None, ex: dict) -> tuple[Tensor, Tensor]:
+            """Push dE/dpre of an angle-indexed GatedMLP back to e (via i and j) and x."""
+            sp = self._new(b, Eu, 256)
+            K.segment_sum(g_pre, None, b.ptr_i, 0, sp[:, :128])
+            K.segment_sum(g_pre, b.perm_j, b.ptr_j, 0, sp[:, 128:])
+            g_e = acc(g_e, sp, ex["wij_b"])
+            spx = self._seg(b, g_pre, b.perm_x, b.ptr_x, N)
+            g_x = acc(g_x, spx, ex["wx_b"])
+            return g_x, g_e
+
+        g_x, g_e = atom_conv_bwd(n_conv - 1, g_x, None)
+        for t in reversed(range(n_conv - 1)):
+            if has_ang:
+                if t < n_conv - 2:  # AngleUpdate_t: a_{t+1} = a_t + G0(e_{t+1}, a_t, x_{t+1})
+                    ga = pw.angle[t]
+                    g_pre, g_a_new = self._new(b, A, 128), self._new(b, A, 64)
+                    K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.extra["w1a_b"], ga.ln, g_pre, g_a_new)
+                    g_a = g_a_new
+                    g_x, g_e = angle_scatter(g_pre, g_x, g_e, ga.extra)
+                # BondConv_t: e_{t+1} = e_t + Wo agg(G(e_t, a_t, x_{t+1}) w_i w_j)
+                gp, sv = pw.bond[t], saved_bond[t]
+                g_agg = self._lin(b, g_e, gp.extra["wo"])
+                g_pre = self._new(b, A, 128)
+                gw_i, gw_j = self._new(b, A, 64), self._new(b, A, 64)
+                if g_a is None:
+                    g_a = self._zeros(b, A, 64)
+                K.bond_conv_bwd(sv["pre"], sv["p"], wbg, b.ang_i, b.ang_j, g_agg, gp.extra["w1a_b"], gp.w2,
+                                gp.ln, g_pre, g_a, gw_i, gw_j)
+                g_x, g_e = angle_scatter(g_pre, g_x, g_e, gp.extra)
+                K.segment_sum(gw_i, None, b.ptr_i, 1, g_wbg)
+                K.segment_sum(gw_j, b.perm_j, b.ptr_j, 1, g_wbg)
+            g_x, g_e = atom_conv_bwd(t, g_x, g_e)
+
+        # ---- geometry reverse: dE/dr per directed edge -> force, virial ------------
+        g_dist = self._new(b, Eu)
+        K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                         hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg if has_ang else self._zeros(b, Eu, 64), g_dist)
+        g_rhat = self._zeros(b, Ed, 3, dtype=torch.float64)
+        if has_ang:
+            K.angle_basis_bwd(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, g_a, g_rhat)
+        force = self._zeros(b, N, 3, dtype=torch.float64)
+        virial = self._zeros(b, B, 9, dtype=torch.float64)
+        K.force_virial(rvec, dist, rhat, g_rhat, g_dist, b.d2u, b.u2d, b.center, b.nbr, b.owner, force, virial)
+        out.force, out.virial = force, virial
+        return out

@@ -1,0 +1,213 @@
+"""Pack a reference ``state_dict`` into the layouts the kernels read.
+
+The ``nn.Module`` parameters (reference names) stay the single
+source of truth; this module only produces re-arranged *views/copies* of them
+(transposes, concatenations, the split of every GatedMLP first layer into its
+per-atom / per-bond / per-angle column blocks).  Call again after a parameter
+update.
+
+First-layer split (the algebraic core of the B200 design):
+``W1 [x_c | e_u | x_n] = W1[:, 0:64] x_c + W1[:, 64:128] e_u + W1[:, 128:192] x_n``
+so the 192->128 (AtomConv, reference layers.py:113-117) and 256->128 (BondConv /
+AngleUpdate, layers.py:238-244, 348-355) products are computed once per ATOM and
+once per BOND instead of once per edge / angle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+from torch import Tensor
+
+
+@dataclass
+class HyperParams:
+    num_radial: int = 31
+    num_angular: int = 31
+    n_conv: int = 4
+    atom_graph_cutoff: float = 6.0
+    bond_graph_cutoff: float = 3.0
+    cutoff_coeff: int = 8
+    use_ln: bool = True
+    readout_ln: bool = True
+    is_intensive: bool = True
+    n_readout_hidden: int = 3
+
+
+@dataclass
+class GatedPack:
+    """One GatedMLP, split by input block."""
+
+    w2t: Tensor | None = None  # [64][128] block halves (core|gate), k-major
+    w2: Tensor | None = None  # [128][64] PyTorch layout stacked (core;gate)
+    b2: Tensor | None = None  # [128]
+    ln: Tensor | None = None  # [4][64]: g1, b1, g2, b2
+    extra: dict = field(default_factory=dict)
+
+
+@dataclass
+class PackedWeights:
+    hp: HyperParams
+    emb: Tensor
+    freq_ag: Tensor
+    freq_bg: Tensor
+    freq_ang: Tensor
+    w3t: Tensor  # [3][R][64]
+    w3: Tensor  # [3][64][R]
+    wang_t: Tensor  # [NA][64]
+    wang: Tensor  # [64][NA]
+    atom: list[GatedPack]
+    bond: list[GatedPack]
+    angle: list[GatedPack]
+    readout_ln: Tensor | None
+    mlp_wt: Tensor
+    mlp_w: Tensor
+    mlp_b: Tensor
+    w_last: Tensor
+    b_last: float
+    w_mag: Tensor
+    b_mag: float
+    atom_ref: Tensor
+
+
+def _cat_t(*blocks: Tensor) -> Tensor:
+    """blocks are [out][in] slices; returns k-major [in][sum(out)] contiguous."""
+    return torch.cat([b.T for b in blocks], dim=1).contiguous()
+
+
+def _ln_pack(sd: dict, prefix: str) -> Tensor | None:
+    if f"{prefix}.bn1.weight" not in sd:
+        return None
+    return torch.stack(
+        [sd[f"{prefix}.bn1.weight"], sd[f"{prefix}.bn1.bias"], sd[f"{prefix}.bn2.weight"], sd[f"{prefix}.bn2.bias"]]
+    ).contiguous()
+
+
+def infer_hyper_params(sd: dict, model_args: dict | None = None) -> HyperParams:
+    a = model_args or {}
+    hp = HyperParams()
+    hp.num_radial = sd["bond_embedding.weight"].shape[1]
+    hp.num_angular = sd["angle_embedding.weight"].shape[1]
+    hp.n_conv = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("atom_conv_layers."))
+    hp.atom_graph_cutoff = float(a.get("atom_graph_cutoff", 6.0))
+    hp.bond_graph_cutoff = float(a.get("bond_graph_cutoff", 3.0))
+    hp.cutoff_coeff = int(a.get("cutoff_coeff", 8))
+    hp.use_ln = "atom_conv_layers.0.twoBody_atom.bn1.weight" in sd
+    hp.readout_ln = "readout_norm.weight" in sd
+    hp.is_intensive = bool(a.get("is_intensive", True))
+    hidden = [k for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight") and sd[k].shape[0] == 64]
+    hp.n_readout_hidden = len(hidden)
+    return hp
+
+
+def pack_weights(state_dict: dict, model_args: dict | None = None, device=None, dtype=torch.float32) -> PackedWeights:
+    sd = {k: v.detach().to(device=device, dtype=dtype) for k, v in state_dict.items()}
+    hp = infer_hyper_params(sd, model_args)
+    for name, dim in (("atom_embedding.embedding.weight", 1), ("bond_embedding.weight", 0), ("angle_embedding.weight", 0)):
+        if sd[name].shape[dim] != 64:
+            raise NotImplementedError("chgnet_b200 kernels are built for atom/bond/angle_fea_dim == 64")
+    if any("bn1.running_mean" in k for k in sd):
+        raise NotImplementedError("gMLP_norm='batch' is not supported by the CUDA path")
+
+    def gated(prefix: str, first: str, second: str | None) -> tuple[Tensor, Tensor, Tensor, GatedPack]:
+        w1c, w1g = sd[f"{prefix}.mlp_core.{first}.weight"], sd[f"{prefix}.mlp_gate.{first}.weight"]
+        b1 = torch.cat([sd[f"{prefix}.mlp_core.{first}.bias"], sd[f"{prefix}.mlp_gate.{first}.bias"]]).contiguous()
+        gp = GatedPack(ln=_ln_pack(sd, prefix))
+        if second is not None:
+            w2c, w2g = sd[f"{prefix}.mlp_core.{second}.weight"], sd[f"{prefix}.mlp_gate.{second}.weight"]
+            if w2c.shape != (64, 64):
+                raise NotImplementedError("GatedMLP hidden_dim must be 64")
+            gp.w2t = _cat_t(w2c, w2g)
+            gp.w2 = torch.cat([w2c, w2g], dim=0).contiguous()
+            gp.b2 = torch.cat([sd[f"{prefix}.mlp_core.{second}.bias"], sd[f"{prefix}.mlp_gate.{second}.bias"]]).contiguous()
+        return w1c, w1g, b1, gp
+
+    atom, bond, angle = [], [], []
+    for t in range(hp.n_conv):
+        w1c, w1g, b1, gp = gated(f"atom_conv_layers.{t}.twoBody_atom", "layers.0", "layers.3")
+        if w1c.shape != (64, 192):
+            raise NotImplementedError("AtomConv GatedMLP must be 192 -> 64 -> 64")
+        cen, bnd, nbr = slice(0, 64), slice(64, 128), slice(128, 192)
+        wo = sd[f"atom_conv_layers.{t}.mlp_out.layers.1.weight"]
+        gp.extra = dict(
+            wcn_t=_cat_t(w1c[:, cen], w1g[:, cen], w1c[:, nbr], w1g[:, nbr]),  # [64][256]
+            we_t=_cat_t(w1c[:, bnd], w1g[:, bnd]),  # [64][128]
+            b1=b1,
+            wcn_b=torch.cat([w1c[:, cen], w1g[:, cen], w1c[:, nbr], w1g[:, nbr]], dim=0).contiguous(),  # [256][64]
+            we_b=torch.cat([w1c[:, bnd], w1g[:, bnd]], dim=0).contiguous(),  # [128][64]
+            wo_t=wo.T.contiguous(),
+            wo=wo.contiguous(),
+            bo=sd.get(f"atom_conv_layers.{t}.mlp_out.layers.1.bias"),
+        )
+        atom.append(gp)
+    bi, bj, an, xc = slice(0, 64), slice(64, 128), slice(128, 192), slice(192, 256)
+    for t in range(hp.n_conv - 1):
+        if f"bond_conv_layers.{t}.twoBody_bond.mlp_core.layers.0.weight" not in sd:
+            raise NotImplementedError("update_bond=False models are not supported")
+        w1c, w1g, b1, gp = gated(f"bond_conv_layers.{t}.twoBody_bond", "layers.0", "layers.3")
+        wo = sd[f"bond_conv_layers.{t}.mlp_out.layers.1.weight"]
+        gp.extra = dict(
+            wij_t=_cat_t(w1c[:, bi], w1g[:, bi], w1c[:, bj], w1g[:, bj]),  # [64][256]
+            bij=torch.cat([b1, torch.zeros_like(b1)]).contiguous(),  # bias rides on the i half
+            wx_t=_cat_t(w1c[:, xc], w1g[:, xc]),
+            w1a_t=_cat_t(w1c[:, an], w1g[:, an]),
+            wij_b=torch.cat([w1c[:, bi], w1g[:, bi], w1c[:, bj], w1g[:, bj]], dim=0).contiguous(),
+            wx_b=torch.cat([w1c[:, xc], w1g[:, xc]], dim=0).contiguous(),
+            w1a_b=torch.cat([w1c[:, an], w1g[:, an]], dim=0).contiguous(),
+            wo_t=wo.T.contiguous(),
+            wo=wo.contiguous(),
+            bo=sd.get(f"bond_conv_layers.{t}.mlp_out.layers.1.bias"),
+        )
+        bond.append(gp)
+        if f"angle_layers.{t}.twoBody_bond.mlp_core.layers.1.weight" not in sd:
+            raise NotImplementedError("update_angle=False / hidden angle layers are not supported")
+        w1c, w1g, b1, gp = gated(f"angle_layers.{t}.twoBody_bond", "layers.1", None)
+        gp.extra = dict(
+            wij_t=_cat_t(w1c[:, bi], w1g[:, bi], w1c[:, bj], w1g[:, bj]),
+            bij=torch.cat([b1, torch.zeros_like(b1)]).contiguous(),
+            wx_t=_cat_t(w1c[:, xc], w1g[:, xc]),
+            w1a_t=_cat_t(w1c[:, an], w1g[:, an]),
+            wij_b=torch.cat([w1c[:, bi], w1g[:, bi], w1c[:, bj], w1g[:, bj]], dim=0).contiguous(),
+            wx_b=torch.cat([w1c[:, xc], w1g[:, xc]], dim=0).contiguous(),
+            w1a_b=torch.cat([w1c[:, an], w1g[:, an]], dim=0).contiguous(),
+        )
+        angle.append(gp)
+
+    hidden_idx = sorted(
+        int(k.split(".")[2]) for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight") and sd[k].shape[0] == 64
+    )
+    last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight"))
+    mlp_w = torch.stack([sd[f"mlp.layers.{i}.weight"] for i in hidden_idx]).contiguous()
+    return PackedWeights(
+        hp=hp,
+        emb=sd["atom_embedding.embedding.weight"].contiguous(),
+        freq_ag=sd["bond_basis_expansion.rbf_expansion_ag.frequencies"].contiguous(),
+        freq_bg=sd["bond_basis_expansion.rbf_expansion_bg.frequencies"].contiguous(),
+        freq_ang=sd["angle_basis_expansion.fourier_expansion.frequencies"].contiguous(),
+        w3t=torch.stack(
+            [sd["bond_embedding.weight"].T, sd["bond_weights_ag.weight"].T, sd["bond_weights_bg.weight"].T]
+        ).contiguous(),
+        w3=torch.stack(
+            [sd["bond_embedding.weight"], sd["bond_weights_ag.weight"], sd["bond_weights_bg.weight"]]
+        ).contiguous(),
+        wang_t=sd["angle_embedding.weight"].T.contiguous(),
+        wang=sd["angle_embedding.weight"].contiguous(),
+        atom=atom,
+        bond=bond,
+        angle=angle,
+        readout_ln=(
+            torch.stack([sd["readout_norm.weight"], sd["readout_norm.bias"]]).contiguous() if hp.readout_ln else None
+        ),
+        mlp_wt=mlp_w.transpose(1, 2).contiguous(),
+        mlp_w=mlp_w,
+        mlp_b=torch.stack([sd[f"mlp.layers.{i}.bias"] for i in hidden_idx]).contiguous(),
+        w_last=sd[f"mlp.layers.{last_idx}.weight"].reshape(-1).contiguous(),
+        b_last=float(sd[f"mlp.layers.{last_idx}.bias"].reshape(-1)[0]),
+        w_mag=sd["site_wise.weight"].reshape(-1).contiguous(),
+        b_mag=float(sd["site_wise.bias"].reshape(-1)[0]),
+        atom_ref=(
+            sd["composition_model.fc.weight"].reshape(-1).contiguous()
+            if "composition_model.fc.weight" in sd
+            else torch.zeros(94, device=device, dtype=dtype)
+        ),
+    )

@@ -1,0 +1,158 @@
+/*
+ * chgnet_b200.h — C ABI of the B200-native CHGNet hot path (libchgnet_b200.so).
+ *
+ * The reference (CederGroupHub/chgnet) has NO native interface for this path:
+ * it is pure PyTorch.  This header is therefore the boundary a
+ * reference maintainer would bind with ctypes from chgnet/model/model.py; each
+ * entry point names the reference lines it replaces.  See INTEGRATION.md for
+ * the binding stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-allocated memory unless it
+ *     says "host"; no entry point allocates or frees device memory;
+ *   - features are fp32 rows of width 64 (CHGNet atom/bond/angle_fea_dim = 64),
+ *     indices are int32 (reference chgnet/graph/crystalgraph.py:12,
+ *     converter.py:143-159);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, negative on error; chg_last_error() then
+ *     returns a static, thread-local message;
+ *   - weight matrices are passed pre-packed; "…_t" means transposed to
+ *     [in_features][out_features] (k-major), otherwise the PyTorch layout
+ *     [out_features][in_features].  chgnet_b200/weights.py does the packing.
+ *
+ * Row layouts used throughout
+ *   P rows of width 128 = [core(64) | gate(64)] pre-activations of a GatedMLP
+ *   (reference chgnet/model/functions.py:168-183).
+ */
+#ifndef CHGNET_B200_H
+#define CHGNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHG_FEA 64
+#define CHG_OK 0
+#define CHG_ERR_ARG (-1)
+#define CHG_ERR_CUDA (-2)
+
+const char* chg_last_error(void);
+int chg_abi_version(void);
+/* number of kernel launches issued by this library since load (host counter) */
+int64_t chg_launch_count(void);
+
+/* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */
+int chg_embed_atoms(const int32_t* z, const float* emb, int32_t n_atoms, float* x, void* stream);
+
+/* ---- K1a: bond geometry per directed edge (model.py:840, encoders.py:98-102)
+ * cart = frac @ L[g];  r = x_c - (x_n + img @ L[g]);  d = |r|;  rhat = r/d        */
+int chg_edge_geometry(const float* frac, const float* lattice, const int32_t* atom_owner,
+                      const int32_t* center, const int32_t* nbr, const float* image,
+                      int32_t n_edges, float* rvec, float* dist, float* rhat, void* stream);
+
+/* ---- K1b: radial Bessel basis (ag + bg) fused with the three 31->64 embeddings
+ * (encoders.py:106-110, basis.py:108-116,188-205, model.py:435-437).
+ * w3t = [3][n_radial][64] : bond_embedding^T, bond_weights_ag^T, bond_weights_bg^T */
+int chg_bond_basis_embed(const float* dist, const int32_t* u2d, int32_t n_bonds,
+                         const float* freq_ag, const float* freq_bg, int32_t n_radial,
+                         float rc_ag, float rc_bg, int32_t p, const float* w3t,
+                         float* e0, float* wag, float* wbg, void* stream);
+/* reverse of K1b: g_dist[u] = d(E)/d(d_u).  w3 = [3][64][n_radial] (PyTorch layout) */
+int chg_bond_basis_bwd(const float* dist, const int32_t* u2d, int32_t n_bonds,
+                       const float* freq_ag, const float* freq_bg, int32_t n_radial,
+                       float rc_ag, float rc_bg, int32_t p, const float* w3,
+                       const float* g_e0, const float* g_wag, const float* g_wbg,
+                       float* g_dist, void* stream);
+
+/* ---- K2: Fourier angle basis fused with angle_embedding
+ * (model.py:864-870, encoders.py:144-146, basis.py:35-40, model.py:439).
+ * n_basis = 2*n_freq+1; wt = [n_basis][64]                                        */
+int chg_angle_basis_embed(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
+                          int32_t n_angles, const float* freq, int32_t n_freq,
+                          const float* wt, float* a0, void* stream);
+/* reverse of K2: g_rhat[e] += dE/d rhat_e (fp64 atomics); w = [64][n_basis]        */
+int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
+                        int32_t n_angles, const float* freq, int32_t n_freq,
+                        const float* w, const float* g_a0, double* g_rhat, void* stream);
+
+/* ---- dense feature mixing: y = x @ wt (+ bias) (+ residual)
+ * x [m][k], wt [k][n_out], k in {64,128,256}, n_out multiple of 64.
+ * Used for the per-atom / per-bond halves of every GatedMLP first layer, for
+ * mlp_out + residual (layers.py:129-132, 256-260) and for their transposes.      */
+int chg_linear(const float* x, int32_t m, int32_t k, const float* wt, const float* bias,
+               const float* residual, int32_t n_out, float* y, void* stream);
+
+/* ---- K4: AtomConv message (layers.py:113-121, functions.py:168-183)
+ * pre = pcn[c][0:128] + pe[u] + pcn[n][128:256];  p = W2.silu(pre)+b2;
+ * msg = silu(LN1(p_core)) * sigmoid(LN2(p_gate)) * wag[u].
+ * pcn [N][256], pe [Eu][128] (first-layer bias folded in), w2t [64][128] block
+ * diagonal halves (core|gate), ln = [4][64] (g1,b1,g2,b2) or NULL.               */
+int chg_atom_conv_fwd(const float* pcn, const float* pe, const float* wag,
+                      const int32_t* center, const int32_t* nbr, const int32_t* d2u,
+                      int32_t n_edges, const float* w2t, const float* b2, const float* ln,
+                      float* msg, float* save_p, void* stream);
+/* reverse: g_pre[e][128] = dE/dpre, g_w[e][64] = dE/d wag row contribution        */
+int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag,
+                      const int32_t* center, const int32_t* nbr, const int32_t* d2u,
+                      int32_t n_edges, const float* save_p, const float* g_agg,
+                      const float* w2, const float* ln, float* g_pre, float* g_w,
+                      void* stream);
+
+/* ---- K4s/K5s: segmented gather-reduce (functions.py:25-37 without atomics)
+ * out[r] (+)= sum_{k in [ptr[r],ptr[r+1])} data[perm ? perm[k] : k], width 64|128 */
+int chg_segment_sum(const float* data, int32_t width, const int32_t* perm,
+                    const int32_t* ptr, int32_t n_rows, int32_t accumulate, float* out,
+                    void* stream);
+
+/* ---- K5: BondConv message (layers.py:238-249)
+ * pre = pij[i][0:128] + pij[j][128:256] + px[c] + ang[a] @ w1a_t;
+ * upd = G(pre) * wbg[i] * wbg[j].  save_pre/save_p may be NULL (no backward).     */
+int chg_bond_conv_fwd(const float* pij, const float* px, const float* ang, const float* wbg,
+                      const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                      int32_t n_angles, const float* w1a_t, const float* w2t,
+                      const float* b2, const float* ln, float* upd, float* save_pre,
+                      float* save_p, void* stream);
+int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg,
+                      const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles,
+                      const float* g_agg, const float* w1a, const float* w2, const float* ln,
+                      float* g_pre, float* g_ang, float* gw_i, float* gw_j, void* stream);
+
+/* ---- K6: AngleUpdate (layers.py:348-360): ang_new = ang + G0(pre), no hidden    */
+int chg_angle_update_fwd(const float* pij, const float* px, const float* ang,
+                         const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                         int32_t n_angles, const float* w1a_t, const float* ln,
+                         float* ang_new, float* save_p, void* stream);
+/* g_ang_in may be NULL (zero).  g_ang_out = g_ang_in + g_pre @ w1a                 */
+int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles,
+                         const float* w1a, const float* ln, float* g_pre, float* g_ang_out,
+                         void* stream);
+
+/* ---- K7: readout (model.py:497-509) + AtomRef sum (composition_model.py:175-205)
+ * h = LN(x); site_e = MLP(h); e_graph[owner] += site_e (fp64); e_ref[owner] +=
+ * atom_ref[z-1] (fp64).  mlp_wt [n_hidden][64][64] (k-major), mlp_w same in
+ * PyTorch layout (needed only when g_x != NULL), mlp_b [n_hidden][64],
+ * w_last [64], b_last host scalar.  Optional outputs (NULL to skip): h_out [N][64]
+ * (for crystal_fea), g_x [N][64] = d(sum E)/dx.                                   */
+int chg_readout(const float* x, const int32_t* z, const int32_t* atom_owner, int32_t n_atoms,
+                const float* ln, const float* mlp_wt, const float* mlp_w, const float* mlp_b,
+                int32_t n_hidden, const float* w_last, float b_last, const float* atom_ref,
+                float* site_e, float* h_out, double* e_graph, double* e_ref, float* g_x,
+                void* stream);
+/* ---- K7a: magmom head (model.py:483-487): m = |w.x + b|                         */
+int chg_magmom(const float* x, int32_t n_atoms, const float* w, float b, float* m, void* stream);
+
+/* ---- K1c: force + virial (model.py:517-535 as ONE reverse pass)
+ * g_r[e] = (g_rhat[e] - rhat (rhat.g_rhat))/d + [e == u2d[d2u[e]]] g_dist[d2u[e]] rhat
+ * force[c] -= g_r; force[n] += g_r; virial[owner[c]] += rvec (x) g_r   (fp64)       */
+int chg_force_virial(const float* rvec, const float* dist, const float* rhat,
+                     const double* g_rhat, const float* g_dist, const int32_t* d2u,
+                     const int32_t* u2d, const int32_t* center, const int32_t* nbr,
+                     const int32_t* atom_owner, int32_t n_edges, double* force,
+                     double* virial, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHGNET_B200_H */

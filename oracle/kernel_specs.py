@@ -1,0 +1,268 @@
+"""TEST INFRASTRUCTURE — executable specification of every C-ABI kernel.
+
+One torch (CPU, fp32 or fp64) function per entry point of
+``include/chgnet_b200.h``, same argument order and caller-allocated outputs.
+The reverse kernels are written as EXPLICIT formulas (no autograd) — they are
+the maths the CUDA kernels transcribe; ``tests/test_engine_spec.py`` checks the
+whole chain against ``oracle/chgnet_oracle.py`` (autograd, fp64), and the
+``-m gpu`` tests check each CUDA kernel against the function of the same name
+here.  Never imported by the product path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor
+
+
+def _sig(x):
+    return torch.sigmoid(x)
+
+
+def _silu(x):
+    return x * _sig(x)
+
+
+def _dsilu(x):
+    s = _sig(x)
+    return s * (1 + x * (1 - s))
+
+
+def _ln_fwd(p, g, b, eps=1e-5):
+    mu = p.mean(dim=1, keepdim=True)
+    var = ((p - mu) ** 2).mean(dim=1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    xhat = (p - mu) * rstd
+    return xhat * g + b, xhat, rstd
+
+
+def _ln_bwd(gy, xhat, rstd, g):
+    gx = gy * g
+    return rstd * (gx - gx.mean(dim=1, keepdim=True) - xhat * (gx * xhat).mean(dim=1, keepdim=True))
+
+
+def _gate_fwd(p, ln):
+    """p [M,128] -> out [M,64] and the pieces the reverse needs."""
+    pc, pg = p[:, :64], p[:, 64:]
+    if ln is not None:
+        y1, xh1, r1 = _ln_fwd(pc, ln[0], ln[1])
+        y2, xh2, r2 = _ln_fwd(pg, ln[2], ln[3])
+    else:
+        y1, y2, xh1, xh2, r1, r2 = pc, pg, None, None, None, None
+    core, gate = _silu(y1), _sig(y2)
+    return core * gate, (y1, y2, core, gate, xh1, xh2, r1, r2)
+
+
+def _gate_bwd(g_out, saved, ln):
+    y1, y2, core, gate, xh1, xh2, r1, r2 = saved
+    gy1 = g_out * gate * _dsilu(y1)
+    gy2 = g_out * core * gate * (1 - gate)
+    if ln is not None:
+        gy1 = _ln_bwd(gy1, xh1, r1, ln[0])
+        gy2 = _ln_bwd(gy2, xh2, r2, ln[2])
+    return torch.cat([gy1, gy2], dim=1)
+
+
+def _rbf(d, freq, rc, p):
+    """basis [M,R] and d(basis)/dd [M,R]  (SURVEY.md appendix B)."""
+    d = d[:, None]
+    x = d / rc
+    nrm = math.sqrt(2.0 / rc)
+    s, c = torch.sin(freq * x), torch.cos(freq * x)
+    if p != 0:
+        a, b, cc = -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
+        env = 1 + a * x**p + b * x ** (p + 1) + cc * x ** (p + 2)
+        denv = (a * p * x ** (p - 1) + b * (p + 1) * x**p + cc * (p + 2) * x ** (p + 1)) / rc
+        inside = x < 1
+        env = torch.where(inside, env, torch.zeros_like(env))
+        denv = torch.where(inside, denv, torch.zeros_like(denv))
+    else:
+        env, denv = torch.ones_like(x), torch.zeros_like(x)
+    raw = nrm * s / d
+    draw = nrm * ((freq / rc) * c / d - s / d**2)
+    return raw * env, draw * env + raw * denv
+
+
+class SpecKernels:
+    """Drop-in for ``chgnet_b200._lib.CudaKernels`` in CPU tests."""
+
+    name = "spec"
+    launches = 0
+
+    # ---- K0
+    def embed_atoms(self, z, emb, x):
+        x.copy_(emb[z.long() - 1])
+
+    # ---- K1a
+    def edge_geometry(self, frac, lattice, owner, center, nbr, image, rvec, dist, rhat):
+        L = lattice.view(-1, 3, 3)
+        cart = torch.einsum("ni,nij->nj", frac, L[owner.long()])
+        c, n = center.long(), nbr.long()
+        Le = L[owner.long()[c]]
+        r = cart[c] - (cart[n] + torch.einsum("ei,eij->ej", image, Le))
+        d = torch.linalg.norm(r, dim=1)
+        rvec.copy_(r), dist.copy_(d), rhat.copy_(r / d[:, None])
+
+    # ---- K1b
+    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg):
+        du = dist[u2d.long()]
+        bag, _ = _rbf(du, freq_ag, rc_ag, p)
+        bbg, _ = _rbf(du, freq_bg, rc_bg, p)
+        e0.copy_(bag @ w3t[0]), wag.copy_(bag @ w3t[1]), wbg.copy_(bbg @ w3t[2])
+
+    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist):
+        du = dist[u2d.long()]
+        _, dag = _rbf(du, freq_ag, rc_ag, p)
+        _, dbg = _rbf(du, freq_bg, rc_bg, p)
+        gb_ag = g_e0 @ w3[0] + g_wag @ w3[1]
+        gb_bg = g_wbg @ w3[2]
+        g_dist.copy_((gb_ag * dag).sum(dim=1) + (gb_bg * dbg).sum(dim=1))
+
+    # ---- K2
+    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0):
+        u = (rhat[ang_di.long()] * rhat[ang_dj.long()]).sum(dim=1) * (1 - 1e-6)
+        th = torch.acos(u)
+        arg = th[:, None] * freq[None, :]
+        f = torch.cat([torch.full_like(th[:, None], 1 / math.sqrt(2.0)), torch.sin(arg), torch.cos(arg)], dim=1)
+        a0.copy_((f / math.sqrt(math.pi)) @ wt)
+
+    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat):
+        ri, rj = rhat[ang_di.long()], rhat[ang_dj.long()]
+        u = (ri * rj).sum(dim=1) * (1 - 1e-6)
+        th = torch.acos(u)
+        arg = th[:, None] * freq[None, :]
+        nf = freq.shape[0]
+        gf = (g_a0 @ w) / math.sqrt(math.pi)  # [A, 2F+1]
+        g_th = (gf[:, 1 : 1 + nf] * torch.cos(arg) * freq).sum(dim=1) - (gf[:, 1 + nf :] * torch.sin(arg) * freq).sum(dim=1)
+        g_u = -g_th / torch.sqrt(1 - u * u) * (1 - 1e-6)
+        g_rhat.index_add_(0, ang_di.long(), (g_u[:, None] * rj).to(g_rhat.dtype))
+        g_rhat.index_add_(0, ang_dj.long(), (g_u[:, None] * ri).to(g_rhat.dtype))
+
+    # ---- dense
+    def linear(self, x, wt, bias, residual, y):
+        out = x @ wt
+        if bias is not None:
+            out = out + bias
+        if residual is not None:
+            out = out + residual
+        y.copy_(out)
+
+    # ---- K4
+    def _atom_pre(self, pcn, pe, center, nbr, d2u):
+        return pcn[center.long(), :128] + pe[d2u.long()] + pcn[nbr.long(), 128:]
+
+    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p):
+        h = _silu(self._atom_pre(pcn, pe, center, nbr, d2u))
+        p = torch.cat([h[:, :64] @ w2t[:, :64], h[:, 64:] @ w2t[:, 64:]], dim=1) + b2
+        out, _ = _gate_fwd(p, ln)
+        msg.copy_(out * wag[d2u.long()])
+        if save_p is not None:
+            save_p.copy_(p)
+
+    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w):
+        pre = self._atom_pre(pcn, pe, center, nbr, d2u)
+        out, saved = _gate_fwd(save_p, ln)
+        g_msg = g_agg[center.long()]
+        g_w.copy_(g_msg * out)
+        g_p = _gate_bwd(g_msg * wag[d2u.long()], saved, ln)
+        g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
+        g_pre.copy_(g_h * _dsilu(pre))
+
+    # ---- K4s
+    def segment_sum(self, data, perm, ptr, accumulate, out):
+        n_rows = ptr.shape[0] - 1
+        counts = (ptr[1:] - ptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(n_rows), counts)
+        total = int(ptr[-1])
+        src = (data if perm is None else data[perm.long()])[:total]
+        acc = torch.zeros_like(out).index_add_(0, rows, src)
+        if accumulate:
+            out.add_(acc)
+        else:
+            out.copy_(acc)
+
+    # ---- K5
+    def _bond_pre(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t):
+        return pij[ang_i.long(), :128] + pij[ang_j.long(), 128:] + px[ang_atom.long()] + ang @ w1a_t
+
+    def bond_conv_fwd(self, pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p):
+        pre = self._bond_pre(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t)
+        h = _silu(pre)
+        p = torch.cat([h[:, :64] @ w2t[:, :64], h[:, 64:] @ w2t[:, 64:]], dim=1) + b2
+        out, _ = _gate_fwd(p, ln)
+        upd.copy_(out * wbg[ang_i.long()] * wbg[ang_j.long()])
+        if save_pre is not None:
+            save_pre.copy_(pre)
+        if save_p is not None:
+            save_p.copy_(p)
+
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j):
+        out, saved = _gate_fwd(save_p, ln)
+        wi, wj = wbg[ang_i.long()], wbg[ang_j.long()]
+        g_upd = g_agg[ang_i.long()]
+        gw_i.copy_(g_upd * out * wj)
+        gw_j.copy_(g_upd * out * wi)
+        g_p = _gate_bwd(g_upd * wi * wj, saved, ln)
+        g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
+        gp = g_h * _dsilu(save_pre)
+        g_pre.copy_(gp)
+        g_ang.add_(gp @ w1a)
+
+    # ---- K6
+    def angle_update_fwd(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p):
+        p = self._bond_pre(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t)
+        out, _ = _gate_fwd(p, ln)
+        ang_new.copy_(out + ang)
+        if save_p is not None:
+            save_p.copy_(p)
+
+    def angle_update_bwd(self, save_p, g_ang_in, w1a, ln, g_pre, g_ang_out):
+        _, saved = _gate_fwd(save_p, ln)
+        if g_ang_in is None:
+            g_ang_in = torch.zeros_like(save_p[:, :64])
+        gp = _gate_bwd(g_ang_in, saved, ln)
+        g_pre.copy_(gp)
+        g_ang_out.copy_(g_ang_in + gp @ w1a)
+
+    # ---- K7
+    def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph, e_ref, g_x):
+        if ln is not None:
+            h0, xhat, rstd = _ln_fwd(x, ln[0], ln[1])
+        else:
+            h0 = x
+        acts, h = [], h0
+        for l in range(mlp_wt.shape[0]):
+            zl = h @ mlp_wt[l] + mlp_b[l]
+            acts.append(zl)
+            h = _silu(zl)
+        se = h @ w_last + b_last
+        site_e.copy_(se)
+        if h_out is not None:
+            h_out.copy_(h0)
+        e_graph.index_add_(0, owner.long(), se.to(e_graph.dtype))
+        e_ref.index_add_(0, owner.long(), atom_ref[z.long() - 1].to(e_ref.dtype))
+        if g_x is not None:
+            g = w_last[None, :].expand_as(h).clone()
+            for l in reversed(range(mlp_wt.shape[0])):
+                g = (g * _dsilu(acts[l])) @ mlp_w[l]
+            if ln is not None:
+                g = _ln_bwd(g, xhat, rstd, ln[0])
+            g_x.copy_(g)
+
+    def magmom(self, x, w, b, m):
+        m.copy_(torch.abs(x @ w + b))
+
+    # ---- K1c
+    def force_virial(self, rvec, dist, rhat, g_rhat, g_dist, d2u, u2d, center, nbr, owner, force, virial):
+        gr = g_rhat.to(torch.float64)
+        rh = rhat.to(torch.float64)
+        d = dist.to(torch.float64)
+        g = (gr - rh * (rh * gr).sum(dim=1, keepdim=True)) / d[:, None]
+        u = d2u.long()
+        is_rep = u2d.long()[u] == torch.arange(len(u))
+        g = g + torch.where(is_rep, g_dist.to(torch.float64)[u], torch.zeros_like(d))[:, None] * rh
+        force.index_add_(0, center.long(), -g)
+        force.index_add_(0, nbr.long(), g)
+        outer = rvec.to(torch.float64)[:, :, None] * g[:, None, :]
+        virial.index_add_(0, owner.long()[center.long()], outer.reshape(-1, 9))
