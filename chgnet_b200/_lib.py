@@ -1,0 +1,196 @@
+"""ctypes binding of ``libchgnet_b200.so`` (the C ABI in include/chgnet_b200.h).
+
+PyTorch is plumbing here: tensors only provide device memory (``data_ptr()``) and
+the current CUDA stream.  There is NO fallback: if the shared library is missing
+or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p
+
+import torch
+from torch import Tensor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchgnet_b200.so")
+
+P, I, F = c_void_p, c_int32, c_float
+
+# name -> argument ctypes (the trailing stream pointer included); mirrors the header 1:1
+SIGNATURES: dict[str, list] = {
+    "chg_embed_atoms": [P, P, I, P, P],
+    "chg_edge_geometry": [P, P, P, P, P, P, I, P, P, P, P],
+    "chg_bond_basis_embed": [P, P, I, P, P, I, F, F, I, P, P, P, P, P],
+    "chg_bond_basis_bwd": [P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
+    "chg_angle_basis_embed": [P, P, P, I, P, I, P, P, P],
+    "chg_angle_basis_bwd": [P, P, P, I, P, I, P, P, P, P],
+    "chg_linear": [P, I, I, P, P, P, I, P, P],
+    "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P],
+    "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_segment_sum": [P, I, P, P, I, I, P, I, P],
+    "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P],
+    "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
+    "chg_angle_update_fwd": [P, P, P, P, P, P, I, P, P, P, P, P],
+    "chg_angle_update_bwd": [P, P, I, P, P, P, P, P],
+    "chg_readout": [P, P, P, I, P, P, P, P, I, P, F, P, P, P, P, P, P, P],
+    "chg_magmom": [P, I, P, F, P, P],
+    "chg_force_virial": [P, P, P, P, P, P, P, P, P, P, I, P, P, P],
+}
+
+_lib = None
+
+
+class ChgnetB200Error(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None) -> ctypes.CDLL:
+    """dlopen the kernel library; raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ChgnetB200Error(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C chgnet_b200/csrc`). chgnet_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(path)
+    lib.chg_last_error.restype = c_char_p
+    lib.chg_last_error.argtypes = []
+    lib.chg_abi_version.restype = c_int32
+    lib.chg_abi_version.argtypes = []
+    lib.chg_launch_count.restype = c_int64
+    lib.chg_launch_count.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int32
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _p(t: Tensor | None):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+class CudaKernels:
+    """Python face of the C ABI: one method per entry point, tensors in, nothing returned."""
+
+    name = "cuda"
+
+    def __init__(self) -> None:
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise ChgnetB200Error("chgnet_b200 needs a CUDA device (B200 / sm_100a); none is visible")
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _call(self, name: str, *args) -> None:
+        rc = getattr(self.lib, name)(*args, self._stream())
+        if rc != 0:
+            raise ChgnetB200Error(f"{name} failed ({rc}): {self.lib.chg_last_error().decode()}")
+
+    @staticmethod
+    def _chk(*tensors: Tensor | None) -> None:
+        for t in tensors:
+            if t is not None and (not t.is_cuda or not t.is_contiguous()):
+                raise ChgnetB200Error("kernel arguments must be contiguous CUDA tensors")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.chg_launch_count())
+
+    # ------------------------------------------------------------------ kernels
+    def embed_atoms(self, z, emb, x):
+        self._chk(z, emb, x)
+        self._call("chg_embed_atoms", _p(z), _p(emb), z.shape[0], _p(x))
+
+    def edge_geometry(self, frac, lattice, owner, center, nbr, image, rvec, dist, rhat):
+        self._chk(frac, lattice, owner, center, nbr, image, rvec, dist, rhat)
+        self._call("chg_edge_geometry", _p(frac), _p(lattice), _p(owner), _p(center), _p(nbr), _p(image),
+                   center.shape[0], _p(rvec), _p(dist), _p(rhat))
+
+    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg):
+        self._chk(dist, u2d, freq_ag, freq_bg, w3t, e0, wag, wbg)
+        self._call("chg_bond_basis_embed", _p(dist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
+                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3t), _p(e0), _p(wag), _p(wbg))
+
+    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist):
+        self._chk(dist, u2d, freq_ag, freq_bg, w3, g_e0, g_wag, g_wbg, g_dist)
+        self._call("chg_bond_basis_bwd", _p(dist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
+                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3), _p(g_e0), _p(g_wag), _p(g_wbg),
+                   _p(g_dist))
+
+    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0):
+        self._chk(rhat, ang_di, ang_dj, freq, wt, a0)
+        self._call("chg_angle_basis_embed", _p(rhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
+                   freq.shape[0], _p(wt), _p(a0))
+
+    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat):
+        self._chk(rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat)
+        self._call("chg_angle_basis_bwd", _p(rhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
+                   freq.shape[0], _p(w), _p(g_a0), _p(g_rhat))
+
+    def linear(self, x, wt, bias, residual, y):
+        self._chk(x, wt, bias, residual, y)
+        self._call("chg_linear", _p(x), x.shape[0], x.shape[1], _p(wt), _p(bias), _p(residual), wt.shape[1], _p(y))
+
+    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p):
+        self._chk(pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p)
+        self._call("chg_atom_conv_fwd", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), center.shape[0],
+                   _p(w2t), _p(b2), _p(ln), _p(msg), _p(save_p))
+
+    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w):
+        self._chk(pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w)
+        self._call("chg_atom_conv_bwd", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), center.shape[0],
+                   _p(save_p), _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(g_w))
+
+    def segment_sum(self, data, perm, ptr, accumulate, out):
+        self._chk(data, perm, ptr)
+        if not out.is_cuda or out.stride(1) != 1:
+            raise ChgnetB200Error("segment_sum output must be a CUDA tensor with unit column stride")
+        self._call("chg_segment_sum", _p(data), data.shape[1], _p(perm), _p(ptr), ptr.shape[0] - 1,
+                   int(accumulate), _p(out), out.stride(0))
+
+    def bond_conv_fwd(self, pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p):
+        self._chk(pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p)
+        self._call("chg_bond_conv_fwd", _p(pij), _p(px), _p(ang), _p(wbg), _p(ang_atom), _p(ang_i), _p(ang_j),
+                   ang_i.shape[0], _p(w1a_t), _p(w2t), _p(b2), _p(ln), _p(upd), _p(save_pre), _p(save_p))
+
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j):
+        self._chk(save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j)
+        self._call("chg_bond_conv_bwd", _p(save_pre), _p(save_p), _p(wbg), _p(ang_i), _p(ang_j), ang_i.shape[0],
+                   _p(g_agg), _p(w1a), _p(w2), _p(ln), _p(g_pre), _p(g_ang), _p(gw_i), _p(gw_j))
+
+    def angle_update_fwd(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p):
+        self._chk(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p)
+        self._call("chg_angle_update_fwd", _p(pij), _p(px), _p(ang), _p(ang_atom), _p(ang_i), _p(ang_j),
+                   ang_i.shape[0], _p(w1a_t), _p(ln), _p(ang_new), _p(save_p))
+
+    def angle_update_bwd(self, save_p, g_ang_in, w1a, ln, g_pre, g_ang_out):
+        self._chk(save_p, g_ang_in, w1a, ln, g_pre, g_ang_out)
+        self._call("chg_angle_update_bwd", _p(save_p), _p(g_ang_in), save_p.shape[0], _p(w1a), _p(ln), _p(g_pre),
+                   _p(g_ang_out))
+
+    def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph,
+                e_ref, g_x):
+        self._chk(x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, atom_ref, site_e, h_out, e_graph, e_ref, g_x)
+        self._call("chg_readout", _p(x), _p(z), _p(owner), x.shape[0], _p(ln), _p(mlp_wt), _p(mlp_w), _p(mlp_b),
+                   mlp_wt.shape[0], _p(w_last), float(b_last), _p(atom_ref), _p(site_e), _p(h_out), _p(e_graph),
+                   _p(e_ref), _p(g_x))
+
+    def magmom(self, x, w, b, m):
+        self._chk(x, w, m)
+        self._call("chg_magmom", _p(x), x.shape[0], _p(w), float(b), _p(m))
+
+    def force_virial(self, rvec, dist, rhat, g_rhat, g_dist, d2u, u2d, center, nbr, owner, force, virial):
+        self._chk(rvec, dist, rhat, g_rhat, g_dist, d2u, u2d, center, nbr, owner, force, virial)
+        self._call("chg_force_virial", _p(rvec), _p(dist), _p(rhat), _p(g_rhat), _p(g_dist), _p(d2u), _p(u2d),
+                   _p(center), _p(nbr), _p(owner), center.shape[0], _p(force), _p(virial))

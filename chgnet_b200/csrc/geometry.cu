@@ -1,0 +1,451 @@
+// Geometry, basis expansion (+ fused 31->64 embeddings), their reverse, and the
+// force / virial accumulation.  One warp per bond / angle; lanes own basis functions
+// in the expansion phase and feature columns (lane, lane+32) in the embedding phase.
+//
+// Reference: chgnet/model/model.py:826-877 (BatchedGraph.from_graphs geometry),
+// encoders.py:98-110, 144-146, basis.py:33-40, 108-116, 188-205, model.py:432-439,
+// and the two autograd.grad calls of model.py:517-535 (here one analytic pass).
+#include "common.cuh"
+
+namespace chg {
+namespace {
+
+constexpr int MAX_BASIS = 32;  // radial <= 32, angular (2F+1) <= 32 : one lane per basis function
+
+__global__ void embed_atoms_kernel(const int32_t* __restrict__ z, const float* __restrict__ emb, int n_atoms,
+                                   float* __restrict__ x) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+  const int atom = idx >> 4, c4 = idx & 15;
+  if (atom >= n_atoms) return;
+  const int row = z[atom] - 1;
+  stg4(x + (size_t)atom * 64 + c4 * 4, ldg4(emb + (size_t)row * 64 + c4 * 4));
+}
+
+__global__ void edge_geometry_kernel(const float* __restrict__ frac, const float* __restrict__ lattice,
+                                     const int32_t* __restrict__ owner, const int32_t* __restrict__ center,
+                                     const int32_t* __restrict__ nbr, const float* __restrict__ image, int n_edges,
+                                     float* __restrict__ rvec, float* __restrict__ dist, float* __restrict__ rhat) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int c = center[e], n = nbr[e];
+  const float* L = lattice + (size_t)owner[c] * 9;
+  float l[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) l[i] = __ldg(L + i);
+  const float fc[3] = {frac[c * 3], frac[c * 3 + 1], frac[c * 3 + 2]};
+  const float fn[3] = {frac[n * 3], frac[n * 3 + 1], frac[n * 3 + 2]};
+  const float im[3] = {image[(size_t)e * 3], image[(size_t)e * 3 + 1], image[(size_t)e * 3 + 2]};
+  float r[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    // cart = frac @ L ; r = x_c - (x_n + img @ L)      (model.py:840, encoders.py:98-99)
+    const float xc = fmaf(fc[2], l[6 + j], fmaf(fc[1], l[3 + j], fc[0] * l[j]));
+    const float xn = fmaf(fn[2], l[6 + j], fmaf(fn[1], l[3 + j], fn[0] * l[j]));
+    const float sh = fmaf(im[2], l[6 + j], fmaf(im[1], l[3 + j], im[0] * l[j]));
+    r[j] = xc - (xn + sh);
+  }
+  const float d = sqrtf(fmaf(r[2], r[2], fmaf(r[1], r[1], r[0] * r[0])));
+  dist[e] = d;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    rvec[(size_t)e * 3 + j] = r[j];
+    rhat[(size_t)e * 3 + j] = r[j] / d;  // d == 0 -> NaN, as in the reference (tests/test_encoders.py:83-96)
+  }
+}
+
+struct Envelope {
+  float env, denv;  // value and d/dd
+};
+// polynomial cutoff 1 + a x^p + b x^(p+1) + c x^(p+2), x = d/rc < 1 (basis.py:184-205)
+__device__ __forceinline__ Envelope envelope(float d, float rc, int p) {
+  Envelope o;
+  if (p == 0) {
+    o.env = 1.f;
+    o.denv = 0.f;
+    return o;
+  }
+  const float x = d / rc;
+  if (!(x < 1.f)) {
+    o.env = 0.f;
+    o.denv = 0.f;
+    return o;
+  }
+  const float pf = (float)p;
+  const float a = -(pf + 1.f) * (pf + 2.f) * 0.5f, b = pf * (pf + 2.f), c = -pf * (pf + 1.f) * 0.5f;
+  float xp1 = 1.f;  // x^(p-1)
+  for (int i = 0; i < p - 1; ++i) xp1 *= x;
+  const float xp = xp1 * x;
+  o.env = 1.f + xp * (a + x * (b + x * c));
+  o.denv = xp1 * (a * pf + x * (b * (pf + 1.f) + x * c * (pf + 2.f))) / rc;
+  return o;
+}
+
+// ---- bond basis + embeddings ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+bond_basis_embed_kernel(const float* __restrict__ dist, const int32_t* __restrict__ u2d, int n_bonds,
+                        const float* __restrict__ freq_ag, const float* __restrict__ freq_bg, int R, float rc_ag,
+                        float rc_bg, int p, const float* __restrict__ w3t, float* __restrict__ e0,
+                        float* __restrict__ wag, float* __restrict__ wbg) {
+  extern __shared__ __align__(16) float s_w[];  // [3][R][64]
+  for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3t[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float f_ag = lane < R ? freq_ag[lane] : 0.f;
+  const float f_bg = lane < R ? freq_bg[lane] : 0.f;
+  const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
+  const float inv_ag = 1.f / rc_ag, inv_bg = 1.f / rc_bg;  // basis.py:108 multiplies by 1/cutoff
+  for (int u = warp; u < n_bonds; u += n_warps) {
+    const float d = dist[u2d[u]];
+    const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
+    // basis.py:110: norm * sin(freq * d_scaled) / d * envelope
+    const float b_ag = lane < R ? ea.env * (nrm_ag * sinf(f_ag * (d * inv_ag)) / d) : 0.f;
+    const float b_bg = lane < R ? eb.env * (nrm_bg * sinf(f_bg * (d * inv_bg)) / d) : 0.f;
+    float o0a = 0.f, o0b = 0.f, o1a = 0.f, o1b = 0.f, o2a = 0.f, o2b = 0.f;
+    const bool bg_live = eb.env != 0.f || !(d == d);  // warp-uniform; NaN propagates
+    for (int k = 0; k < R; ++k) {
+      const float ba = __shfl_sync(0xffffffffu, b_ag, k);
+      const float* w = s_w + k * 64;
+      o0a = fmaf(ba, w[lane], o0a);
+      o0b = fmaf(ba, w[lane + 32], o0b);
+      o1a = fmaf(ba, w[R * 64 + lane], o1a);
+      o1b = fmaf(ba, w[R * 64 + lane + 32], o1b);
+      if (bg_live) {
+        const float bb = __shfl_sync(0xffffffffu, b_bg, k);
+        o2a = fmaf(bb, w[2 * R * 64 + lane], o2a);
+        o2b = fmaf(bb, w[2 * R * 64 + lane + 32], o2b);
+      }
+    }
+    float* r0 = e0 + (size_t)u * 64;
+    float* r1 = wag + (size_t)u * 64;
+    float* r2 = wbg + (size_t)u * 64;
+    r0[lane] = o0a; r0[lane + 32] = o0b;
+    r1[lane] = o1a; r1[lane + 32] = o1b;
+    r2[lane] = o2a; r2[lane + 32] = o2b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict__ u2d, int n_bonds,
+                      const float* __restrict__ freq_ag, const float* __restrict__ freq_bg, int R, float rc_ag,
+                      float rc_bg, int p, const float* __restrict__ w3, const float* __restrict__ g_e0,
+                      const float* __restrict__ g_wag, const float* __restrict__ g_wbg,
+                      float* __restrict__ g_dist) {
+  extern __shared__ __align__(16) float s_w[];  // [3][64][R]
+  for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int kl = lane < R ? lane : 0;
+  const float f_ag = freq_ag[kl], f_bg = freq_bg[kl];
+  const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
+  for (int u = warp; u < n_bonds; u += n_warps) {
+    const float d = dist[u2d[u]];
+    const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
+    const float* q0 = g_e0 + (size_t)u * 64;
+    const float* q1 = g_wag + (size_t)u * 64;
+    const float* q2 = g_wbg + (size_t)u * 64;
+    const float a0 = q0[lane], a1 = q0[lane + 32], b0 = q1[lane], b1 = q1[lane + 32];
+    const float c0 = q2[lane], c1 = q2[lane + 32];
+    const bool bg_live = eb.env != 0.f || eb.denv != 0.f || !(d == d);
+    // lane k: gradient wrt basis function k
+    float gb_ag = 0.f, gb_bg = 0.f;
+    for (int n = 0; n < 32; ++n) {
+      const float va = __shfl_sync(0xffffffffu, a0, n), vb = __shfl_sync(0xffffffffu, b0, n);
+      const float va2 = __shfl_sync(0xffffffffu, a1, n), vb2 = __shfl_sync(0xffffffffu, b1, n);
+      gb_ag = fmaf(va, s_w[n * R + kl], gb_ag);
+      gb_ag = fmaf(vb, s_w[(64 + n) * R + kl], gb_ag);
+      gb_ag = fmaf(va2, s_w[(n + 32) * R + kl], gb_ag);
+      gb_ag = fmaf(vb2, s_w[(64 + n + 32) * R + kl], gb_ag);
+      if (bg_live) {
+        const float vc = __shfl_sync(0xffffffffu, c0, n), vc2 = __shfl_sync(0xffffffffu, c1, n);
+        gb_bg = fmaf(vc, s_w[(128 + n) * R + kl], gb_bg);
+        gb_bg = fmaf(vc2, s_w[(128 + n + 32) * R + kl], gb_bg);
+      }
+    }
+    // d basis_k / dd = norm [ (w/rc) cos(w d/rc)/d - sin(w d/rc)/d^2 ] env + norm sin(w d/rc)/d env'
+    float contrib = 0.f;
+    if (lane < R) {
+      float s, c;
+      sincosf(f_ag * (d / rc_ag), &s, &c);
+      const float raw = nrm_ag * s / d;
+      const float draw = nrm_ag * ((f_ag / rc_ag) * c / d - s / (d * d));
+      contrib = gb_ag * fmaf(draw, ea.env, raw * ea.denv);
+      if (bg_live) {
+        sincosf(f_bg * (d / rc_bg), &s, &c);
+        const float raw2 = nrm_bg * s / d;
+        const float draw2 = nrm_bg * ((f_bg / rc_bg) * c / d - s / (d * d));
+        contrib += gb_bg * fmaf(draw2, eb.env, raw2 * eb.denv);
+      }
+    }
+    contrib = sum32(contrib);
+    if (lane == 0) g_dist[u] = contrib;
+  }
+}
+
+// ---- angle basis + embedding -----------------------------------------------------
+__device__ __forceinline__ float angle_cos(const float* __restrict__ rhat, int di, int dj, float (&ri)[3],
+                                           float (&rj)[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    ri[j] = rhat[(size_t)di * 3 + j];
+    rj[j] = rhat[(size_t)dj * 3 + j];
+  }
+  // encoders.py:144: (1 - 1e-6) keeps acos away from |u| = 1
+  return fmaf(ri[2], rj[2], fmaf(ri[1], rj[1], ri[0] * rj[0])) * (1.f - 1e-6f);
+}
+
+__global__ void __launch_bounds__(256)
+angle_basis_embed_kernel(const float* __restrict__ rhat, const int32_t* __restrict__ ang_di,
+                         const int32_t* __restrict__ ang_dj, int n_angles, const float* __restrict__ freq, int nf,
+                         const float* __restrict__ wt, float* __restrict__ a0) {
+  extern __shared__ __align__(16) float s_w[];  // [2nf+1][64]
+  const int nb = 2 * nf + 1;
+  for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool is_sin = lane >= 1 && lane <= nf, is_cos = lane > nf && lane < nb;
+  const float w = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
+  const float inv_sqrt_pi = 0.5641895835477563f;
+  for (int a = warp; a < n_angles; a += n_warps) {
+    float ri[3], rj[3];
+    const float u = angle_cos(rhat, ang_di[a], ang_dj[a], ri, rj);
+    const float th = acosf(u);
+    float f = 0.f;
+    if (lane == 0) f = 0.7071067811865476f;
+    else if (is_sin) f = sinf(w * th);
+    else if (is_cos) f = cosf(w * th);
+    f *= inv_sqrt_pi;
+    float oa = 0.f, ob = 0.f;
+    for (int m = 0; m < nb; ++m) {
+      const float fm = __shfl_sync(0xffffffffu, f, m);
+      oa = fmaf(fm, s_w[m * 64 + lane], oa);
+      ob = fmaf(fm, s_w[m * 64 + lane + 32], ob);
+    }
+    a0[(size_t)a * 64 + lane] = oa;
+    a0[(size_t)a * 64 + lane + 32] = ob;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict__ ang_di,
+                       const int32_t* __restrict__ ang_dj, int n_angles, const float* __restrict__ freq, int nf,
+                       const float* __restrict__ w, const float* __restrict__ g_a0, double* __restrict__ g_rhat) {
+  extern __shared__ __align__(16) float s_w[];  // [64][2nf+1]
+  const int nb = 2 * nf + 1;
+  for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool is_sin = lane >= 1 && lane <= nf, is_cos = lane > nf && lane < nb;
+  const float wf = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
+  const int ml = lane < nb ? lane : 0;
+  const float inv_sqrt_pi = 0.5641895835477563f;
+  for (int a = warp; a < n_angles; a += n_warps) {
+    const int di = ang_di[a], dj = ang_dj[a];
+    float ri[3], rj[3];
+    const float u = angle_cos(rhat, di, dj, ri, rj);
+    const float th = acosf(u);
+    const float ga = g_a0[(size_t)a * 64 + lane], gb = g_a0[(size_t)a * 64 + lane + 32];
+    float gf = 0.f;  // lane m: dE/d f_m
+    for (int n = 0; n < 32; ++n) {
+      gf = fmaf(__shfl_sync(0xffffffffu, ga, n), s_w[n * nb + ml], gf);
+      gf = fmaf(__shfl_sync(0xffffffffu, gb, n), s_w[(n + 32) * nb + ml], gf);
+    }
+    float g_th = 0.f;
+    if (is_sin) g_th = gf * wf * cosf(wf * th);
+    else if (is_cos) g_th = -gf * wf * sinf(wf * th);
+    g_th = sum32(g_th) * inv_sqrt_pi;
+    // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
+    const float g_u = -g_th / sqrtf(1.f - u * u) * (1.f - 1e-6f);
+    if (lane < 3) atomicAdd(g_rhat + (size_t)di * 3 + lane, (double)(g_u * rj[lane]));
+    else if (lane < 6) atomicAdd(g_rhat + (size_t)dj * 3 + (lane - 3), (double)(g_u * ri[lane - 3]));
+  }
+}
+
+// ---- magmom head -------------------------------------------------------------------
+__global__ void magmom_kernel(const float* __restrict__ x, int n_atoms, const float* __restrict__ w, float b,
+                              float* __restrict__ m) {
+  const int lane = threadIdx.x & 31;
+  const int atom = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (atom >= n_atoms) return;
+  const float* row = x + (size_t)atom * 64;
+  float v = fmaf(row[lane], w[lane], row[lane + 32] * w[lane + 32]);
+  v = sum32(v);
+  if (lane == 0) m[atom] = fabsf(v + b);
+}
+
+// ---- force + virial -------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+force_virial_kernel(const float* __restrict__ rvec, const float* __restrict__ dist, const float* __restrict__ rhat,
+                    const double* __restrict__ g_rhat, const float* __restrict__ g_dist,
+                    const int32_t* __restrict__ d2u, const int32_t* __restrict__ u2d,
+                    const int32_t* __restrict__ center, const int32_t* __restrict__ nbr,
+                    const int32_t* __restrict__ owner, int n_edges, double* __restrict__ force,
+                    double* __restrict__ virial) {
+  __shared__ double s_v[8][9];
+  __shared__ int s_uniform;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int first = blockIdx.x * blockDim.x;
+  const int last = min(first + (int)blockDim.x, n_edges) - 1;
+  if (threadIdx.x == 0) s_uniform = owner[center[first]] == owner[center[last]];
+  __syncthreads();
+  const bool uniform = s_uniform != 0;
+  double g[3] = {0.0, 0.0, 0.0}, r[3] = {0.0, 0.0, 0.0};
+  int graph = -1;
+  if (e < n_edges) {
+    const int c = center[e], n = nbr[e], u = d2u[e];
+    graph = owner[c];
+    double rh[3], gr[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      rh[j] = (double)rhat[(size_t)e * 3 + j];
+      gr[j] = g_rhat[(size_t)e * 3 + j];
+      r[j] = (double)rvec[(size_t)e * 3 + j];
+    }
+    const double dot = rh[0] * gr[0] + rh[1] * gr[1] + rh[2] * gr[2];
+    const double inv_d = 1.0 / (double)dist[e];
+    const double gd = (u2d[u] == e) ? (double)g_dist[u] : 0.0;  // d_u is taken from its representative edge only
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      g[j] = (gr[j] - rh[j] * dot) * inv_d + gd * rh[j];
+      atomicAdd(force + (size_t)c * 3 + j, -g[j]);
+      atomicAdd(force + (size_t)n * 3 + j, g[j]);
+    }
+  }
+  if (uniform) {
+    double v[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v[i * 3 + j] = sum32d(r[i] * g[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s_v[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      double t = 0.0;
+      for (int w8 = 0; w8 < 8; ++w8) t += s_v[w8][threadIdx.x];
+      atomicAdd(virial + (size_t)owner[center[first]] * 9 + threadIdx.x, t);
+    }
+  } else if (graph >= 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) atomicAdd(virial + (size_t)graph * 9 + i * 3 + j, r[i] * g[j]);
+  }
+}
+
+inline int warp_grid(int n_items, int threads = 256) {
+  const int warps_per_block = threads / 32;
+  const int need = (n_items + warps_per_block - 1) / warps_per_block;
+  return max(1, min(need, sm_count() * 8));
+}
+
+}  // namespace
+}  // namespace chg
+
+using namespace chg;
+
+extern "C" int chg_embed_atoms(const int32_t* z, const float* emb, int32_t n_atoms, float* x, void* stream) {
+  CHG_CHECK_ARG(n_atoms >= 0, "negative size");
+  if (n_atoms == 0) return CHG_OK;
+  CHG_CHECK_ARG(z && emb && x, "null pointer");
+  const int total = n_atoms * 16;
+  embed_atoms_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(z, emb, n_atoms, x);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_edge_geometry(const float* frac, const float* lattice, const int32_t* atom_owner,
+                                 const int32_t* center, const int32_t* nbr, const float* image, int32_t n_edges,
+                                 float* rvec, float* dist, float* rhat, void* stream) {
+  CHG_CHECK_ARG(n_edges >= 0, "negative size");
+  if (n_edges == 0) return CHG_OK;
+  CHG_CHECK_ARG(frac && lattice && atom_owner && center && nbr && image && rvec && dist && rhat, "null pointer");
+  edge_geometry_kernel<<<(n_edges + 255) / 256, 256, 0, as_stream(stream)>>>(frac, lattice, atom_owner, center, nbr,
+                                                                             image, n_edges, rvec, dist, rhat);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_bond_basis_embed(const float* dist, const int32_t* u2d, int32_t n_bonds, const float* freq_ag,
+                                    const float* freq_bg, int32_t n_radial, float rc_ag, float rc_bg, int32_t p,
+                                    const float* w3t, float* e0, float* wag, float* wbg, void* stream) {
+  CHG_CHECK_ARG(n_bonds >= 0, "negative size");
+  CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
+  if (n_bonds == 0) return CHG_OK;
+  CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3t && e0 && wag && wbg, "null pointer");
+  const int smem = 3 * n_radial * 64 * 4;
+  bond_basis_embed_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3t, e0, wag, wbg);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_bond_basis_bwd(const float* dist, const int32_t* u2d, int32_t n_bonds, const float* freq_ag,
+                                  const float* freq_bg, int32_t n_radial, float rc_ag, float rc_bg, int32_t p,
+                                  const float* w3, const float* g_e0, const float* g_wag, const float* g_wbg,
+                                  float* g_dist, void* stream) {
+  CHG_CHECK_ARG(n_bonds >= 0, "negative size");
+  CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
+  if (n_bonds == 0) return CHG_OK;
+  CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3 && g_e0 && g_wag && g_wbg && g_dist, "null pointer");
+  const int smem = 3 * n_radial * 64 * 4;
+  bond_basis_bwd_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_angle_basis_embed(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
+                                     int32_t n_angles, const float* freq, int32_t n_freq, const float* wt, float* a0,
+                                     void* stream) {
+  CHG_CHECK_ARG(n_angles >= 0, "negative size");
+  CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
+  if (n_angles == 0) return CHG_OK;
+  CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && wt && a0, "null pointer");
+  const int smem = (2 * n_freq + 1) * 64 * 4;
+  angle_basis_embed_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles,
+                                                                                  freq, n_freq, wt, a0);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj, int32_t n_angles,
+                                   const float* freq, int32_t n_freq, const float* w, const float* g_a0,
+                                   double* g_rhat, void* stream) {
+  CHG_CHECK_ARG(n_angles >= 0, "negative size");
+  CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
+  if (n_angles == 0) return CHG_OK;
+  CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && w && g_a0 && g_rhat, "null pointer");
+  const int smem = (2 * n_freq + 1) * 64 * 4;
+  angle_basis_bwd_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles, freq,
+                                                                                n_freq, w, g_a0, g_rhat);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_magmom(const float* x, int32_t n_atoms, const float* w, float b, float* m, void* stream) {
+  CHG_CHECK_ARG(n_atoms >= 0, "negative size");
+  if (n_atoms == 0) return CHG_OK;
+  CHG_CHECK_ARG(x && w && m, "null pointer");
+  const int blocks = (n_atoms * 32 + 255) / 256;
+  magmom_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, n_atoms, w, b, m);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_force_virial(const float* rvec, const float* dist, const float* rhat, const double* g_rhat,
+                                const float* g_dist, const int32_t* d2u, const int32_t* u2d, const int32_t* center,
+                                const int32_t* nbr, const int32_t* atom_owner, int32_t n_edges, double* force,
+                                double* virial, void* stream) {
+  CHG_CHECK_ARG(n_edges >= 0, "negative size");
+  if (n_edges == 0) return CHG_OK;
+  CHG_CHECK_ARG(rvec && dist && rhat && g_rhat && g_dist && d2u && u2d && center && nbr && atom_owner && force &&
+                    virial,
+                "null pointer");
+  force_virial_kernel<<<(n_edges + 255) / 256, 256, 0, as_stream(stream)>>>(
+      rvec, dist, rhat, g_rhat, g_dist, d2u, u2d, center, nbr, atom_owner, n_edges, force, virial);
+  CHG_LAUNCH_END();
+}

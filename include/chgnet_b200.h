@@ -104,7 +104,7 @@ int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag,
  * out[r] (+)= sum_{k in [ptr[r],ptr[r+1])} data[perm ? perm[k] : k], width 64|128 */
 int chg_segment_sum(const float* data, int32_t width, const int32_t* perm,
                     const int32_t* ptr, int32_t n_rows, int32_t accumulate, float* out,
-                    void* stream);
+                    int32_t out_ld /* row stride of out, in floats */, void* stream);
 
 /* ---- K5: BondConv message (layers.py:238-249)
  * pre = pij[i][0:128] + pij[j][128:256] + px[c] + ang[a] @ w1a_t;

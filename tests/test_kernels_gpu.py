@@ -1,0 +1,113 @@
+"""-m gpu: every C-ABI kernel, called through ctypes with the exact arguments of a real
+forward + reverse pass, against its torch specification (oracle/kernel_specs.py)."""
+import numpy as np
+import pytest
+import torch
+
+from chgnet_b200 import graphgen
+from chgnet_b200.batch import build_batch
+from chgnet_b200.engine import Engine
+from chgnet_b200.weights import pack_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _record(weights, graphs, **kw):
+    from kernel_replay import RecordingKernels
+
+    sd = {k: torch.as_tensor(v) for k, v in weights.items()}
+    pw = pack_weights(sd, None, device="cpu")
+    rec = RecordingKernels()
+    Engine(pw, rec).run(build_batch(graphs, "cpu"), **kw)
+    return rec.calls
+
+
+def _close(name, idx, got, want):
+    got, want = got.double().cpu(), want.double()
+    scale = float(want.abs().max()) if want.numel() else 1.0
+    err = float((got - want).abs().max()) if want.numel() else 0.0
+    # fp32 kernels vs fp32 spec: different summation order only
+    tol = 2e-5 * max(scale, 1.0) + 1e-6
+    assert err <= tol, f"{name} out[{idx}]: max err {err:.3e} > {tol:.3e} (scale {scale:.3e})"
+    return err
+
+
+@pytest.fixture(scope="module")
+def recorded(weights030):
+    graphs = graphgen.random_graphs(3, 10, 16, 9300)
+    return _record(weights030, graphs, need_grad=True, need_magmom=True, need_atom_fea=True, need_crystal_fea=True)
+
+
+def test_every_kernel_matches_its_spec(recorded):
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    seen = {}
+    for name, snap, outs in recorded:
+        args = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
+        getattr(K, name)(*args)
+        torch.cuda.synchronize()
+        for idx, want in outs.items():
+            err = _close(name, idx, args[idx], want)
+            seen[name] = max(seen.get(name, 0.0), err)
+    assert set(seen) == set(__import__("kernel_replay").OUT_ARGS), sorted(seen)
+    print({k: f"{v:.2e}" for k, v in seen.items()})
+
+
+def test_kernels_without_layernorm_and_small_basis(weights030):
+    """v0.2.0-shaped path: no LayerNorm, 9 radial / 9 angular functions, mlp_out bias."""
+    from chgnet_b200._lib import CudaKernels
+    from oracle import chgnet_oracle as orc
+
+    args = dict(num_radial=9, num_angular=9, gMLP_norm=None, readout_norm=None, mlp_out_bias=True, cutoff_coeff=5)
+    w = orc.random_weights(3, args)
+    w = {k: v for k, v in w.items() if k != "mlp.layers.4.weight" and k != "mlp.layers.4.bias"}
+    w["mlp.layers.5.weight"], w["mlp.layers.5.bias"] = w.pop("mlp.layers.7.weight"), w.pop("mlp.layers.7.bias")
+    graphs = graphgen.random_graphs(2, 8, 12, 9400, atom_graph_cutoff=5.0)
+    sd = {k: torch.as_tensor(v) for k, v in w.items()}
+    from kernel_replay import RecordingKernels
+
+    pw = pack_weights(sd, dict(atom_graph_cutoff=5.0, cutoff_coeff=5), device="cpu")
+    assert not pw.hp.use_ln and pw.hp.n_readout_hidden == 2 and pw.hp.num_radial == 9
+    rec = RecordingKernels()
+    Engine(pw, rec).run(build_batch(graphs, "cpu"), need_grad=True, need_magmom=True)
+    K = CudaKernels()
+    for name, snap, outs in rec.calls:
+        cargs = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
+        getattr(K, name)(*cargs)
+        for idx, want in outs.items():
+            _close(name, idx, cargs[idx], want)
+
+
+def test_segment_sum_strided_output_and_determinism():
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    g = torch.Generator().manual_seed(0)
+    n_rows, n_items = 1000, 50000
+    owners = torch.sort(torch.randint(0, n_rows, (n_items,), generator=g)).values
+    ptr = torch.searchsorted(owners, torch.arange(n_rows + 1)).int().cuda()
+    perm = torch.randperm(n_items, generator=g).int().cuda()
+    for width in (64, 128):
+        data = torch.randn(n_items, width, generator=g).cuda()
+        out = torch.zeros(n_rows, 256, device="cuda")
+        K.segment_sum(data, perm, ptr, 0, out[:, 64 : 64 + width])
+        want = torch.zeros(n_rows, width, dtype=torch.float64).index_add_(0, owners, data[perm.long()].double().cpu())
+        assert torch.allclose(out[:, 64 : 64 + width].double().cpu(), want, atol=1e-4)
+        assert float(out[:, :64].abs().max()) == 0.0 and float(out[:, 64 + width :].abs().max()) == 0.0
+        again = torch.zeros(n_rows, 256, device="cuda")
+        K.segment_sum(data, perm, ptr, 0, again[:, 64 : 64 + width])
+        assert torch.equal(out, again)  # bitwise reproducible
+        K.segment_sum(data, perm, ptr, 1, again[:, 64 : 64 + width])
+        assert torch.allclose(again[:, 64 : 64 + width], 2 * out[:, 64 : 64 + width], rtol=1e-6)
+
+
+def test_bad_arguments_are_reported():
+    from chgnet_b200._lib import ChgnetB200Error, CudaKernels
+
+    K = CudaKernels()
+    x = torch.zeros(4, 96, device="cuda")
+    with pytest.raises(ChgnetB200Error, match="k must be"):
+        K.linear(x, torch.zeros(96, 64, device="cuda"), None, None, torch.zeros(4, 64, device="cuda"))
+    with pytest.raises(ChgnetB200Error):
+        K.linear(torch.zeros(4, 64), torch.zeros(64, 64), None, None, torch.zeros(4, 64))  # CPU tensors

@@ -1,0 +1,153 @@
+"""-m gpu: end-to-end parity of chgnet_b200.CHGNet (CUDA kernels through the C ABI)
+against the committed golden vectors of the live reference, the fp64 oracle, and the
+invariants the reference's own tests pin (reference tests/test_model.py:60-219)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from chgnet_b200 import graphgen
+
+pytestmark = pytest.mark.gpu
+
+# north-star tolerances (BASELINE.json): 1e-4 eV/atom, 1e-3 eV/A, 1e-3 GPa (and 1e-3 muB)
+TOL = {"e": 1e-4, "f": 1e-3, "s": 1e-3, "m": 1e-3}
+
+
+@pytest.fixture(scope="module")
+def model():
+    from chgnet_b200.model import CHGNet
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz")
+    return CHGNet.from_file(path, version="0.3.0").to("cuda")
+
+
+def _maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+def test_limno2_known_answers(model, limno2_graph, golden):
+    out = model.predict_graph(limno2_graph, return_site_energies=True, return_atom_feas=True,
+                              return_crystal_feas=True)
+    assert sorted(out) == ["atom_fea", "crystal_fea", *"efms", "site_energies"]
+    # published known answers (reference tests/test_model.py:68-119)
+    assert out["e"] == pytest.approx(-7.36769, rel=1e-4, abs=1e-4)
+    assert out["e"].shape == () and out["f"].shape == (8, 3) and out["s"].shape == (3, 3)
+    assert out["crystal_fea"].mean() == pytest.approx(0.26999, rel=1e-4, abs=1e-4)
+    assert out["atom_fea"].mean() == pytest.approx(-0.09668, rel=1e-4, abs=1e-4)
+    assert out["crystal_fea"].shape == (64,) and out["atom_fea"].shape == (8, 64)
+    assert np.sum(out["site_energies"]) / 8 == pytest.approx(out["e"], rel=1e-4, abs=1e-6)
+    # live-reference fp32 outputs and fp64 truth, at the north-star tolerances
+    for tag in ("ref32", "oracle64"):
+        for k, tol in TOL.items():
+            err = _maxabs(out[k], golden[f"limno2.{tag}.{k}"])
+            assert err < tol, (tag, k, err)
+        assert _maxabs(out["site_energies"], golden[f"limno2.{tag}.site_energies"]) < 1e-4
+    print({k: f"{_maxabs(out[k], golden[f'limno2.oracle64.{k}']):.2e}" for k in TOL})
+
+
+def test_random_batch_vs_reference_golden(model, golden):
+    graphs = graphgen.random_graphs(4, 12, 20, 7000)
+    preds = model.predict_graph(graphs, task="efsm", batch_size=4)
+    assert isinstance(preds, list) and len(preds) == 4
+    for i, p in enumerate(preds):
+        for tag in ("ref32", "oracle64"):
+            for k, tol in TOL.items():
+                assert _maxabs(p[k], golden[f"rand4.{i}.{tag}.{k}"]) < tol, (i, tag, k)
+
+
+def test_batched_equals_single_and_batch_size(model):
+    graphs = graphgen.random_graphs(5, 8, 14, 7100)
+    together = model.predict_graph(graphs, batch_size=16)
+    chunked = model.predict_graph(graphs, batch_size=2)
+    for g, a, b in zip(graphs, together, chunked):
+        single = model.predict_graph(g)
+        for k, tol in TOL.items():
+            assert _maxabs(a[k], single[k]) < tol * 0.1 and _maxabs(a[k], b[k]) < tol * 0.1
+
+
+def test_against_fp64_oracle_on_larger_batch(model, weights030):
+    from oracle import chgnet_oracle as orc
+
+    graphs = graphgen.random_graphs(6, 24, 40, 7200)
+    preds = model.predict_graph(graphs, task="efsm", batch_size=6)
+    ref = orc.predict_graph(weights030, graphs, "efsm", batch_size=6, dtype=torch.float64)
+    worst = {k: max(_maxabs(p[k], r[k]) for p, r in zip(preds, ref)) for k in TOL}
+    print("max |cuda - oracle64|:", {k: f"{v:.2e}" for k, v in worst.items()})
+    for k, tol in TOL.items():
+        assert worst[k] < tol, (k, worst[k])
+
+
+def test_rotation_and_supercell_invariance(model):
+    """reference tests/test_model.py:122-191"""
+    z, frac, lat = graphgen.random_structure(10, 7300)
+    base = model.predict_structure((z, frac, lat))
+    th = np.deg2rad(30.0)
+    axis = np.array([-2.0, 3.0, 1.0]) / np.linalg.norm([-2.0, 3.0, 1.0])
+    Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    Rm = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    rot = model.predict_structure((z, frac, lat @ Rm.T))
+    assert rot["e"] == pytest.approx(base["e"], abs=1e-4)
+    assert _maxabs(rot["f"], base["f"] @ Rm.T) < 1e-3
+    assert _maxabs(rot["s"], Rm @ base["s"] @ Rm.T) < 1e-3
+    assert _maxabs(rot["m"], base["m"]) < 1e-3
+    # 2x1x1 supercell: same energy per atom, forces tiled
+    frac2 = np.concatenate([frac / [2, 1, 1], frac / [2, 1, 1] + [0.5, 0, 0]])
+    sup = model.predict_structure((np.tile(z, 2), frac2, lat * np.array([[2], [1], [1]])))
+    assert sup["e"] == pytest.approx(base["e"], abs=1e-4)
+    assert _maxabs(sup["f"], np.tile(base["f"], (2, 1))) < 1e-3
+    assert _maxabs(sup["s"], base["s"]) < 1e-3
+
+
+def test_tasks_keys_and_errors(model, limno2_graph):
+    out = model([limno2_graph])
+    assert list(out) == ["atoms_per_graph", "e"]  # reference tests/test_model.py:47
+    assert out["atoms_per_graph"].shape == (1,) and out["e"] < 0
+    for task, keys in (("e", "e"), ("ef", "ef"), ("em", "em"), ("efs", "efs"), ("efsm", "efms")):
+        assert sorted(model.predict_graph(limno2_graph, task=task)) == sorted(keys)
+    with pytest.raises(ValueError, match="Invalid task='abc'"):
+        model.predict_graph(limno2_graph, task="abc")
+    with pytest.raises(TypeError, match="must be CrystalGraph or list of CrystalGraphs"):
+        model.predict_graph(3)
+
+
+def test_isolated_atoms_and_empty_bond_graph(model, weights030):
+    from oracle import chgnet_oracle as orc
+
+    g_far = graphgen.make_crystal_graph([3, 8], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 5.5)
+    g_iso = graphgen.make_crystal_graph([1, 1], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 20.0)
+    assert len(g_far.bond_graph) == 0 and len(g_iso.atom_graph) == 0
+    for graphs in ([g_far], [g_iso], [g_iso, g_far], graphgen.random_graphs(1, 9, 9, 7400) + [g_iso]):
+        preds = model.predict_graph(graphs, task="efsm")
+        ref = orc.predict_graph(weights030, graphs, "efsm", dtype=torch.float64)
+        for p, r in zip(preds, ref):
+            for k, tol in TOL.items():
+                assert _maxabs(p[k], r[k]) < tol
+    g10 = graphgen.make_crystal_graph([1, 1], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 10.0)
+    e10, e20 = model.predict_graph(g10)["e"], model.predict_graph(g_iso)["e"]
+    assert e10 == pytest.approx(e20, rel=1e-5, abs=1e-5)  # reference tests/test_model.py:210-219
+
+
+def test_state_dict_round_trip(model):
+    from chgnet_b200.model import CHGNet
+
+    dct = model.as_dict()
+    assert {*dct} == {"model_args", "state_dict"} and len(dct["state_dict"]) == 136
+    clone = CHGNet.from_dict(dct).to("cuda")
+    assert clone.n_params == 412525
+    g = graphgen.random_graphs(1, 8, 8, 7500)[0]
+    a, b = model.predict_graph(g), clone.predict_graph(g)
+    assert all(np.array_equal(a[k], b[k]) for k in "efsm")
+
+
+def test_large_cell_properties(model):
+    """Size-independent checks at a config-4-like size (LiMnO2 6x4x3 = 576 atoms):
+    net force ~ 0 (translation invariance), stress symmetric, results reproducible."""
+    z, frac, lat = graphgen.limno2_structure((6, 4, 3), 0.02, 4000)
+    g = graphgen.make_crystal_graph(z, frac, lat)
+    a = model.predict_graph(g)
+    b = model.predict_graph(g)
+    assert np.abs(a["f"].sum(axis=0)).max() < 1e-3
+    assert _maxabs(a["s"], a["s"].T) < 1e-3
+    assert np.array_equal(a["e"], b["e"]) and _maxabs(a["f"], b["f"]) < 1e-5
