@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the CHGNet hot path (E + F + sigma) on B200.
+
+Contract (see task statement): ``python bench.py --gpus N --steps K --warmup W`` prints ONE
+JSON line.  A "step" is one pass of the hot path (forward + the force/stress reverse pass)
+over one batch of synthetic CrystalGraphs.
+
+Workloads (BASELINE.json `configs`):
+  c2  (default) batch = 64 random periodic cells, 40..60 atoms, cutoffs 6 A / 3 A   [configs[1]]
+  c3  batch = 256 random cells, 20..40 atoms                                       [configs[2]]
+  c4  one 10,000-atom LiMnO2 supercell (10x5x25), sigma = 0.02 A displacements      [configs[3]]
+  c1  the 8-atom LiMnO2 cell                                                       [configs[0]]
+
+value      structures/s of the kernel path, batch descriptor already resident in HBM
+e2e        the same through ``CHGNet.predict_graph`` from host CrystalGraphs (host packing,
+           H2D, CSR build, kernels, D2H numpy) — the user-facing call
+roofline   AtomConv scatter-reduce kernel (chg_segment_sum over center-sorted messages),
+           timed alone with CUDA events at this workload's size, L2 flushed between launches
+cpu_baseline / --impl reference
+           the oracle port of the reference's torch CPU path (oracle/chgnet_oracle.py) on
+           the host cores, on a bounded sample of the same workload
+
+Multi-GPU: one process per GPU (torchrun), graphs sharded by rank, no device-path
+collective (inference); time = max over ranks; weak scaling (each rank owns one batch).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WEIGHTS = os.path.join(ROOT, "tests", "golden", "chgnet_0.3.0_weights.npz")
+L2_FLUSH_BYTES = 256 << 20
+
+
+def make_workload(name: str, rank: int):
+    from chgnet_b200 import graphgen
+
+    if name == "c1":
+        z, frac, lat = graphgen.limno2_structure()
+        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="mp-18767")], "LiMnO2 mp-18767, 8 atoms"
+    if name == "c2":
+        return graphgen.random_graphs(64, 40, 60, 1000 + 100 * rank), "batch=64 random periodic cells, 40..60 atoms, rho=0.10/A^3, cutoffs 6/3 A"
+    if name == "c3":
+        return graphgen.random_graphs(256, 20, 40, 2000 + 1000 * rank), "batch=256 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A"
+    if name == "c4":
+        z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000 + rank)
+        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="LiMnO2-10x5x25")], "LiMnO2 10x5x25 supercell, 10,000 atoms, sigma=0.02 A"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def counts(graphs):
+    n = sum(int(g.atomic_number.shape[0]) for g in graphs)
+    ed = sum(int(g.atom_graph.reshape(-1, 2).shape[0]) for g in graphs)
+    a = sum(int(g.bond_graph.reshape(-1, 5).shape[0]) for g in graphs)
+    return {"graphs": len(graphs), "atoms": n, "directed_edges": ed, "undirected_bonds": ed // 2, "angles": a}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int) -> None:
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.sm_max = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self) -> None:
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int) -> None:
+    """--impl reference: the reference's CPU path (oracle port), bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import chgnet_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    graphs, desc = make_workload(args.workload, 0)
+    sample = graphs[: max(1, min(len(graphs), args.cpu_sample))]
+    if args.workload == "c4":
+        from chgnet_b200 import graphgen
+
+        z, frac, lat = graphgen.limno2_structure((5, 4, 3), 0.02, 4000)
+        sample = [graphgen.make_crystal_graph(z, frac, lat)]
+        desc_s = "LiMnO2 5x4x3 supercell (480 atoms) — largest cell timed on the CPU; value scaled by atoms"
+    else:
+        desc_s = f"first {len(sample)} graphs of the batch per step"
+    w = orc.load_weights_npz(WEIGHTS)
+    for _ in range(args.warmup):
+        orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+    dt = (time.perf_counter() - t0) / args.steps
+    c = counts(sample)
+    value = c["graphs"] / dt
+    if args.workload == "c4":
+        value = (c["atoms"] / dt) / counts(graphs)["atoms"]  # 10k-atom structures/s at the same atoms/s
+    line = {
+        "impl": "reference", "metric": "structures_per_sec_EFS", "value": value, "unit": "structures/s",
+        "atoms_per_s": c["atoms"] / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "task": "efs"},
+        "cpu_baseline": {"value": value, "unit": "structures/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": desc_s},
+        "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def time_scatter_kernel(K, batch, n_iter: int = 20):
+    """AtomConv scatter-reduce alone: CUDA events on the launching stream, L2 flushed."""
+    dev = batch.z.device
+    msg = torch.randn(batch.n_edges, 64, device=dev)
+    out = torch.empty(batch.n_atoms, 64, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES // 4, device=dev)
+    for _ in range(3):
+        K.segment_sum(msg, None, batch.ptr_c, 0, out)
+    total = 0.0
+    for _ in range(n_iter):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        K.segment_sum(msg, None, batch.ptr_c, 0, out)
+        e.record()
+        e.synchronize()
+        total += s.elapsed_time(e)
+    ms = total / n_iter
+    alg_bytes = 256 * batch.n_edges + 256 * batch.n_atoms + 4 * (batch.n_atoms + 1)
+    return ms, alg_bytes
+
+
+class EventKernels:
+    """Wraps the kernel binding with per-call CUDA events (used OUTSIDE the timed region)."""
+
+    def __init__(self, inner) -> None:
+        self._inner, self.records = inner, []
+
+    def __getattr__(self, name):
+        attr = getattr(self._inner, name)
+        if not callable(attr) or name.startswith("_"):
+            return attr
+
+        def timed(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            attr(*a)
+            e.record()
+            self.records.append((name, s, e))
+
+        return timed
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg: dict[str, list] = {}
+        for name, s, e in self.records:
+            agg.setdefault(name, [0.0, 0])
+            agg[name][0] += s.elapsed_time(e)
+            agg[name][1] += 1
+        tot = sum(v[0] for v in agg.values()) or 1.0
+        return {k: {"ms": round(v[0], 4), "calls": v[1], "share": round(v[0] / tot, 4)}
+                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+    import torch.distributed as dist
+
+    from chgnet_b200.batch import build_batch
+    from chgnet_b200.engine import EV_A3_TO_GPA, Engine
+    from chgnet_b200.model import CHGNet
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev).eval()
+    graphs, desc = make_workload(args.workload, rank)
+    c = counts(graphs)
+    engine = model._get_engine()
+    K = engine.K
+    flush = torch.empty(L2_FLUSH_BYTES // 4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel path, inputs resident in HBM ----------------
+    batch = build_batch(graphs, dev, with_reverse=True)
+
+    def step_resident():
+        out = engine.run(batch, need_grad=True)
+        scale = EV_A3_TO_GPA / batch.volume.to(torch.float64)
+        stress = (out.virial.view(-1, 3, 3) * scale[:, None, None]).to(torch.float32)
+        return out.energy, out.force.to(torch.float32), stress
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = K.launches
+    elapsed_ms = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step_resident()
+        e.record()
+        e.synchronize()
+        elapsed_ms += s.elapsed_time(e)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = K.launches - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+
+    # ---------------- end to end through the public API ----------------
+    def step_e2e():
+        return model.predict_graph(graphs, task="efs", batch_size=len(graphs))
+
+    for _ in range(2):
+        preds = step_e2e()
+    d2h = sum(int(v.nbytes) for p in preds for v in p.values())
+    h2d = int(model.last_batch.h2d_bytes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(t.item()) / args.steps
+
+    if rank != 0:
+        return
+    # ---------------- roofline of the AtomConv scatter kernel ----------------
+    peaks, peak_kind = measured_peaks()
+    sc_ms, sc_bytes = time_scatter_kernel(K, batch)
+    achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
+    roofline = {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm",
+                "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth",
+                "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+                "us_per_launch": round(sc_ms * 1e3, 2), "algorithmic_bytes": sc_bytes,
+                "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+    # per-kernel shares (own events, outside the timed region)
+    ek = EventKernels(K)
+    Engine(engine.pw, ek).run(batch, need_grad=True)
+    shares = ek.table()
+
+    # ---------------- CPU baseline: oracle port on the host cores ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import chgnet_oracle as orc
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        w = orc.load_weights_npz(WEIGHTS)
+        if args.workload == "c4":
+            from chgnet_b200 import graphgen
+
+            z, frac, lat = graphgen.limno2_structure((5, 4, 3), 0.02, 4000)
+            sample = [graphgen.make_crystal_graph(z, frac, lat)]
+            sdesc = "LiMnO2 5x4x3 (480 atoms), 1 warm-up + 2 timed; structures/s scaled by atoms to the 10,000-atom cell"
+        else:
+            sample = graphs[: min(len(graphs), args.cpu_sample)]
+            sdesc = f"first {len(sample)} graphs of the batch, 1 warm-up + 2 timed predict_graph(task='efs') calls"
+        orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+        t0 = time.perf_counter()
+        for _ in range(2):
+            orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+        dt = (time.perf_counter() - t0) / 2
+        cs = counts(sample)
+        v = cs["graphs"] / dt if args.workload != "c4" else (cs["atoms"] / dt) / c["atoms"]
+        cpu = {"value": v, "unit": "structures/s", "atoms_per_s": cs["atoms"] / dt, "cores": torch.get_num_threads(),
+               "kind": "port", "sample": sdesc}
+
+    total_graphs = c["graphs"] * world
+    value = total_graphs / (ms_per_step * 1e-3)
+    line = {
+        "metric": "structures_per_sec_EFS", "value": value, "unit": "structures/s",
+        "atoms_per_s": c["atoms"] * world / (ms_per_step * 1e-3),
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "task": "efs", "per_gpu": c, "weights": "CHGNet 0.3.0",
+                   "l2": "256 MiB buffer written between timed iterations", "parallelism": f"graph-sharded x{world}"},
+        "e2e": {"value": total_graphs / (e2e_ms_per_step * 1e-3), "unit": "structures/s",
+                "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "CHGNet.predict_graph(list[CrystalGraph] on host, task='efs')"},
+        "gpu_launches": int(launches), "wall_ms_timed_region": wall_ms,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernel_shares": shares,
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CHGNET_BENCH_WORKLOAD", "c2"), choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU implementation")
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
