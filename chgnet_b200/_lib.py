@@ -26,10 +26,12 @@ SIGNATURES: dict[str, list] = {
     "chg_bond_basis_bwd": [P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
     "chg_angle_basis_embed": [P, P, P, I, P, I, P, P, P],
     "chg_angle_basis_bwd": [P, P, P, I, P, I, P, P, P, P],
-    "chg_linear": [P, I, I, P, P, P, I, P, P],
+    "chg_linear": [P, P, I, I, P, P, P, P, I, P, P],
+    "chg_gather_rows": [P, P, I, I, P, P],
+    "chg_scatter_rows": [P, P, I, I, P, P],
     "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P],
     "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
-    "chg_segment_sum": [P, I, P, P, I, I, P, I, P],
+    "chg_segment_sum": [P, I, P, P, I, I, I, P, I, P],
     "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P],
     "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
     "chg_angle_update_fwd": [P, P, P, P, P, P, I, P, P, P, P, P],
@@ -138,9 +140,19 @@ class CudaKernels:
         self._call("chg_angle_basis_bwd", _p(rhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
                    freq.shape[0], _p(w), _p(g_a0), _p(g_rhat))
 
-    def linear(self, x, wt, bias, residual, y):
-        self._chk(x, wt, bias, residual, y)
-        self._call("chg_linear", _p(x), x.shape[0], x.shape[1], _p(wt), _p(bias), _p(residual), wt.shape[1], _p(y))
+    def linear(self, x, wt, bias, residual, y, x_rows=None, y_rows=None):
+        self._chk(x, wt, bias, residual, y, x_rows, y_rows)
+        m = x_rows.shape[0] if x_rows is not None else x.shape[0]
+        self._call("chg_linear", _p(x), _p(x_rows), m, x.shape[1], _p(wt), _p(bias), _p(residual), _p(y_rows),
+                   wt.shape[1], _p(y))
+
+    def gather_rows(self, src, idx, dst):
+        self._chk(src, idx, dst)
+        self._call("chg_gather_rows", _p(src), _p(idx), idx.shape[0], src.shape[1], _p(dst))
+
+    def scatter_rows(self, src, idx, dst):
+        self._chk(src, idx, dst)
+        self._call("chg_scatter_rows", _p(src), _p(idx), idx.shape[0], src.shape[1], _p(dst))
 
     def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p):
         self._chk(pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p)
@@ -156,7 +168,8 @@ class CudaKernels:
         self._chk(data, perm, ptr)
         if not out.is_cuda or out.stride(1) != 1:
             raise ChgnetB200Error("segment_sum output must be a CUDA tensor with unit column stride")
-        self._call("chg_segment_sum", _p(data), data.shape[1], _p(perm), _p(ptr), ptr.shape[0] - 1,
+        n_items = data.shape[0] if perm is None else perm.shape[0]
+        self._call("chg_segment_sum", _p(data), data.shape[1], _p(perm), _p(ptr), ptr.shape[0] - 1, n_items,
                    int(accumulate), _p(out), out.stride(0))
 
     def bond_conv_fwd(self, pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p):

@@ -16,6 +16,9 @@ Segment structures (all int32, device):
   ptr_i   [Eu+1]  angles grouped by bond i (angles are i-sorted)
   perm_j  [A], ptr_j [Eu+1]     angles grouped by bond j
   perm_x  [A], ptr_x [N+1]      angles grouped by center atom
+  short_ids [Es], ang_is/ang_js [A], ptr_is, perm_js/ptr_js [Es+1]
+                  the same angle groupings in the COMPACT index space of the bonds that
+                  appear in the bond graph (about 1/8 of all bonds at 6 A / 3 A cutoffs)
 """
 from __future__ import annotations
 
@@ -63,6 +66,15 @@ class DeviceBatch:
     ptr_j: Tensor
     perm_x: Tensor
     ptr_x: Tensor
+    # bond-graph bonds ("short" bonds, d < bond_graph_cutoff): the only bonds BondConv /
+    # AngleUpdate read or write.  Angles address them through compact slots.
+    n_short: int = 0
+    short_ids: Tensor | None = None  # [Es] undirected bond index of each slot (ascending)
+    ang_is: Tensor | None = None  # [A] slot of bond i   (non-decreasing)
+    ang_js: Tensor | None = None  # [A] slot of bond j
+    ptr_is: Tensor | None = None  # [Es+1] angles by slot i
+    perm_js: Tensor | None = None  # [A], ptr_js [Es+1]: angles by slot j
+    ptr_js: Tensor | None = None
     h2d_bytes: int = 0
 
 
@@ -89,7 +101,8 @@ def _group(keys: Tensor, n_rows: int) -> tuple[Tensor, Tensor]:
     return perm.to(torch.int32), _csr_ptr(sk, n_rows)
 
 
-def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True) -> DeviceBatch:
+def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True,
+                compact_bonds: bool = True) -> DeviceBatch:
     device = torch.device(device)
     B = len(graphs)
     n_at = [int(g.atomic_number.shape[0]) for g in graphs]
@@ -207,6 +220,24 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         ptr_n = ptr_x = torch.zeros(N + 1, **i32)
         ptr_u = ptr_j = torch.zeros(Eu + 1, **i32)
 
+    # ---- compact index space of the bond-graph bonds (one host sync: the slot count) ----
+    if A and compact_bonds:
+        mask = torch.zeros(Eu, dtype=torch.int32, device=device)
+        mask[ang_i.long()] = 1
+        mask[ang_j.long()] = 1
+        slot = torch.cumsum(mask, 0, dtype=torch.int32) - 1
+        short_ids = torch.nonzero(mask).view(-1).to(torch.int32)  # syncs; ascending
+        ang_is, ang_js = slot[ang_i.long()], slot[ang_j.long()]
+    else:  # identity "compaction": every bond has a slot
+        short_ids = torch.arange(Eu, **i32)
+        ang_is, ang_js = ang_i, ang_j
+    Es = int(short_ids.shape[0])
+    ptr_is = _csr_ptr(ang_is, Es)
+    if with_reverse:
+        perm_js, ptr_js = _group(ang_js, Es)
+    else:
+        perm_js, ptr_js = torch.zeros(0, **i32), torch.zeros(Es + 1, **i32)
+
     lattice = fview("lattice").view(B, 9)
     L = lattice.view(B, 3, 3)
     volume = (L[:, 0] * torch.linalg.cross(L[:, 1], L[:, 2])).sum(dim=1)  # model.py:834-836
@@ -218,7 +249,9 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         center=c(center), nbr=c(nbr), image=c(image), d2u=c(d2u), u2d=c(u2d),
         ptr_c=ptr_c, perm_n=perm_n, ptr_n=ptr_n, perm_u=perm_u, ptr_u=ptr_u,
         ang_atom=c(ang_atom), ang_i=c(ang_i), ang_j=c(ang_j), ang_di=c(ang_di), ang_dj=c(ang_dj),
-        ptr_i=ptr_i, perm_j=perm_j, ptr_j=ptr_j, perm_x=perm_x, ptr_x=ptr_x, h2d_bytes=h2d,
+        ptr_i=ptr_i, perm_j=perm_j, ptr_j=ptr_j, perm_x=perm_x, ptr_x=ptr_x,
+        n_short=Es, short_ids=c(short_ids), ang_is=c(ang_is), ang_js=c(ang_js), ptr_is=ptr_is,
+        perm_js=perm_js, ptr_js=ptr_js, h2d_bytes=h2d,
     )
 
 

@@ -1,4 +1,4 @@
-// Dense feature mixing  y = x @ wt (+ bias) (+ residual)   — the "true GEMM" part of the
+// Dense feature mixing  y[yr] = x[xr] @ wt (+ bias) (+ residual[yr])   — the "true GEMM" part of the
 // path: the per-atom / per-bond halves of every GatedMLP first layer, mlp_out + residual
 // (reference chgnet/model/layers.py:129-132, 256-260) and their transposes in the
 // reverse pass.  x [m][k] row-major, wt [k][n_out] (k-major), k in {64,128,256}.
@@ -17,8 +17,9 @@ constexpr int XS = 68;  // smem stride of the x chunk
 
 template <int NT>
 __global__ void __launch_bounds__(NTHR, 2)
-linear_kernel(const float* __restrict__ x, int m, int k, const float* __restrict__ wt,
-              const float* __restrict__ bias, const float* residual, int n_out, float* y) {
+linear_kernel(const float* __restrict__ x, const int32_t* __restrict__ x_rows, int m, int k,
+              const float* __restrict__ wt, const float* __restrict__ bias, const float* residual,
+              const int32_t* __restrict__ y_rows, int n_out, float* y) {
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;           // [k][NT]
   float* s_x = smem + k * NT;  // [64][XS]
@@ -49,7 +50,8 @@ linear_kernel(const float* __restrict__ x, int m, int k, const float* __restrict
       for (int q = 0; q < 4; ++q) {
         const int id = tid + q * NTHR;
         const int row = id >> 4, c4 = id & 15;
-        const int r = min(base + row, m - 1);
+        int r = min(base + row, m - 1);
+        if (x_rows != nullptr) r = __ldg(x_rows + r);  // fused row gather
         sts4(s_x + row * XS + c4 * 4, ldg4(x + (size_t)r * k + kc + c4 * 4));
       }
       __syncthreads();
@@ -89,8 +91,9 @@ linear_kernel(const float* __restrict__ x, int m, int k, const float* __restrict
       if (bias != nullptr) b = ldg4(bias + col);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int g = base + r0 + i;
+        int g = base + r0 + i;
         if (g < m) {
+          if (y_rows != nullptr) g = __ldg(y_rows + g);  // fused row scatter (rows are unique)
           float4 v = make_float4(acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]) + b;
           if (residual != nullptr) v = v + *reinterpret_cast<const float4*>(residual + (size_t)g * n_out + col);
           stg4(y + (size_t)g * n_out + col, v);
@@ -101,8 +104,8 @@ linear_kernel(const float* __restrict__ x, int m, int k, const float* __restrict
 }
 
 template <int NT>
-int launch_linear(const float* x, int m, int k, const float* wt, const float* bias, const float* residual,
-                  int n_out, float* y, cudaStream_t stream) {
+int launch_linear(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
+                  const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream) {
   const int smem = (k * NT + TM * XS) * 4;
   static int max_smem_set = 0;
   if (smem > max_smem_set) {
@@ -113,7 +116,7 @@ int launch_linear(const float* x, int m, int k, const float* wt, const float* bi
   const int col_tiles = n_out / NT;
   const int per_col = max(1, (2 * sm_count()) / col_tiles);
   dim3 grid(min(n_tiles, per_col), col_tiles);
-  linear_kernel<NT><<<grid, NTHR, smem, stream>>>(x, m, k, wt, bias, residual, n_out, y);
+  linear_kernel<NT><<<grid, NTHR, smem, stream>>>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y);
   CHG_LAUNCH_END();
 }
 
@@ -122,13 +125,15 @@ int launch_linear(const float* x, int m, int k, const float* wt, const float* bi
 
 using namespace chg;
 
-extern "C" int chg_linear(const float* x, int32_t m, int32_t k, const float* wt, const float* bias,
-                          const float* residual, int32_t n_out, float* y, void* stream) {
+extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int32_t k, const float* wt,
+                          const float* bias, const float* residual, const int32_t* y_rows, int32_t n_out, float* y,
+                          void* stream) {
   CHG_CHECK_ARG(m >= 0, "negative size");
   CHG_CHECK_ARG(k == 64 || k == 128 || k == 256, "k must be 64, 128 or 256");
   CHG_CHECK_ARG(n_out > 0 && n_out % 64 == 0, "n_out must be a positive multiple of 64");
   if (m == 0) return CHG_OK;
   CHG_CHECK_ARG(x && wt && y, "null pointer");
-  if (n_out % 128 == 0 && k <= 128) return launch_linear<128>(x, m, k, wt, bias, residual, n_out, y, as_stream(stream));
-  return launch_linear<64>(x, m, k, wt, bias, residual, n_out, y, as_stream(stream));
+  if (n_out % 128 == 0 && k <= 128)
+    return launch_linear<128>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
+  return launch_linear<64>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
 }

@@ -58,9 +58,10 @@ class Engine:
     def _zeros(self, b: DeviceBatch, *shape, dtype=None) -> Tensor:
         return torch.zeros(*shape, dtype=dtype or self.pw.emb.dtype, device=b.z.device)
 
-    def _lin(self, b, x, wt, bias=None, residual=None) -> Tensor:
-        y = self._new(b, x.shape[0], wt.shape[1])
-        self.K.linear(x, wt, bias, residual, y)
+    def _lin(self, b, x, wt, bias=None, residual=None, x_rows=None) -> Tensor:
+        m = x.shape[0] if x_rows is None else x_rows.shape[0]
+        y = self._new(b, m, wt.shape[1])
+        self.K.linear(x, wt, bias, residual, y, x_rows, None)
         return y
 
     def _seg(self, b, data, perm, ptr, n_rows) -> Tensor:
@@ -116,29 +117,40 @@ class Engine:
                 saved_atom.append(dict(pcn=pcn, pe=pe, p=save_p))
             return self._lin(b, agg, gp.extra["wo_t"], bias=gp.extra["bo"], residual=x)
 
+        # BondConv / AngleUpdate work in the compact space of the Es bond-graph bonds
+        Es, sid = b.n_short, b.short_ids
+        wbg_s = None
+        if has_ang:
+            wbg_s = self._new(b, Es, 64)
+            K.gather_rows(wbg, sid, wbg_s)
+
         magmom = atom_fea = None
         for t in range(n_conv - 1):
             x = atom_conv(t, x, e)
             if has_ang:
                 gp = pw.bond[t]
-                pij = self._lin(b, e, gp.extra["wij_t"], bias=gp.extra["bij"])
+                pij = self._lin(b, e, gp.extra["wij_t"], bias=gp.extra["bij"], x_rows=sid)
                 px = self._lin(b, x, gp.extra["wx_t"])
                 upd = self._new(b, A, 64)
                 s_pre = self._new(b, A, 128) if need_grad else None
                 s_p = self._new(b, A, 128) if need_grad else None
-                K.bond_conv_fwd(pij, px, ang, wbg, b.ang_atom, b.ang_i, b.ang_j, gp.extra["w1a_t"],
+                K.bond_conv_fwd(pij, px, ang, wbg_s, b.ang_atom, b.ang_is, b.ang_js, gp.extra["w1a_t"],
                                 gp.w2t, gp.b2, gp.ln, upd, s_pre, s_p)
-                agg = self._seg(b, upd, None, b.ptr_i, Eu)
-                e = self._lin(b, agg, gp.extra["wo_t"], bias=gp.extra["bo"], residual=e)
+                agg = self._seg(b, upd, None, b.ptr_is, Es)
+                # e[sid] += Wo agg (+ bias); bonds outside the bond graph keep their features
+                # (with mlp_out bias the batch is built with identity compaction, Es == Eu)
+                if keep_intermediates:
+                    e = e.clone()
+                K.linear(agg, gp.extra["wo_t"], gp.extra["bo"], e, e, None, sid)
                 if need_grad:
                     saved_bond.append(dict(pre=s_pre, p=s_p))
                 if t < n_conv - 2:  # the last AngleUpdate is dead compute
                     ga = pw.angle[t]
-                    pij = self._lin(b, e, ga.extra["wij_t"], bias=ga.extra["bij"])
+                    pij = self._lin(b, e, ga.extra["wij_t"], bias=ga.extra["bij"], x_rows=sid)
                     px = self._lin(b, x, ga.extra["wx_t"])
                     ang_new = self._new(b, A, 64)
                     s_p = self._new(b, A, 128) if need_grad else None
-                    K.angle_update_fwd(pij, px, ang, b.ang_atom, b.ang_i, b.ang_j, ga.extra["w1a_t"], ga.ln,
+                    K.angle_update_fwd(pij, px, ang, b.ang_atom, b.ang_is, b.ang_js, ga.extra["w1a_t"], ga.ln,
                                        ang_new, s_p)
                     ang = ang_new
                     if need_grad:
@@ -178,7 +190,7 @@ class Engine:
         # ======================= reverse pass (inputs only) ======================
         g_e = None  # d(sum E)/d e at the current level
         g_wag = self._zeros(b, Eu, 64)
-        g_wbg = self._zeros(b, Eu, 64) if has_ang else None
+        g_wbg = self._zeros(b, Es, 64) if has_ang else None  # compact; expanded at the end
         g_a = None
 
         def acc(dst: Tensor | None, x_in: Tensor, wt: Tensor) -> Tensor:
@@ -202,10 +214,10 @@ class Engine:
 
         def angle_scatter(g_pre: Tensor, g_x: Tensor, g_e: Tensor | None, ex: dict) -> tuple[Tensor, Tensor]:
             """Push dE/dpre of an angle-indexed GatedMLP back to e (via i and j) and x."""
-            sp = self._new(b, Eu, 256)
-            K.segment_sum(g_pre, None, b.ptr_i, 0, sp[:, :128])
-            K.segment_sum(g_pre, b.perm_j, b.ptr_j, 0, sp[:, 128:])
-            g_e = acc(g_e, sp, ex["wij_b"])
+            sp = self._new(b, Es, 256)
+            K.segment_sum(g_pre, None, b.ptr_is, 0, sp[:, :128])
+            K.segment_sum(g_pre, b.perm_js, b.ptr_js, 0, sp[:, 128:])
+            K.linear(sp, ex["wij_b"], None, g_e, g_e, None, sid)  # g_e[sid] += sp @ Wij
             spx = self._seg(b, g_pre, b.perm_x, b.ptr_x, N)
             g_x = acc(g_x, spx, ex["wx_b"])
             return g_x, g_e
@@ -221,22 +233,25 @@ class Engine:
                     g_x, g_e = angle_scatter(g_pre, g_x, g_e, ga.extra)
                 # BondConv_t: e_{t+1} = e_t + Wo agg(G(e_t, a_t, x_{t+1}) w_i w_j)
                 gp, sv = pw.bond[t], saved_bond[t]
-                g_agg = self._lin(b, g_e, gp.extra["wo"])
+                g_agg = self._lin(b, g_e, gp.extra["wo"], x_rows=sid)
                 g_pre = self._new(b, A, 128)
                 gw_i, gw_j = self._new(b, A, 64), self._new(b, A, 64)
                 if g_a is None:
                     g_a = self._zeros(b, A, 64)
-                K.bond_conv_bwd(sv["pre"], sv["p"], wbg, b.ang_i, b.ang_j, g_agg, gp.extra["w1a_b"], gp.w2,
+                K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.extra["w1a_b"], gp.w2,
                                 gp.ln, g_pre, g_a, gw_i, gw_j)
                 g_x, g_e = angle_scatter(g_pre, g_x, g_e, gp.extra)
-                K.segment_sum(gw_i, None, b.ptr_i, 1, g_wbg)
-                K.segment_sum(gw_j, b.perm_j, b.ptr_j, 1, g_wbg)
+                K.segment_sum(gw_i, None, b.ptr_is, 1, g_wbg)
+                K.segment_sum(gw_j, b.perm_js, b.ptr_js, 1, g_wbg)
             g_x, g_e = atom_conv_bwd(t, g_x, g_e)
 
         # ---- geometry reverse: dE/dr per directed edge -> force, virial ------------
         g_dist = self._new(b, Eu)
+        g_wbg_full = self._zeros(b, Eu, 64)
+        if has_ang:
+            K.scatter_rows(g_wbg, sid, g_wbg_full)
         K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
-                         hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg if has_ang else self._zeros(b, Eu, 64), g_dist)
+                         hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg_full, g_dist)
         g_rhat = self._zeros(b, Ed, 3, dtype=torch.float64)
         if has_ang:
             K.angle_basis_bwd(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, g_a, g_rhat)

@@ -330,7 +330,9 @@ class CHGNet(nn.Module):
                           "inference only, parameter gradients are not available yet", stacklevel=2)
             self._warned_train = True
         need_grad = "f" in task or "s" in task
-        batch = build_batch(graphs, self.device, with_reverse=need_grad)
+        # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
+        compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
+        batch = build_batch(graphs, self.device, with_reverse=need_grad, compact_bonds=compact)
         self.last_batch = batch
         out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
                          need_crystal_fea=return_crystal_feas)

@@ -77,12 +77,21 @@ int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, const int32_t*
                         int32_t n_angles, const float* freq, int32_t n_freq,
                         const float* w, const float* g_a0, double* g_rhat, void* stream);
 
-/* ---- dense feature mixing: y = x @ wt (+ bias) (+ residual)
- * x [m][k], wt [k][n_out], k in {64,128,256}, n_out multiple of 64.
+/* ---- dense feature mixing: y[yr(r)] = x[xr(r)] @ wt (+ bias) (+ residual[yr(r)]), r < m
+ * x [.][k], wt [k][n_out], k in {64,128,256}, n_out multiple of 64; xr = x_rows ?
+ * x_rows[r] : r (fused gather), yr likewise (fused scatter, rows must be unique).
  * Used for the per-atom / per-bond halves of every GatedMLP first layer, for
- * mlp_out + residual (layers.py:129-132, 256-260) and for their transposes.      */
-int chg_linear(const float* x, int32_t m, int32_t k, const float* wt, const float* bias,
-               const float* residual, int32_t n_out, float* y, void* stream);
+ * mlp_out + residual (layers.py:129-132, 256-260) and for their transposes.
+ * BondConv / AngleUpdate only touch the bonds of the bond graph (d < 3 A, about 1/8
+ * of all bonds): x_rows / y_rows carry that compaction.                            */
+int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int32_t k, const float* wt,
+               const float* bias, const float* residual, const int32_t* y_rows, int32_t n_out,
+               float* y, void* stream);
+/* row movers for the same compaction: dst[i] = src[idx[i]]  /  dst[idx[i]] = src[i]   */
+int chg_gather_rows(const float* src, const int32_t* idx, int32_t n, int32_t width, float* dst,
+                    void* stream);
+int chg_scatter_rows(const float* src, const int32_t* idx, int32_t n, int32_t width, float* dst,
+                     void* stream);
 
 /* ---- K4: AtomConv message (layers.py:113-121, functions.py:168-183)
  * pre = pcn[c][0:128] + pe[u] + pcn[n][128:256];  p = W2.silu(pre)+b2;
@@ -103,8 +112,9 @@ int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag,
 /* ---- K4s/K5s: segmented gather-reduce (functions.py:25-37 without atomics)
  * out[r] (+)= sum_{k in [ptr[r],ptr[r+1])} data[perm ? perm[k] : k], width 64|128 */
 int chg_segment_sum(const float* data, int32_t width, const int32_t* perm,
-                    const int32_t* ptr, int32_t n_rows, int32_t accumulate, float* out,
-                    int32_t out_ld /* row stride of out, in floats */, void* stream);
+                    const int32_t* ptr, int32_t n_rows,
+                    int32_t n_items /* ptr[n_rows]; scheduling hint only */, int32_t accumulate,
+                    float* out, int32_t out_ld /* row stride of out, in floats */, void* stream);
 
 /* ---- K5: BondConv message (layers.py:238-249)
  * pre = pij[i][0:128] + pij[j][128:256] + px[c] + ang[a] @ w1a_t;

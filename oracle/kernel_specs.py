@@ -140,13 +140,24 @@ class SpecKernels:
         g_rhat.index_add_(0, ang_dj.long(), (g_u[:, None] * ri).to(g_rhat.dtype))
 
     # ---- dense
-    def linear(self, x, wt, bias, residual, y):
-        out = x @ wt
+    def linear(self, x, wt, bias, residual, y, x_rows=None, y_rows=None):
+        out = (x if x_rows is None else x[x_rows.long()]) @ wt
         if bias is not None:
             out = out + bias
-        if residual is not None:
-            out = out + residual
-        y.copy_(out)
+        if y_rows is None:
+            if residual is not None:
+                out = out + residual
+            y.copy_(out)
+        else:
+            if residual is not None:
+                out = out + residual[y_rows.long()]
+            y[y_rows.long()] = out
+
+    def gather_rows(self, src, idx, dst):
+        dst.copy_(src[idx.long()])
+
+    def scatter_rows(self, src, idx, dst):
+        dst[idx.long()] = src
 
     # ---- K4
     def _atom_pre(self, pcn, pe, center, nbr, d2u):

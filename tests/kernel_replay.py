@@ -16,6 +16,8 @@ OUT_ARGS = {
     "angle_basis_embed": [5],
     "angle_basis_bwd": [6],
     "linear": [4],
+    "gather_rows": [2],
+    "scatter_rows": [2],
     "atom_conv_fwd": [9, 10],
     "atom_conv_bwd": [10, 11],
     "segment_sum": [4],

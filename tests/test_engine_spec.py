@@ -14,10 +14,10 @@ from oracle import chgnet_oracle as orc
 from oracle.kernel_specs import SpecKernels
 
 
-def run_engine(weights, graphs, dtype, **kw):
+def run_engine(weights, graphs, dtype, compact=True, model_args=None, **kw):
     sd = {k: torch.as_tensor(v) for k, v in weights.items()}
-    pw = pack_weights(sd, None, device="cpu", dtype=dtype)
-    b = build_batch(graphs, "cpu")
+    pw = pack_weights(sd, model_args, device="cpu", dtype=dtype)
+    b = build_batch(graphs, "cpu", compact_bonds=compact)
     for name in ("frac", "image", "lattice", "volume"):
         setattr(b, name, getattr(b, name).to(dtype))
     if dtype == torch.float64:  # fp64 truth needs fp64 geometry inputs
@@ -95,3 +95,30 @@ def test_no_angles_and_isolated_atom(weights030):
     ref = orc.forward(weights030, [g_iso, g], "efs", dtype=torch.float64)
     assert torch.allclose((out.energy + out.e_ref) / torch.tensor([1, 2]), ref["e"], atol=2e-6)
     assert torch.allclose(out.force, torch.cat(ref["f"]), atol=1e-9)
+
+
+def test_identity_compaction_gives_same_result(weights030):
+    graphs = graphgen.random_graphs(2, 8, 12, 9500)
+    b1, o1 = run_engine(weights030, graphs, torch.float64, compact=True, need_grad=True)
+    b2, o2 = run_engine(weights030, graphs, torch.float64, compact=False, need_grad=True)
+    assert b1.n_short < b2.n_short == b2.n_bonds
+    assert torch.allclose(o1.energy, o2.energy, atol=1e-11) and torch.allclose(o1.force, o2.force, atol=1e-11)
+    assert torch.allclose(o1.virial, o2.virial, atol=1e-10)
+
+
+def test_v020_shaped_model_no_layernorm_bias_small_basis():
+    """0.2.0 architecture: 9 radial / 9 angular functions, no LayerNorm anywhere, mlp_out bias,
+    two readout hidden layers, cutoff_coeff 5, atom-graph cutoff 5 A."""
+    args = dict(num_radial=9, num_angular=9, gMLP_norm=None, readout_norm=None, mlp_out_bias=True, cutoff_coeff=5,
+                atom_graph_cutoff=5.0)
+    w = orc.random_weights(3, args)
+    w = {k: v for k, v in w.items() if not k.startswith("mlp.layers.4.")}
+    w["mlp.layers.5.weight"], w["mlp.layers.5.bias"] = w.pop("mlp.layers.7.weight"), w.pop("mlp.layers.7.bias")
+    graphs = graphgen.random_graphs(2, 8, 12, 9400, atom_graph_cutoff=5.0)
+    b, out = run_engine(w, graphs, torch.float64, compact=False, model_args=dict(atom_graph_cutoff=5.0, cutoff_coeff=5),
+                        need_grad=True, need_magmom=True)
+    ref = orc.forward(w, graphs, "efsm", dtype=torch.float64, args=args)
+    assert torch.allclose(out.force, torch.cat(ref["f"]), atol=1e-10)
+    assert torch.allclose(out.magmom, torch.cat(ref["m"]), atol=1e-10)
+    s = out.virial.view(-1, 3, 3) * (EV_A3_TO_GPA / b.volume.double())[:, None, None]
+    assert torch.allclose(s, torch.stack(ref["s"]), atol=1e-9)

@@ -70,7 +70,7 @@ def test_kernels_without_layernorm_and_small_basis(weights030):
     pw = pack_weights(sd, dict(atom_graph_cutoff=5.0, cutoff_coeff=5), device="cpu")
     assert not pw.hp.use_ln and pw.hp.n_readout_hidden == 2 and pw.hp.num_radial == 9
     rec = RecordingKernels()
-    Engine(pw, rec).run(build_batch(graphs, "cpu"), need_grad=True, need_magmom=True)
+    Engine(pw, rec).run(build_batch(graphs, "cpu", compact_bonds=False), need_grad=True, need_magmom=True)
     K = CudaKernels()
     for name, snap, outs in rec.calls:
         cargs = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
