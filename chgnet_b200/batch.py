@@ -78,6 +78,31 @@ class DeviceBatch:
     h2d_bytes: int = 0
 
 
+_STAGING: dict = {}  # (dtype, pinned) -> [buffer, event of the last H2D copy that read it]
+
+
+def _staging_buffer(n: int, dtype, pin: bool) -> Tensor:
+    """Grow-only host staging buffer (pinned when the target is a CUDA device), reused across
+    batches so that cudaHostAlloc is not paid per call."""
+    key = (dtype, pin)
+    slot = _STAGING.get(key)
+    if slot is not None and slot[1] is not None:
+        slot[1].synchronize()  # the previous batch's copy out of this buffer has finished
+        slot[1] = None
+    if slot is None or slot[0].numel() < n:
+        cap = max(n, int(1.5 * slot[0].numel()) if slot is not None else n)
+        slot = [torch.empty(cap, dtype=dtype, pin_memory=pin), None]
+        _STAGING[key] = slot
+    return slot[0][:n]
+
+
+def _mark_staging_in_flight(dtype, pin: bool, device: torch.device) -> None:
+    if device.type == "cuda":
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        _STAGING[(dtype, pin)][1] = ev
+
+
 def _is_sorted(t: Tensor) -> bool:
     if t.numel() < 2:
         return True
@@ -116,14 +141,10 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         if e_d != 2 * e_u or int(g.directed2undirected.shape[0]) != e_d:
             raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
 
-    # host-side sortedness checks (cheap; decide whether the device has to reorder)
-    edges_sorted = all(_is_sorted(a[:, 0]) for a in ag_l)
-    angles_sorted = all(_is_sorted(b[:, 1]) for b in bg_l)
-
     src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
-    pin = src_dev.type == "cpu" and device.type == "cuda"
+    host_src = src_dev.type == "cpu"
+    pin = host_src and device.type == "cuda"
 
-    # ---- one int32 staging buffer ----
     int_fields = [
         ("z", [g.atomic_number.reshape(-1) for g in graphs], N),
         ("ag", [a.reshape(-1) for a in ag_l], 2 * Ed),
@@ -141,22 +162,61 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
     n_flt = sum(f[2] for f in flt_fields)
 
     def stage(fields, total, dtype, tail=None):
-        buf = torch.empty(total, dtype=dtype, device=src_dev, pin_memory=pin)
-        off, views = 0, {}
+        """Concatenate all parts into one staging buffer and ship it with one copy.  Host
+        graphs are packed with numpy (single-threaded memcpy: torch CPU ops fork an OpenMP
+        team per call, which costs milliseconds on a many-core host) into a cached pinned
+        buffer; device-resident graphs are concatenated on the device."""
+        views, off = {}, 0
+        if host_src:
+            buf = _staging_buffer(total, dtype, pin)
+            host = buf.numpy()
+            for name, parts, size in fields:
+                if size:
+                    np.concatenate([p.numpy() for p in parts], out=host[off : off + size], casting="unsafe")
+                views[name] = (off, size)
+                off += size
+            if tail is not None:
+                host[off : off + tail.size] = tail
+                views["_tail"] = (off, tail.size)
+            dbuf = buf.to(device, non_blocking=True)
+            _mark_staging_in_flight(dtype, pin, device)
+            return dbuf, views, host
+        buf = torch.empty(total, dtype=dtype, device=src_dev)
         for name, parts, size in fields:
             if size:
-                torch.cat([p.to(dtype) if p.dtype != dtype else p for p in parts], out=buf[off : off + size])
+                torch.cat([p.to(dtype) for p in parts], out=buf[off : off + size])
             views[name] = (off, size)
             off += size
         if tail is not None:
-            buf[off : off + tail.numel()] = tail
-            views["_tail"] = (off, tail.numel())
-        dbuf = buf.to(device, non_blocking=True)
-        return dbuf, views
+            buf[off : off + tail.size] = torch.from_numpy(tail).to(src_dev)
+            views["_tail"] = (off, tail.size)
+        return buf.to(device), views, None
 
-    ibuf, iv = stage(int_fields, n_int, torch.int32, torch.from_numpy(counts_host))
-    fbuf, fv = stage(flt_fields, n_flt, torch.float32)
+    ibuf, iv, ihost = stage(int_fields, n_int, torch.int32, counts_host)
+    fbuf, fv, _ = stage(flt_fields, n_flt, torch.float32)
     h2d = (n_int + n_flt) * 4 if src_dev != device else 0
+
+    # sortedness (decides whether the device has to reorder): one vectorised pass over the
+    # concatenated raw indices; a decrease is only legal at a graph boundary
+    def sorted_within_graphs(raw: np.ndarray | Tensor, sizes: list[int]) -> bool:
+        if len(raw) < 2:
+            return True
+        if isinstance(raw, Tensor):
+            return all(_is_sorted(t) for t in torch.split(raw, sizes))
+        dec = raw[1:] < raw[:-1]
+        ends = np.cumsum(sizes)[:-1] - 1
+        ends = ends[(ends >= 0) & (ends < len(dec))]
+        dec[ends] = False
+        return not bool(dec.any())
+
+    if ihost is not None:
+        o, sz = iv["ag"]
+        edges_sorted = sorted_within_graphs(ihost[o : o + sz : 2].copy(), n_ed)
+        o, sz = iv["bg"]
+        angles_sorted = sorted_within_graphs(ihost[o + 1 : o + sz : 5].copy(), n_an)
+    else:
+        edges_sorted = all(_is_sorted(a[:, 0]) for a in ag_l)
+        angles_sorted = all(_is_sorted(b[:, 1]) for b in bg_l)
 
     def iview(name):
         o, s = iv[name]

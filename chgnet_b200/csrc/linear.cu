@@ -6,6 +6,8 @@
 // FFMA version: 64-row x NT-col tile per CTA step, the whole [k][NT] weight panel
 // resident in shared memory for the lifetime of a persistent CTA, x streamed in
 // [64][64] chunks.  Thread tile 4 rows x (NT/16) cols.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace chg {
@@ -121,6 +123,19 @@ int launch_linear(const float* x, const int32_t* x_rows, int m, int k, const flo
 }
 
 }  // namespace
+
+int linear_tc(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
+              const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
+
+// 1 = tcgen05 3xTF32 (default), 0 = FFMA; CHG_LINEAR_IMPL=ffma selects the latter for A/B runs
+static int linear_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("CHG_LINEAR_IMPL");
+    impl = (e != nullptr && e[0] == 'f') ? 0 : 1;
+  }
+  return impl;
+}
 }  // namespace chg
 
 using namespace chg;
@@ -133,6 +148,7 @@ extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int3
   CHG_CHECK_ARG(n_out > 0 && n_out % 64 == 0, "n_out must be a positive multiple of 64");
   if (m == 0) return CHG_OK;
   CHG_CHECK_ARG(x && wt && y, "null pointer");
+  if (linear_impl() == 1) return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (n_out % 128 == 0 && k <= 128)
     return launch_linear<128>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   return launch_linear<64>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));

@@ -314,6 +314,39 @@ class CHGNet(nn.Module):
         return self._engine
 
     # ------------------------------------------------------------------ forward
+    def _run(self, graphs, task, return_site_energies, return_atom_feas, return_crystal_feas) -> dict[str, Any]:
+        """One batch through the kernel engine; returns BATCHED device tensors."""
+        engine = self._get_engine()
+        need_grad = "f" in task or "s" in task
+        # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
+        compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
+        batch = build_batch(graphs, self.device, with_reverse=need_grad, compact_bonds=compact)
+        self.last_batch = batch
+        out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
+                         need_crystal_fea=return_crystal_feas)
+        n_dev = torch.tensor(batch.atoms_per_graph, device=self.device)
+        raw: dict[str, Any] = {"atoms_per_graph": n_dev}
+        if return_atom_feas:
+            raw["atom_fea"] = out.atom_fea
+        if "m" in task:
+            raw["m"] = out.magmom
+        if return_site_energies:
+            raw["site_energies"] = out.site_e + engine.pw.atom_ref[batch.z.long() - 1]
+        if return_crystal_feas:
+            raw["crystal_fea"] = out.crystal_fea
+        if "f" in task:
+            raw["f"] = out.force.to(torch.float32)
+        if "s" in task:
+            scale = EV_A3_TO_GPA / batch.volume.to(torch.float64)
+            raw["s"] = (out.virial.view(-1, 3, 3) * scale[:, None, None]).to(torch.float32)
+        total = out.energy + out.e_ref
+        if self.is_intensive:
+            total = total / n_dev
+        raw["e"] = total.to(torch.float32)
+        return raw
+
+    _PER_ATOM = ("atom_fea", "m", "site_energies", "f")
+
     def forward(
         self,
         graphs: Sequence[CrystalGraph],
@@ -323,41 +356,24 @@ class CHGNet(nn.Module):
         return_atom_feas: bool = False,
         return_crystal_feas: bool = False,
     ) -> dict[str, Tensor]:
-        """Prediction for a list of CrystalGraphs (reference model.py:330-387)."""
-        engine = self._get_engine()
+        """Prediction for a list of CrystalGraphs (reference model.py:330-387): ``e`` Tensor[B],
+        ``f`` / ``m`` / ``site_energies`` / ``atom_fea`` lists of per-graph tensors, ``s`` list of
+        [3,3], ``crystal_fea`` Tensor[B,64], ``atoms_per_graph``."""
         if self.training and torch.is_grad_enabled() and not getattr(self, "_warned_train", False):
             warnings.warn("chgnet_b200 (round 1) returns tensors without autograd history: "
                           "inference only, parameter gradients are not available yet", stacklevel=2)
             self._warned_train = True
-        need_grad = "f" in task or "s" in task
-        # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
-        compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
-        batch = build_batch(graphs, self.device, with_reverse=need_grad, compact_bonds=compact)
-        self.last_batch = batch
-        out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
-                         need_crystal_fea=return_crystal_feas)
-        n_list = batch.atoms_per_graph
-        n_dev = torch.tensor(n_list, device=self.device)
-        pred: dict[str, Any] = {"atoms_per_graph": n_dev}
-        if return_atom_feas:
-            pred["atom_fea"] = torch.split(out.atom_fea, n_list)
-        if "m" in task:
-            pred["m"] = list(torch.split(out.magmom, n_list))
-        if return_site_energies:
-            shift = engine.pw.atom_ref[batch.z.long() - 1]
-            pred["site_energies"] = list(torch.split(out.site_e + shift, n_list))
-        if return_crystal_feas:
-            pred["crystal_fea"] = out.crystal_fea
-        if "f" in task:
-            pred["f"] = list(torch.split(out.force.to(torch.float32), n_list))
-        if "s" in task:
-            scale = EV_A3_TO_GPA / batch.volume.to(torch.float64)
-            stress = (out.virial.view(-1, 3, 3) * scale[:, None, None]).to(torch.float32)
-            pred["s"] = list(stress.unbind(0))
-        total = out.energy + out.e_ref
-        if self.is_intensive:
-            total = total / n_dev
-        pred["e"] = total.to(torch.float32)
+        raw = self._run(graphs, task, return_site_energies, return_atom_feas, return_crystal_feas)
+        n_list = self.last_batch.atoms_per_graph
+        pred: dict[str, Any] = {}
+        for key, val in raw.items():
+            if key in self._PER_ATOM:
+                parts = torch.split(val, n_list)
+                pred[key] = parts if key == "atom_fea" else list(parts)
+            elif key == "s":
+                pred[key] = list(val.unbind(0))
+            else:
+                pred[key] = val
         return pred
 
     # ------------------------------------------------------------------ predict API
@@ -387,25 +403,13 @@ class CHGNet(nn.Module):
         predictions: list[dict[str, np.ndarray]] = [{} for _ in graphs]
         for start in range(0, len(graphs), batch_size):
             chunk = graphs[start : start + batch_size]
-            with torch.no_grad():
-                pred = self.forward(chunk, task=task, return_site_energies=return_site_energies,
-                                    return_atom_feas=return_atom_feas, return_crystal_feas=return_crystal_feas)
-            n_list = [int(n) for n in self.last_batch.atoms_per_graph]
-            bounds = np.cumsum(n_list)[:-1]
+            raw = self._run(chunk, task, return_site_energies, return_atom_feas, return_crystal_feas)
+            bounds = np.cumsum(self.last_batch.atoms_per_graph)[:-1]
             for key in ("e", "f", "s", "m", "site_energies", "atom_fea", "crystal_fea"):
-                if key not in pred:
+                if key not in raw:
                     continue
-                val = pred[key]
-                if isinstance(val, (list, tuple)):  # one D2H copy per key, split on the host
-                    if key == "s":
-                        host = torch.stack(list(val)).cpu().numpy()
-                        parts = [host[i] for i in range(len(chunk))]
-                    else:
-                        host = torch.cat(list(val)).cpu().numpy()
-                        parts = np.split(host, bounds)
-                else:
-                    host = val.cpu().numpy()
-                    parts = [host[i] for i in range(len(chunk))]
+                host = raw[key].cpu().numpy()  # ONE device->host copy per key, split on the host
+                parts = np.split(host, bounds) if key in self._PER_ATOM else [host[i] for i in range(len(chunk))]
                 for i, part in enumerate(parts):
                     predictions[start + i][key] = np.asarray(part)
         return predictions[0] if single else predictions
