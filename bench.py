@@ -325,6 +325,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     e2e_ms_per_step = float(t.item()) / args.steps
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()  # wait for rank 0's extra legs (roofline, shares, CPU baseline)
         return
     # e2e breakdown (one synchronised pass, outside the timed loops)
     torch.cuda.synchronize()
@@ -400,7 +402,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         "gpu_launches": int(launches), "wall_ms_timed_region": wall_ms,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernel_shares": shares,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
 
 
 def main() -> None:

@@ -32,10 +32,10 @@ SIGNATURES: dict[str, list] = {
     "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P],
     "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
     "chg_segment_sum": [P, I, P, P, I, I, I, P, I, P],
-    "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P],
-    "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
-    "chg_angle_update_fwd": [P, P, P, P, P, P, I, P, P, P, P, P],
-    "chg_angle_update_bwd": [P, P, I, P, P, P, P, P],
+    "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_angle_update_fwd": [P, P, P, P, P, P, P, I, P, P, P, P],
+    "chg_angle_update_bwd": [P, P, I, P, P, P],
     "chg_readout": [P, P, P, I, P, P, P, P, I, P, F, P, P, P, P, P, P, P],
     "chg_magmom": [P, I, P, F, P, P],
     "chg_force_virial": [P, P, P, P, P, P, P, P, P, P, I, P, P, P],
@@ -172,25 +172,24 @@ class CudaKernels:
         self._call("chg_segment_sum", _p(data), data.shape[1], _p(perm), _p(ptr), ptr.shape[0] - 1, n_items,
                    int(accumulate), _p(out), out.stride(0))
 
-    def bond_conv_fwd(self, pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p):
-        self._chk(pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p)
-        self._call("chg_bond_conv_fwd", _p(pij), _p(px), _p(ang), _p(wbg), _p(ang_atom), _p(ang_i), _p(ang_j),
-                   ang_i.shape[0], _p(w1a_t), _p(w2t), _p(b2), _p(ln), _p(upd), _p(save_pre), _p(save_p))
+    def bond_conv_fwd(self, pij, px, pa, wbg, ang_atom, ang_i, ang_j, w2t, b2, ln, upd, save_pre, save_p):
+        self._chk(pij, px, pa, wbg, ang_atom, ang_i, ang_j, w2t, b2, ln, upd, save_pre, save_p)
+        self._call("chg_bond_conv_fwd", _p(pij), _p(px), _p(pa), _p(wbg), _p(ang_atom), _p(ang_i), _p(ang_j),
+                   ang_i.shape[0], _p(w2t), _p(b2), _p(ln), _p(upd), _p(save_pre), _p(save_p))
 
-    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j):
-        self._chk(save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j)
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j):
+        self._chk(save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j)
         self._call("chg_bond_conv_bwd", _p(save_pre), _p(save_p), _p(wbg), _p(ang_i), _p(ang_j), ang_i.shape[0],
-                   _p(g_agg), _p(w1a), _p(w2), _p(ln), _p(g_pre), _p(g_ang), _p(gw_i), _p(gw_j))
+                   _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(gw_i), _p(gw_j))
 
-    def angle_update_fwd(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p):
-        self._chk(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p)
-        self._call("chg_angle_update_fwd", _p(pij), _p(px), _p(ang), _p(ang_atom), _p(ang_i), _p(ang_j),
-                   ang_i.shape[0], _p(w1a_t), _p(ln), _p(ang_new), _p(save_p))
+    def angle_update_fwd(self, pij, px, pa, ang, ang_atom, ang_i, ang_j, ln, ang_new, save_p):
+        self._chk(pij, px, pa, ang, ang_atom, ang_i, ang_j, ln, ang_new, save_p)
+        self._call("chg_angle_update_fwd", _p(pij), _p(px), _p(pa), _p(ang), _p(ang_atom), _p(ang_i), _p(ang_j),
+                   ang_i.shape[0], _p(ln), _p(ang_new), _p(save_p))
 
-    def angle_update_bwd(self, save_p, g_ang_in, w1a, ln, g_pre, g_ang_out):
-        self._chk(save_p, g_ang_in, w1a, ln, g_pre, g_ang_out)
-        self._call("chg_angle_update_bwd", _p(save_p), _p(g_ang_in), save_p.shape[0], _p(w1a), _p(ln), _p(g_pre),
-                   _p(g_ang_out))
+    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre):
+        self._chk(save_p, g_ang_in, ln, g_pre)
+        self._call("chg_angle_update_bwd", _p(save_p), _p(g_ang_in), save_p.shape[0], _p(ln), _p(g_pre))
 
     def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph,
                 e_ref, g_x):

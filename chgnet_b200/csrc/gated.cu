@@ -5,113 +5,33 @@
 // chgnet/model/functions.py:168-183.
 //
 // B200 design: the first Linear of every GatedMLP is split by input
-// block and evaluated per ATOM / per BOND by chg_linear; these kernels only gather
-// the three 128-wide pre-activation rows of each edge/angle, add them, and run the
-// remaining dense work of the row (the 64x128 angle block, the two 64x64 second
-// layers) as register-tiled FFMA GEMMs on a 64-row tile staged in shared memory,
-// with LayerNorm / SiLU / sigmoid / bond-weight smoothing fused in the epilogue.
-// One persistent CTA per resident slot; weights are loaded to shared memory once.
+// block and evaluated per ATOM / per BOND / per ANGLE by chg_linear (tensor cores); the
+// kernels here gather the 128-wide pre-activation rows of each edge/angle (3 for AtomConv,
+// 4 for BondConv / AngleUpdate), add them, run the two 64x64 second layers, and fuse
+// LayerNorm / SiLU / sigmoid / bond-weight smoothing / residual in the epilogue.
+//
+// This file is the FFMA implementation (64-row tiles in shared memory, register-tiled
+// GEMM; measured shared-memory-bandwidth bound, profiles/SUMMARY_r01.md).  gated_tc.cu
+// is the tcgen05 implementation of the same entry points; CHG_GATED_IMPL=ffma selects
+// this one.  One persistent CTA per resident slot; weights stay in shared memory.
 //
 // Thread map: 256 threads = 16 (ty) x 16 (tx); a thread owns rows ty*4..+3 and, in
 // each 64-wide half (core | gate), columns tx*4..+3 — so core and gate of the same
 // feature live in the same thread and LayerNorm reduces over the 16 tx lanes.
-#include "common.cuh"
+#include <cstdlib>
+
+#include "gated_common.cuh"
 
 namespace chg {
 namespace {
 
+using namespace gated;
+
 constexpr int TM = 64;     // rows (edges / angles) per tile
 constexpr int NTHR = 256;  // threads per CTA
-constexpr int HS = 132;    // smem stride of a 128-wide row
-constexpr int AS = 68;     // smem stride of a 64-wide row
-constexpr float LN_EPS = 1e-5f;
-
-enum Mode { ATOM = 0, BOND = 1, ANGLE = 2 };
-
-struct FwdArgs {
-  const float* p_a;     // ATOM: pcn [N][256]        BOND/ANGLE: pij [Eu][256]
-  const float* p_b;     // ATOM: pe  [Eu][128]       BOND/ANGLE: px  [N][128]
-  const float* feat;    // BOND/ANGLE: angle features [A][64]
-  const float* wgt;     // ATOM: wag [Eu][64]        BOND: wbg [Eu][64]
-  const int32_t* idx0;  // row of p_a, first half    (center | bond i)
-  const int32_t* idx1;  // row of p_a, second half   (nbr    | bond j)
-  const int32_t* idx2;  // row of p_b                (d2u    | atom)
-  int32_t n_rows;
-  const float* w1a_t;  // [64][128]
-  const float* w2t;    // [64][128]
-  const float* b2;     // [128]
-  const float* ln;     // [4][64] or null
-  float* out;          // [rows][64]
-  float* save_pre;     // [rows][128] or null
-  float* save_p;       // [rows][128] or null
-};
-
-struct BwdArgs {
-  const float* p_a;
-  const float* p_b;
-  const float* wgt;
-  const int32_t* idx0;
-  const int32_t* idx1;
-  const int32_t* idx2;
-  int32_t n_rows;
-  const float* save_pre;  // BOND
-  const float* save_p;
-  const float* g_in;  // ATOM: g_agg [N][64]; BOND: g_agg [Eu][64]; ANGLE: g_ang_in [A][64] or null
-  const float* w1a;   // [128][64]
-  const float* w2;    // [128][64]
-  const float* ln;
-  float* g_pre;   // [rows][128]
-  float* g_w0;    // ATOM: g_w; BOND: gw_i
-  float* g_w1;    // BOND: gw_j
-  float* g_feat;  // BOND: g_ang (+=); ANGLE: g_ang_out (=)
-};
 
 __device__ __forceinline__ void copy_to_smem(float* dst, const float* src, int n_floats, int tid) {
   for (int i = tid * 4; i < n_floats; i += NTHR * 4) sts4(dst + i, ldg4(src + i));
-}
-
-// LayerNorm statistics of one 64-wide row spread over 16 lanes (4 values each)
-__device__ __forceinline__ void ln_stats(const float (&v)[4], float (&xhat)[4], float& rstd) {
-  const float mean = sum16(v[0] + v[1] + v[2] + v[3]) * (1.f / 64.f);
-  float d[4], ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    d[j] = v[j] - mean;
-    ss = fmaf(d[j], d[j], ss);
-  }
-  const float var = sum16(ss) * (1.f / 64.f);
-  rstd = 1.f / sqrtf(var + LN_EPS);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) xhat[j] = d[j] * rstd;
-}
-
-// acc[i][0..3] += sum_k A[r0+i][k] * B[k][c0..], acc[i][4..7] += sum_k A[r0+i][k] * B[k][64+c0..]
-// A: smem [64][lda] (k < 64), B: smem [64][128]
-__device__ __forceinline__ void gemm_dense64(float (&acc)[4][8], const float* __restrict__ sA, int lda,
-                                             const float* __restrict__ sB, int r0, int c0) {
-#pragma unroll 2
-  for (int k4 = 0; k4 < 16; ++k4) {
-    float4 av[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) av[i] = lds4(sA + (r0 + i) * lda + k4 * 4);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float4 wc = lds4(sB + (k4 * 4 + kk) * 128 + c0);
-      const float4 wg = lds4(sB + (k4 * 4 + kk) * 128 + 64 + c0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = f4at(av[i], kk);
-        acc[i][0] = fmaf(a, wc.x, acc[i][0]);
-        acc[i][1] = fmaf(a, wc.y, acc[i][1]);
-        acc[i][2] = fmaf(a, wc.z, acc[i][2]);
-        acc[i][3] = fmaf(a, wc.w, acc[i][3]);
-        acc[i][4] = fmaf(a, wg.x, acc[i][4]);
-        acc[i][5] = fmaf(a, wg.y, acc[i][5]);
-        acc[i][6] = fmaf(a, wg.z, acc[i][6]);
-        acc[i][7] = fmaf(a, wg.w, acc[i][7]);
-      }
-    }
-  }
 }
 
 // Block-diagonal pair of 64x64 products on a [64][HS] tile:
@@ -150,30 +70,12 @@ __device__ __forceinline__ void gemm_blockdiag(float (&acc)[4][8], const float* 
   }
 }
 
-// pre-activation rows gathered from the per-atom / per-bond first-layer products
-__device__ __forceinline__ void gather_pre(float (&acc)[4][8], const float* __restrict__ p_a,
-                                           const float* __restrict__ p_b, const int* s_idx, int r0, int c0) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = r0 + i;
-    const float* s0 = p_a + (size_t)s_idx[row] * 256 + c0;
-    const float* s1 = p_a + (size_t)s_idx[TM + row] * 256 + 128 + c0;
-    const float* s2 = p_b + (size_t)s_idx[2 * TM + row] * 128 + c0;
-    const float4 vc = ldg4(s0) + ldg4(s1) + ldg4(s2);
-    const float4 vg = ldg4(s0 + 64) + ldg4(s1 + 64) + ldg4(s2 + 64);
-    acc[i][0] += vc.x; acc[i][1] += vc.y; acc[i][2] += vc.z; acc[i][3] += vc.w;
-    acc[i][4] += vg.x; acc[i][5] += vg.y; acc[i][6] += vg.z; acc[i][7] += vg.w;
-  }
-}
-
 template <int MODE>
 struct FwdSmem {
   static constexpr bool HAS_W2 = MODE != ANGLE;
-  static constexpr bool HAS_W1A = MODE != ATOM;
   static constexpr int W2_OFF = 0;
-  static constexpr int W1A_OFF = W2_OFF + (HAS_W2 ? 64 * 128 : 0);
-  static constexpr int TILE_OFF = W1A_OFF + (HAS_W1A ? 64 * 128 : 0);
-  static constexpr int TILE_FLOATS = HAS_W2 ? TM * HS : TM * AS;
+  static constexpr int TILE_OFF = W2_OFF + (HAS_W2 ? 64 * 128 : 0);
+  static constexpr int TILE_FLOATS = HAS_W2 ? TM * HS : 0;
   static constexpr int B2_OFF = TILE_OFF + TILE_FLOATS;
   static constexpr int LN_OFF = B2_OFF + 128;
   static constexpr int IDX_OFF = LN_OFF + 256;
@@ -185,8 +87,7 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
   using L = FwdSmem<MODE>;
   extern __shared__ __align__(16) float smem[];
   float* s_w2t = smem + L::W2_OFF;
-  float* s_w1a = smem + L::W1A_OFF;
-  float* s_tile = smem + L::TILE_OFF;  // H [64][HS]; BOND stages the angle tile [64][AS] here first
+  float* s_tile = smem + L::TILE_OFF;  // H [64][HS]
   float* s_b2 = smem + L::B2_OFF;
   float* s_ln = smem + L::LN_OFF;
   int* s_idx = reinterpret_cast<int*>(smem + L::IDX_OFF);
@@ -200,7 +101,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
     copy_to_smem(s_w2t, a.w2t, 64 * 128, tid);
     if (tid < 128) s_b2[tid] = a.b2[tid];
   }
-  if (L::HAS_W1A) copy_to_smem(s_w1a, a.w1a_t, 64 * 128, tid);
   if (use_ln) s_ln[tid] = a.ln[tid];
 
   const int n_tiles = (a.n_rows + TM - 1) / TM;
@@ -213,15 +113,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
       s_idx[TM + tid] = a.idx1[r];
       s_idx[2 * TM + tid] = a.idx2[r];
     }
-    if (L::HAS_W1A) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int id = tid + q * NTHR;
-        const int row = id >> 4, c4 = id & 15;
-        const int r = min(base + row, a.n_rows - 1);
-        sts4(s_tile + row * AS + c4 * 4, ldg4(a.feat + (size_t)r * 64 + c4 * 4));
-      }
-    }
     __syncthreads();
 
     float acc[4][8];
@@ -229,16 +120,7 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-    float4 resid[4];
-    if (L::HAS_W1A) {
-      gemm_dense64(acc, s_tile, AS, s_w1a, r0, c0);
-      if (MODE == ANGLE) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) resid[i] = lds4(s_tile + (r0 + i) * AS + c0);
-      }
-    }
-    gather_pre(acc, a.p_a, a.p_b, s_idx, r0, c0);
+    gather_pre<TM>(acc, a.p_a, a.p_b, a.p_c, s_idx, base, a.n_rows, r0, c0);
 
     if (L::HAS_W2) {
       if (a.save_pre != nullptr) {
@@ -251,7 +133,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
           }
         }
       }
-      if (MODE == BOND) __syncthreads();  // angle tile fully consumed before H overwrites it
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         sts4(s_tile + (r0 + i) * HS + c0,
@@ -305,7 +186,7 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
       } else if (MODE == BOND) {
         o = o * ldg4(a.wgt + (size_t)s_idx[row] * 64 + c0) * ldg4(a.wgt + (size_t)s_idx[TM + row] * 64 + c0);
       } else {
-        o = o + resid[i];
+        o = o + ldg4(a.feat + (size_t)min(g, a.n_rows - 1) * 64 + c0);
       }
       if (valid) stg4(a.out + (size_t)g * 64 + c0, o);
     }
@@ -315,11 +196,9 @@ __global__ void __launch_bounds__(NTHR, 2) gated_fwd_kernel(const FwdArgs a) {
 template <int MODE>
 struct BwdSmem {
   static constexpr bool HAS_W2 = MODE != ANGLE;
-  static constexpr bool HAS_W1A = MODE != ATOM;
   static constexpr int W2_OFF = 0;
-  static constexpr int W1A_OFF = W2_OFF + (HAS_W2 ? 128 * 64 : 0);
-  static constexpr int TILE_OFF = W1A_OFF + (HAS_W1A ? 128 * 64 : 0);
-  static constexpr int LN_OFF = TILE_OFF + TM * HS;
+  static constexpr int TILE_OFF = W2_OFF + (HAS_W2 ? 128 * 64 : 0);
+  static constexpr int LN_OFF = TILE_OFF + (HAS_W2 ? TM * HS : 0);
   static constexpr int IDX_OFF = LN_OFF + 256;
   static constexpr int TOTAL_BYTES = (IDX_OFF + 3 * TM) * 4;
 };
@@ -328,9 +207,8 @@ template <int MODE>
 __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
   using L = BwdSmem<MODE>;
   extern __shared__ __align__(16) float smem[];
-  float* s_w2 = smem + L::W2_OFF;    // [128][64]
-  float* s_w1a = smem + L::W1A_OFF;  // [128][64]
-  float* s_g = smem + L::TILE_OFF;   // [64][HS]
+  float* s_w2 = smem + L::W2_OFF;   // [128][64]
+  float* s_g = smem + L::TILE_OFF;  // [64][HS]
   float* s_ln = smem + L::LN_OFF;
   int* s_idx = reinterpret_cast<int*>(smem + L::IDX_OFF);
 
@@ -340,7 +218,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
   const bool use_ln = a.ln != nullptr;
 
   if (L::HAS_W2) copy_to_smem(s_w2, a.w2, 128 * 64, tid);
-  if (L::HAS_W1A) copy_to_smem(s_w1a, a.w1a, 128 * 64, tid);
   if (use_ln) s_ln[tid] = a.ln[tid];
 
   const int n_tiles = (a.n_rows + TM - 1) / TM;
@@ -362,7 +239,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
       g2 = lds4(s_ln + 128 + c0);
       b2v = lds4(s_ln + 192 + c0);
     }
-    float4 go_keep[4];  // ANGLE: upstream gradient, reused for the residual path
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = r0 + i;
@@ -410,7 +286,6 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
         go = gm * wi * wj;
       } else {
         go = a.g_in != nullptr ? ldg4(a.g_in + (size_t)r * 64 + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
-        go_keep[i] = go;
       }
       float gy1[4], gy2[4];
 #pragma unroll
@@ -446,16 +321,17 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
       }
       const float4 gpc = make_float4(gy1[0], gy1[1], gy1[2], gy1[3]);
       const float4 gpg = make_float4(gy2[0], gy2[1], gy2[2], gy2[3]);
-      sts4(s_g + row * HS + c0, gpc);
-      sts4(s_g + row * HS + 64 + c0, gpg);
-      if (MODE == ANGLE && valid) {  // no hidden layer: dE/dpre == dE/dp
+      if (L::HAS_W2) {
+        sts4(s_g + row * HS + c0, gpc);
+        sts4(s_g + row * HS + 64 + c0, gpg);
+      } else if (valid) {  // no hidden layer: dE/dpre == dE/dp
         stg4(a.g_pre + (size_t)g * 128 + c0, gpc);
         stg4(a.g_pre + (size_t)g * 128 + 64 + c0, gpg);
       }
     }
-    __syncthreads();
 
     if (L::HAS_W2) {
+      __syncthreads();
       float acc[4][8];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -469,7 +345,7 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) pre[i][j] = 0.f;
-        gather_pre(pre, a.p_a, a.p_b, s_idx, r0, c0);
+        gather_pre<TM>(pre, a.p_a, a.p_b, nullptr, s_idx, base, a.n_rows, r0, c0);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -480,63 +356,14 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
           pre[i][4] = vg.x; pre[i][5] = vg.y; pre[i][6] = vg.z; pre[i][7] = vg.w;
         }
       }
-      if (MODE == BOND) __syncthreads();  // everyone is done reading g_p from s_g
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int g = base + r0 + i;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] *= dsilu_f(pre[i][j]);
-        const float4 vc = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        const float4 vg = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
         if (g < a.n_rows) {
-          stg4(a.g_pre + (size_t)g * 128 + c0, vc);
-          stg4(a.g_pre + (size_t)g * 128 + 64 + c0, vg);
-        }
-        if (MODE == BOND) {
-          sts4(s_g + (r0 + i) * HS + c0, vc);
-          sts4(s_g + (r0 + i) * HS + 64 + c0, vg);
-        }
-      }
-      if (MODE == BOND) __syncthreads();
-    }
-
-    if (L::HAS_W1A) {
-      // dE/d(angle feature) = g_pre [64][128] . W1a [128][64]; thread tile 4 rows x 4 cols
-      float ga[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ga[i][j] = 0.f;
-#pragma unroll 2
-      for (int k4 = 0; k4 < 32; ++k4) {
-        float4 gv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gv[i] = lds4(s_g + (r0 + i) * HS + k4 * 4);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float4 w = lds4(s_w1a + (k4 * 4 + kk) * 64 + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float v = f4at(gv[i], kk);
-            ga[i][0] = fmaf(v, w.x, ga[i][0]);
-            ga[i][1] = fmaf(v, w.y, ga[i][1]);
-            ga[i][2] = fmaf(v, w.z, ga[i][2]);
-            ga[i][3] = fmaf(v, w.w, ga[i][3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int g = base + r0 + i;
-        if (g < a.n_rows) {
-          float* dst = a.g_feat + (size_t)g * 64 + c0;
-          float4 v = make_float4(ga[i][0], ga[i][1], ga[i][2], ga[i][3]);
-          if (MODE == BOND) {
-            v = v + *reinterpret_cast<const float4*>(dst);
-          } else {
-            v = v + go_keep[i];
-          }
-          stg4(dst, v);
+          stg4(a.g_pre + (size_t)g * 128 + c0, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+          stg4(a.g_pre + (size_t)g * 128 + 64 + c0, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
         }
       }
     }
@@ -579,10 +406,21 @@ int launch_bwd(const BwdArgs& a, cudaStream_t stream) {
   CHG_LAUNCH_END();
 }
 
+// 1 = tcgen05 (default) for the kernels that contain a GEMM, 0 = FFMA (CHG_GATED_IMPL=ffma)
+int gated_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("CHG_GATED_IMPL");
+    impl = (e != nullptr && e[0] == 'f') ? 0 : 1;
+  }
+  return impl;
+}
+
 }  // namespace
 }  // namespace chg
 
 using namespace chg;
+using namespace chg::gated;
 
 extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float* wag, const int32_t* center,
                                  const int32_t* nbr, const int32_t* d2u, int32_t n_edges, const float* w2t,
@@ -590,7 +428,8 @@ extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(n_edges >= 0, "negative size");
   if (n_edges == 0) return CHG_OK;
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && w2t && b2 && msg, "null pointer");
-  FwdArgs a{pcn, pe, nullptr, wag, center, nbr, d2u, n_edges, nullptr, w2t, b2, ln, msg, nullptr, save_p};
+  FwdArgs a{pcn, pe, nullptr, nullptr, wag, center, nbr, d2u, n_edges, w2t, b2, ln, msg, nullptr, save_p};
+  if (gated_impl() == 1) return atom_conv_fwd_tc(a, as_stream(stream));
   return launch_fwd<ATOM>(a, as_stream(stream));
 }
 
@@ -601,52 +440,52 @@ extern "C" int chg_atom_conv_bwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(n_edges >= 0, "negative size");
   if (n_edges == 0) return CHG_OK;
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && save_p && g_agg && w2 && g_pre && g_w, "null pointer");
-  BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, nullptr, w2, ln, g_pre, g_w, nullptr, nullptr};
+  BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, w2, ln, g_pre, g_w, nullptr};
+  if (gated_impl() == 1) return atom_conv_bwd_tc(a, as_stream(stream));
   return launch_bwd<ATOM>(a, as_stream(stream));
 }
 
-extern "C" int chg_bond_conv_fwd(const float* pij, const float* px, const float* ang, const float* wbg,
+extern "C" int chg_bond_conv_fwd(const float* pij, const float* px, const float* pa, const float* wbg,
                                  const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
-                                 int32_t n_angles, const float* w1a_t, const float* w2t, const float* b2,
-                                 const float* ln, float* upd, float* save_pre, float* save_p, void* stream) {
+                                 int32_t n_angles, const float* w2t, const float* b2, const float* ln, float* upd,
+                                 float* save_pre, float* save_p, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
-  CHG_CHECK_ARG(pij && px && ang && wbg && ang_atom && ang_i && ang_j && w1a_t && w2t && b2 && upd, "null pointer");
-  FwdArgs a{pij, px, ang, wbg, ang_i, ang_j, ang_atom, n_angles, w1a_t, w2t, b2, ln, upd, save_pre, save_p};
+  CHG_CHECK_ARG(pij && px && pa && wbg && ang_atom && ang_i && ang_j && w2t && b2 && upd, "null pointer");
+  FwdArgs a{pij, px, pa, nullptr, wbg, ang_i, ang_j, ang_atom, n_angles, w2t, b2, ln, upd, save_pre, save_p};
+  if (gated_impl() == 1) return bond_conv_fwd_tc(a, as_stream(stream));
   return launch_fwd<BOND>(a, as_stream(stream));
 }
 
 extern "C" int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg, const int32_t* ang_i,
-                                 const int32_t* ang_j, int32_t n_angles, const float* g_agg, const float* w1a,
-                                 const float* w2, const float* ln, float* g_pre, float* g_ang, float* gw_i,
-                                 float* gw_j, void* stream) {
+                                 const int32_t* ang_j, int32_t n_angles, const float* g_agg, const float* w2,
+                                 const float* ln, float* g_pre, float* gw_i, float* gw_j, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
-  CHG_CHECK_ARG(save_pre && save_p && wbg && ang_i && ang_j && g_agg && w1a && w2 && g_pre && g_ang && gw_i && gw_j,
-                "null pointer");
-  BwdArgs a{nullptr, nullptr, wbg, ang_i, ang_j, nullptr, n_angles, save_pre, save_p, g_agg, w1a, w2, ln,
-            g_pre, gw_i, gw_j, g_ang};
+  CHG_CHECK_ARG(save_pre && save_p && wbg && ang_i && ang_j && g_agg && w2 && g_pre && gw_i && gw_j, "null pointer");
+  BwdArgs a{nullptr, nullptr, wbg, ang_i, ang_j, nullptr, n_angles, save_pre, save_p, g_agg, w2, ln,
+            g_pre, gw_i, gw_j};
+  if (gated_impl() == 1) return bond_conv_bwd_tc(a, as_stream(stream));
   return launch_bwd<BOND>(a, as_stream(stream));
 }
 
-extern "C" int chg_angle_update_fwd(const float* pij, const float* px, const float* ang, const int32_t* ang_atom,
-                                    const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles,
-                                    const float* w1a_t, const float* ln, float* ang_new, float* save_p,
-                                    void* stream) {
+extern "C" int chg_angle_update_fwd(const float* pij, const float* px, const float* pa, const float* ang,
+                                    const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                                    int32_t n_angles, const float* ln, float* ang_new, float* save_p, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
-  CHG_CHECK_ARG(pij && px && ang && ang_atom && ang_i && ang_j && w1a_t && ang_new, "null pointer");
-  FwdArgs a{pij, px, ang, nullptr, ang_i, ang_j, ang_atom, n_angles, w1a_t, nullptr, nullptr, ln, ang_new,
+  CHG_CHECK_ARG(pij && px && pa && ang && ang_atom && ang_i && ang_j && ang_new, "null pointer");
+  FwdArgs a{pij, px, pa, ang, nullptr, ang_i, ang_j, ang_atom, n_angles, nullptr, nullptr, ln, ang_new,
             nullptr, save_p};
   return launch_fwd<ANGLE>(a, as_stream(stream));
 }
 
-extern "C" int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles, const float* w1a,
-                                    const float* ln, float* g_pre, float* g_ang_out, void* stream) {
+extern "C" int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles, const float* ln,
+                                    float* g_pre, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
-  CHG_CHECK_ARG(save_p && w1a && g_pre && g_ang_out, "null pointer");
-  BwdArgs a{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_angles, nullptr, save_p, g_ang_in, w1a,
-            nullptr, ln, g_pre, nullptr, nullptr, g_ang_out};
+  CHG_CHECK_ARG(save_p && g_pre, "null pointer");
+  BwdArgs a{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_angles, nullptr, save_p, g_ang_in,
+            nullptr, ln, g_pre, nullptr, nullptr};
   return launch_bwd<ANGLE>(a, as_stream(stream));
 }

@@ -131,11 +131,12 @@ class Engine:
                 gp = pw.bond[t]
                 pij = self._lin(b, e, gp.extra["wij_t"], bias=gp.extra["bij"], x_rows=sid)
                 px = self._lin(b, x, gp.extra["wx_t"])
+                pa = self._lin(b, ang, gp.extra["w1a_t"])  # angle block of the first layer, per angle
                 upd = self._new(b, A, 64)
                 s_pre = self._new(b, A, 128) if need_grad else None
                 s_p = self._new(b, A, 128) if need_grad else None
-                K.bond_conv_fwd(pij, px, ang, wbg_s, b.ang_atom, b.ang_is, b.ang_js, gp.extra["w1a_t"],
-                                gp.w2t, gp.b2, gp.ln, upd, s_pre, s_p)
+                K.bond_conv_fwd(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, gp.w2t, gp.b2, gp.ln,
+                                upd, s_pre, s_p)
                 agg = self._seg(b, upd, None, b.ptr_is, Es)
                 # e[sid] += Wo agg (+ bias); bonds outside the bond graph keep their features
                 # (with mlp_out bias the batch is built with identity compaction, Es == Eu)
@@ -148,10 +149,10 @@ class Engine:
                     ga = pw.angle[t]
                     pij = self._lin(b, e, ga.extra["wij_t"], bias=ga.extra["bij"], x_rows=sid)
                     px = self._lin(b, x, ga.extra["wx_t"])
+                    pa = self._lin(b, ang, ga.extra["w1a_t"])
                     ang_new = self._new(b, A, 64)
                     s_p = self._new(b, A, 128) if need_grad else None
-                    K.angle_update_fwd(pij, px, ang, b.ang_atom, b.ang_is, b.ang_js, ga.extra["w1a_t"], ga.ln,
-                                       ang_new, s_p)
+                    K.angle_update_fwd(pij, px, pa, ang, b.ang_atom, b.ang_is, b.ang_js, ga.ln, ang_new, s_p)
                     ang = ang_new
                     if need_grad:
                         saved_angle.append(dict(p=s_p))
@@ -227,19 +228,18 @@ class Engine:
             if has_ang:
                 if t < n_conv - 2:  # AngleUpdate_t: a_{t+1} = a_t + G0(e_{t+1}, a_t, x_{t+1})
                     ga = pw.angle[t]
-                    g_pre, g_a_new = self._new(b, A, 128), self._new(b, A, 64)
-                    K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.extra["w1a_b"], ga.ln, g_pre, g_a_new)
-                    g_a = g_a_new
+                    g_pre = self._new(b, A, 128)
+                    K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.ln, g_pre)
+                    g_a = acc(g_a, g_pre, ga.extra["w1a_b"])  # residual + through the angle block
                     g_x, g_e = angle_scatter(g_pre, g_x, g_e, ga.extra)
                 # BondConv_t: e_{t+1} = e_t + Wo agg(G(e_t, a_t, x_{t+1}) w_i w_j)
                 gp, sv = pw.bond[t], saved_bond[t]
                 g_agg = self._lin(b, g_e, gp.extra["wo"], x_rows=sid)
                 g_pre = self._new(b, A, 128)
                 gw_i, gw_j = self._new(b, A, 64), self._new(b, A, 64)
-                if g_a is None:
-                    g_a = self._zeros(b, A, 64)
-                K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.extra["w1a_b"], gp.w2,
-                                gp.ln, g_pre, g_a, gw_i, gw_j)
+                K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
+                                gw_i, gw_j)
+                g_a = acc(g_a, g_pre, gp.extra["w1a_b"])
                 g_x, g_e = angle_scatter(g_pre, g_x, g_e, gp.extra)
                 K.segment_sum(gw_i, None, b.ptr_is, 1, g_wbg)
                 K.segment_sum(gw_j, b.perm_js, b.ptr_js, 1, g_wbg)

@@ -117,27 +117,29 @@ int chg_segment_sum(const float* data, int32_t width, const int32_t* perm,
                     float* out, int32_t out_ld /* row stride of out, in floats */, void* stream);
 
 /* ---- K5: BondConv message (layers.py:238-249)
- * pre = pij[i][0:128] + pij[j][128:256] + px[c] + ang[a] @ w1a_t;
- * upd = G(pre) * wbg[i] * wbg[j].  save_pre/save_p may be NULL (no backward).     */
-int chg_bond_conv_fwd(const float* pij, const float* px, const float* ang, const float* wbg,
+ * pre = pij[i][0:128] + pij[j][128:256] + px[c] + pa[a], pa = ang @ W1a (chg_linear);
+ * upd = G(pre) * wbg[i] * wbg[j].  save_pre/save_p may be NULL (no backward).
+ * i, j index the rows of pij / wbg (compact bond-graph slots).                      */
+int chg_bond_conv_fwd(const float* pij, const float* px, const float* pa, const float* wbg,
                       const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
-                      int32_t n_angles, const float* w1a_t, const float* w2t,
-                      const float* b2, const float* ln, float* upd, float* save_pre,
-                      float* save_p, void* stream);
+                      int32_t n_angles, const float* w2t, const float* b2, const float* ln,
+                      float* upd, float* save_pre, float* save_p, void* stream);
+/* g_pre[a][128] = dE/dpre; gw_i / gw_j [a][64] = dE/d wbg row contributions.
+ * dE/d ang = g_pre @ W1a is a chg_linear call on g_pre.                             */
 int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg,
                       const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles,
-                      const float* g_agg, const float* w1a, const float* w2, const float* ln,
-                      float* g_pre, float* g_ang, float* gw_i, float* gw_j, void* stream);
+                      const float* g_agg, const float* w2, const float* ln, float* g_pre,
+                      float* gw_i, float* gw_j, void* stream);
 
-/* ---- K6: AngleUpdate (layers.py:348-360): ang_new = ang + G0(pre), no hidden    */
-int chg_angle_update_fwd(const float* pij, const float* px, const float* ang,
+/* ---- K6: AngleUpdate (layers.py:348-360): ang_new = ang + G0(pre), no hidden layer    */
+int chg_angle_update_fwd(const float* pij, const float* px, const float* pa, const float* ang,
                          const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
-                         int32_t n_angles, const float* w1a_t, const float* ln,
-                         float* ang_new, float* save_p, void* stream);
-/* g_ang_in may be NULL (zero).  g_ang_out = g_ang_in + g_pre @ w1a                 */
-int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles,
-                         const float* w1a, const float* ln, float* g_pre, float* g_ang_out,
+                         int32_t n_angles, const float* ln, float* ang_new, float* save_p,
                          void* stream);
+/* g_ang_in may be NULL (zero).  g_pre = dE/dpre; dE/d ang = g_ang_in + g_pre @ W1a
+ * (chg_linear with residual).                                                       */
+int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles,
+                         const float* ln, float* g_pre, void* stream);
 
 /* ---- K7: readout (model.py:497-509) + AtomRef sum (composition_model.py:175-205)
  * h = LN(x); site_e = MLP(h); e_graph[owner] += site_e (fp64); e_ref[owner] +=

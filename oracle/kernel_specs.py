@@ -194,11 +194,11 @@ class SpecKernels:
             out.copy_(acc)
 
     # ---- K5
-    def _bond_pre(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t):
-        return pij[ang_i.long(), :128] + pij[ang_j.long(), 128:] + px[ang_atom.long()] + ang @ w1a_t
+    def _bond_pre(self, pij, px, pa, ang_atom, ang_i, ang_j):
+        return pij[ang_i.long(), :128] + pij[ang_j.long(), 128:] + px[ang_atom.long()] + pa
 
-    def bond_conv_fwd(self, pij, px, ang, wbg, ang_atom, ang_i, ang_j, w1a_t, w2t, b2, ln, upd, save_pre, save_p):
-        pre = self._bond_pre(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t)
+    def bond_conv_fwd(self, pij, px, pa, wbg, ang_atom, ang_i, ang_j, w2t, b2, ln, upd, save_pre, save_p):
+        pre = self._bond_pre(pij, px, pa, ang_atom, ang_i, ang_j)
         h = _silu(pre)
         p = torch.cat([h[:, :64] @ w2t[:, :64], h[:, 64:] @ w2t[:, 64:]], dim=1) + b2
         out, _ = _gate_fwd(p, ln)
@@ -208,7 +208,7 @@ class SpecKernels:
         if save_p is not None:
             save_p.copy_(p)
 
-    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w1a, w2, ln, g_pre, g_ang, gw_i, gw_j):
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j):
         out, saved = _gate_fwd(save_p, ln)
         wi, wj = wbg[ang_i.long()], wbg[ang_j.long()]
         g_upd = g_agg[ang_i.long()]
@@ -216,25 +216,21 @@ class SpecKernels:
         gw_j.copy_(g_upd * out * wi)
         g_p = _gate_bwd(g_upd * wi * wj, saved, ln)
         g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
-        gp = g_h * _dsilu(save_pre)
-        g_pre.copy_(gp)
-        g_ang.add_(gp @ w1a)
+        g_pre.copy_(g_h * _dsilu(save_pre))
 
     # ---- K6
-    def angle_update_fwd(self, pij, px, ang, ang_atom, ang_i, ang_j, w1a_t, ln, ang_new, save_p):
-        p = self._bond_pre(pij, px, ang, ang_atom, ang_i, ang_j, w1a_t)
+    def angle_update_fwd(self, pij, px, pa, ang, ang_atom, ang_i, ang_j, ln, ang_new, save_p):
+        p = self._bond_pre(pij, px, pa, ang_atom, ang_i, ang_j)
         out, _ = _gate_fwd(p, ln)
         ang_new.copy_(out + ang)
         if save_p is not None:
             save_p.copy_(p)
 
-    def angle_update_bwd(self, save_p, g_ang_in, w1a, ln, g_pre, g_ang_out):
+    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre):
         _, saved = _gate_fwd(save_p, ln)
         if g_ang_in is None:
             g_ang_in = torch.zeros_like(save_p[:, :64])
-        gp = _gate_bwd(g_ang_in, saved, ln)
-        g_pre.copy_(gp)
-        g_ang_out.copy_(g_ang_in + gp @ w1a)
+        g_pre.copy_(_gate_bwd(g_ang_in, saved, ln))
 
     # ---- K7
     def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph, e_ref, g_x):

@@ -21,10 +21,10 @@ OUT_ARGS = {
     "atom_conv_fwd": [9, 10],
     "atom_conv_bwd": [10, 11],
     "segment_sum": [4],
-    "bond_conv_fwd": [11, 12, 13],
-    "bond_conv_bwd": [9, 10, 11, 12],
+    "bond_conv_fwd": [10, 11, 12],
+    "bond_conv_bwd": [8, 9, 10],
     "angle_update_fwd": [8, 9],
-    "angle_update_bwd": [4, 5],
+    "angle_update_bwd": [3],
     "readout": [10, 11, 12, 13, 14],
     "magmom": [3],
     "force_virial": [10, 11],
