@@ -66,6 +66,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.chg_abi_version.argtypes = []
     lib.chg_launch_count.restype = c_int64
     lib.chg_launch_count.argtypes = []
+    lib.chg_set_option.restype = c_int32
+    lib.chg_set_option.argtypes = [c_char_p, c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32
@@ -104,6 +106,11 @@ class CudaKernels:
         for t in tensors:
             if t is not None and (not t.is_cuda or not t.is_contiguous()):
                 raise ChgnetB200Error("kernel arguments must be contiguous CUDA tensors")
+
+    def set_option(self, name: str, value: int) -> None:
+        """A/B switches: 'linear_impl' / 'gated_impl', 1 = tcgen05, 0 = FFMA."""
+        if self.lib.chg_set_option(name.encode(), int(value)) != 0:
+            raise ChgnetB200Error(self.lib.chg_last_error().decode())
 
     @property
     def launches(self) -> int:

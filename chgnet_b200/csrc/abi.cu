@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -30,6 +32,38 @@ int sm_count() {
   return n;
 }
 }  // namespace chg
+
+namespace chg {
+namespace {
+// implementation switches: 1 = tcgen05 (tensor memory), 0 = FFMA.  Defaults follow the measured
+// A/B (profiles/): the dense feature-mixing GEMM runs on tcgen05; the AtomConv/BondConv tile
+// kernels default to FFMA until their tcgen05 version is warp-specialised.
+std::atomic<int> g_linear_impl{-1}, g_gated_impl{-1};
+int env_default(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  return (e[0] == 't' || e[0] == '1') ? 1 : 0;
+}
+}  // namespace
+int linear_impl() {
+  int v = g_linear_impl.load();
+  if (v < 0) { v = env_default("CHG_LINEAR_IMPL", 1); g_linear_impl.store(v); }
+  return v;
+}
+int gated_impl() {
+  int v = g_gated_impl.load();
+  if (v < 0) { v = env_default("CHG_GATED_IMPL", 0); g_gated_impl.store(v); }
+  return v;
+}
+}  // namespace chg
+
+extern "C" int chg_set_option(const char* name, int32_t value) {
+  if (name == nullptr) return CHG_ERR_ARG;
+  if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value ? 1 : 0); return CHG_OK; }
+  if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value ? 1 : 0); return CHG_OK; }
+  chg::set_error("chg_set_option: unknown option %s", name);
+  return CHG_ERR_ARG;
+}
 
 extern "C" const char* chg_last_error(void) { return chg::g_err; }
 extern "C" int chg_abi_version(void) { return 1; }

@@ -11,6 +11,8 @@ namespace chg {
 void set_error(const char* fmt, ...);
 void count_launch();
 int sm_count();
+int linear_impl();  // 1 = tcgen05, 0 = FFMA
+int gated_impl();
 
 #define CHG_CHECK_ARG(cond, msg)                \
   do {                                          \

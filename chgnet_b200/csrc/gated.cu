@@ -406,16 +406,6 @@ int launch_bwd(const BwdArgs& a, cudaStream_t stream) {
   CHG_LAUNCH_END();
 }
 
-// 1 = tcgen05 (default) for the kernels that contain a GEMM, 0 = FFMA (CHG_GATED_IMPL=ffma)
-int gated_impl() {
-  static int impl = -1;
-  if (impl < 0) {
-    const char* e = getenv("CHG_GATED_IMPL");
-    impl = (e != nullptr && e[0] == 'f') ? 0 : 1;
-  }
-  return impl;
-}
-
 }  // namespace
 }  // namespace chg
 

@@ -127,15 +127,6 @@ int launch_linear(const float* x, const int32_t* x_rows, int m, int k, const flo
 int linear_tc(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
               const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
 
-// 1 = tcgen05 3xTF32 (default), 0 = FFMA; CHG_LINEAR_IMPL=ffma selects the latter for A/B runs
-static int linear_impl() {
-  static int impl = -1;
-  if (impl < 0) {
-    const char* e = getenv("CHG_LINEAR_IMPL");
-    impl = (e != nullptr && e[0] == 'f') ? 0 : 1;
-  }
-  return impl;
-}
 }  // namespace chg
 
 using namespace chg;

@@ -138,9 +138,11 @@ extern "C" int chg_segment_sum(const float* data, int32_t width, const int32_t* 
   // lane-groups per output row: enough to keep >= ~8 rows per group for long segments and to
   // fill the machine when there are few segments (n_items is only a hint, any value is correct)
   const int avg = n_items / n_rows;
-  const int max_s = width == 64 ? 8 : 8;
+  const int groups = 256 / (width / 4);  // lane-groups per CTA
+  const int resident = sm_count() * 8;   // CTAs of one wave
   int S = 1;
-  while (S < max_s && avg >= 16 * S && (long long)n_rows * (width / 4) * S < (long long)sm_count() * 4096) S *= 2;
+  // grow S while segments stay long enough AND all CTAs still fit in a single wave
+  while (S < 8 && avg >= 16 * S && ((long long)n_rows * (2 * S) + groups - 1) / groups <= resident) S *= 2;
   cudaStream_t st = as_stream(stream);
 #define CHG_SEG(W_, S_) launch_segsum<W_, S_>(data, perm, ptr, n_rows, accumulate, out, out_ld, st)
   if (width == 64) {

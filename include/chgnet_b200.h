@@ -42,6 +42,10 @@ const char* chg_last_error(void);
 int chg_abi_version(void);
 /* number of kernel launches issued by this library since load (host counter) */
 int64_t chg_launch_count(void);
+/* implementation switches for A/B measurements: name in {"linear_impl", "gated_impl"},
+ * value 1 = tcgen05 / tensor-memory kernels, 0 = FFMA kernels (same results, same ABI).
+ * Defaults: linear_impl = 1, gated_impl = 0 (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = tc|ffma). */
+int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */
 int chg_embed_atoms(const int32_t* z, const float* emb, int32_t n_atoms, float* x, void* stream);

@@ -38,20 +38,28 @@ def recorded(weights030):
     return _record(weights030, graphs, need_grad=True, need_magmom=True, need_atom_fea=True, need_crystal_fea=True)
 
 
-def test_every_kernel_matches_its_spec(recorded):
+@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 0), (0, 1)], ids=["linear=tcgen05,gated=ffma", "linear=ffma,gated=tcgen05"])
+def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
+    """Both implementations of every entry point (tcgen05 3xTF32 and FFMA) against the spec."""
     from chgnet_b200._lib import CudaKernels
 
     K = CudaKernels()
-    seen = {}
-    for name, snap, outs in recorded:
-        args = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
-        getattr(K, name)(*args)
-        torch.cuda.synchronize()
-        for idx, want in outs.items():
-            err = _close(name, idx, args[idx], want)
-            seen[name] = max(seen.get(name, 0.0), err)
-    assert set(seen) == set(__import__("kernel_replay").OUT_ARGS), sorted(seen)
-    print({k: f"{v:.2e}" for k, v in seen.items()})
+    K.set_option("linear_impl", linear_impl)
+    K.set_option("gated_impl", gated_impl)
+    try:
+        seen = {}
+        for name, snap, outs in recorded:
+            args = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
+            getattr(K, name)(*args)
+            torch.cuda.synchronize()
+            for idx, want in outs.items():
+                err = _close(name, idx, args[idx], want)
+                seen[name] = max(seen.get(name, 0.0), err)
+        assert set(seen) == set(__import__("kernel_replay").OUT_ARGS), sorted(seen)
+        print({k: f"{v:.2e}" for k, v in seen.items()})
+    finally:
+        K.set_option("linear_impl", 1)
+        K.set_option("gated_impl", 0)
 
 
 def test_kernels_without_layernorm_and_small_basis(weights030):

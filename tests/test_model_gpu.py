@@ -47,6 +47,22 @@ def test_limno2_known_answers(model, limno2_graph, golden):
     print({k: f"{_maxabs(out[k], golden[f'limno2.oracle64.{k}']):.2e}" for k in TOL})
 
 
+@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 1), (0, 0)], ids=["all-tcgen05", "all-ffma"])
+def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, linear_impl, gated_impl):
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    K.set_option("linear_impl", linear_impl)
+    K.set_option("gated_impl", gated_impl)
+    try:
+        out = model.predict_graph(limno2_graph)
+        for k, tol in TOL.items():
+            assert _maxabs(out[k], golden[f"limno2.oracle64.{k}"]) < tol, k
+    finally:
+        K.set_option("linear_impl", 1)
+        K.set_option("gated_impl", 0)
+
+
 def test_random_batch_vs_reference_golden(model, golden):
     graphs = graphgen.random_graphs(4, 12, 20, 7000)
     preds = model.predict_graph(graphs, task="efsm", batch_size=4)
