@@ -246,25 +246,41 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
   const float wf = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
   const int ml = lane < nb ? lane : 0;
   const float inv_sqrt_pi = 0.5641895835477563f;
-  for (int a = warp; a < n_angles; a += n_warps) {
-    const int di = ang_di[a], dj = ang_dj[a];
-    float ri[3], rj[3];
-    const float u = angle_cos(rhat, di, dj, ri, rj);
-    const float th = acosf(u);
-    const float ga = g_a0[(size_t)a * 64 + lane], gb = g_a0[(size_t)a * 64 + lane + 32];
-    float gf = 0.f;  // lane m: dE/d f_m
-    for (int n = 0; n < 32; ++n) {
-      gf = fmaf(__shfl_sync(0xffffffffu, ga, n), s_w[n * nb + ml], gf);
-      gf = fmaf(__shfl_sync(0xffffffffu, gb, n), s_w[(n + 32) * nb + ml], gf);
+  // A warp owns CHUNK consecutive angles.  Angles are sorted by bond i, so the directed edge
+  // di repeats in runs: its contribution is accumulated in registers and flushed with one
+  // atomic per component when di changes (cuts same-address fp64 atomics by the run length).
+  constexpr int CHUNK = 16;
+  const int n_chunks = (n_angles + CHUNK - 1) / CHUNK;
+  for (int ch = warp; ch < n_chunks; ch += n_warps) {
+    const int a_beg = ch * CHUNK, a_end = min(a_beg + CHUNK, n_angles);
+    int cur_di = -1;
+    double acc_i = 0.0;  // lanes 0..2: pending sum for g_rhat[cur_di][lane]
+    for (int a = a_beg; a < a_end; ++a) {
+      const int di = ang_di[a], dj = ang_dj[a];
+      float ri[3], rj[3];
+      const float u = angle_cos(rhat, di, dj, ri, rj);
+      const float th = acosf(u);
+      const float ga = g_a0[(size_t)a * 64 + lane], gb = g_a0[(size_t)a * 64 + lane + 32];
+      float gf = 0.f;  // lane m: dE/d f_m
+      for (int n = 0; n < 32; ++n) {
+        gf = fmaf(__shfl_sync(0xffffffffu, ga, n), s_w[n * nb + ml], gf);
+        gf = fmaf(__shfl_sync(0xffffffffu, gb, n), s_w[(n + 32) * nb + ml], gf);
+      }
+      float g_th = 0.f;
+      if (is_sin) g_th = gf * wf * cosf(wf * th);
+      else if (is_cos) g_th = -gf * wf * sinf(wf * th);
+      g_th = sum32(g_th) * inv_sqrt_pi;
+      // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
+      const float g_u = -g_th / sqrtf(1.f - u * u) * (1.f - 1e-6f);
+      if (di != cur_di) {
+        if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
+        cur_di = di;
+        acc_i = 0.0;
+      }
+      if (lane < 3) acc_i += (double)(g_u * rj[lane]);
+      else if (lane < 6) atomicAdd(g_rhat + (size_t)dj * 3 + (lane - 3), (double)(g_u * ri[lane - 3]));
     }
-    float g_th = 0.f;
-    if (is_sin) g_th = gf * wf * cosf(wf * th);
-    else if (is_cos) g_th = -gf * wf * sinf(wf * th);
-    g_th = sum32(g_th) * inv_sqrt_pi;
-    // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
-    const float g_u = -g_th / sqrtf(1.f - u * u) * (1.f - 1e-6f);
-    if (lane < 3) atomicAdd(g_rhat + (size_t)di * 3 + lane, (double)(g_u * rj[lane]));
-    else if (lane < 6) atomicAdd(g_rhat + (size_t)dj * 3 + (lane - 3), (double)(g_u * ri[lane - 3]));
+    if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
   }
 }
 
@@ -422,7 +438,7 @@ extern "C" int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, con
   if (n_angles == 0) return CHG_OK;
   CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && w && g_a0 && g_rhat, "null pointer");
   const int smem = (2 * n_freq + 1) * 64 * 4;
-  angle_basis_bwd_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles, freq,
+  angle_basis_bwd_kernel<<<warp_grid((n_angles + 15) / 16), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles, freq,
                                                                                 n_freq, w, g_a0, g_rhat);
   CHG_LAUNCH_END();
 }
