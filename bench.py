@@ -186,17 +186,33 @@ def run_reference(args, rank: int, world: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------
+class L2Flush:
+    """Evicts everything of ours from the 126 MB L2 between timed iterations: writes a 256 MiB
+    buffer (the rule of the task statement), then streams a second 256 MiB buffer through with a
+    read so that the cache is left holding CLEAN lines — otherwise the timed kernel also pays
+    for the write-back of the flush buffer's dirty lines."""
+
+    def __init__(self, dev) -> None:
+        self.w = torch.empty(L2_FLUSH_BYTES // 4, device=dev)
+        self.r = torch.zeros(L2_FLUSH_BYTES // 4, device=dev)
+        self.sink = torch.zeros((), device=dev)
+
+    def __call__(self) -> None:
+        self.w.zero_()
+        self.sink.copy_(self.r.sum())
+
+
 def time_scatter_kernel(K, batch, n_iter: int = 20):
     """AtomConv scatter-reduce alone: CUDA events on the launching stream, L2 flushed."""
     dev = batch.z.device
     msg = torch.randn(batch.n_edges, 64, device=dev)
     out = torch.empty(batch.n_atoms, 64, device=dev)
-    flush = torch.empty(L2_FLUSH_BYTES // 4, device=dev)
+    flush = L2Flush(dev)
     for _ in range(3):
         K.segment_sum(msg, None, batch.ptr_c, 0, out)
     total = 0.0
     for _ in range(n_iter):
-        flush.zero_()
+        flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         K.segment_sum(msg, None, batch.ptr_c, 0, out)
@@ -258,7 +274,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     c = counts(graphs)
     engine = model._get_engine()
     K = engine.K
-    flush = torch.empty(L2_FLUSH_BYTES // 4, device=dev)
+    flush = L2Flush(dev)
 
     def barrier():
         if world > 1:
@@ -279,7 +295,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         return out.energy, out.force.to(torch.float32), stress
 
     for _ in range(max(args.warmup, 3)):
-        flush.zero_()
+        flush()
         step_resident()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -288,7 +304,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     elapsed_ms = 0.0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
-        flush.zero_()
+        flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         step_resident()
@@ -315,7 +331,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        flush.zero_()
+        flush()
         step_e2e()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -407,7 +423,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "task": "efs", "per_gpu": c, "weights": "CHGNet 0.3.0",
-                   "l2": "256 MiB buffer written between timed iterations", "parallelism": f"graph-sharded x{world}"},
+                   "l2": "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations", "parallelism": f"graph-sharded x{world}"},
         "e2e": {"value": total_graphs / (e2e_ms_per_step * 1e-3), "unit": "structures/s",
                 "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "CHGNet.predict_graph(list[CrystalGraph] on host, task='efs')", "breakdown": breakdown},

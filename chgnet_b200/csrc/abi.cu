@@ -59,7 +59,7 @@ int gated_impl() {
 
 extern "C" int chg_set_option(const char* name, int32_t value) {
   if (name == nullptr) return CHG_ERR_ARG;
-  if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value ? 1 : 0); return CHG_OK; }
+  if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
   if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value ? 1 : 0); return CHG_OK; }
   chg::set_error("chg_set_option: unknown option %s", name);
   return CHG_ERR_ARG;

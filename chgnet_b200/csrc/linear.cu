@@ -126,6 +126,8 @@ int launch_linear(const float* x, const int32_t* x_rows, int m, int k, const flo
 
 int linear_tc(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
               const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
+int linear_tma(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
+               const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
 
 }  // namespace chg
 
@@ -139,7 +141,10 @@ extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int3
   CHG_CHECK_ARG(n_out > 0 && n_out % 64 == 0, "n_out must be a positive multiple of 64");
   if (m == 0) return CHG_OK;
   CHG_CHECK_ARG(x && wt && y, "null pointer");
-  if (linear_impl() == 1) return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
+  // tcgen05 paths: TMA-fed kernel for k <= 128 (impl 1), register-staged kernel for k = 256 or impl 2
+  if (linear_impl() == 1 && k <= 128)
+    return linear_tma(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
+  if (linear_impl() >= 1) return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (n_out % 128 == 0 && k <= 128)
     return launch_linear<128>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   return launch_linear<64>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));

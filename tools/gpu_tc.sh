@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/linear_ab.py 2>&1 | tee gpurun_out/linear_ab_tc.log
-CHG_LINEAR_IMPL=ffma timeout 120 python tools/linear_ab.py 2>&1 | tee gpurun_out/linear_ab_ffma.log
-timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -15
+timeout 200 python tools/linear_ab.py 2>&1 | tee gpurun_out/linear_ab.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -5
