@@ -130,36 +130,48 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
                 compact_bonds: bool = True) -> DeviceBatch:
     device = torch.device(device)
     B = len(graphs)
-    n_at = [int(g.atomic_number.shape[0]) for g in graphs]
-    ag_l = [g.atom_graph.reshape(-1, 2) for g in graphs]  # model.py:841-843
-    n_ed = [int(a.shape[0]) for a in ag_l]
-    n_eu = [int(g.undirected2directed.shape[0]) for g in graphs]
-    bg_l = [g.bond_graph.reshape(-1, 5) for g in graphs]
-    n_an = [int(b.shape[0]) for b in bg_l]
+    # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
+    ag_l, bg_l = [], []
+    for g in graphs:
+        ag, bg = g.atom_graph, g.bond_graph
+        if ag.dim() != 2:  # structure with every atom isolated (model.py:841-843)
+            ag = ag.reshape(0, 2)
+        if bg.dim() != 2:
+            bg = bg.reshape(0, 5)
+        ag_l.append(ag)
+        bg_l.append(bg)
+    n_at = [g.atomic_number.shape[0] for g in graphs]
+    n_ed = [a.shape[0] for a in ag_l]
+    n_eu = [g.undirected2directed.shape[0] for g in graphs]
+    n_an = [b.shape[0] for b in bg_l]
     N, Ed, Eu, A = sum(n_at), sum(n_ed), sum(n_eu), sum(n_an)
     for g, e_d, e_u in zip(graphs, n_ed, n_eu):
-        if e_d != 2 * e_u or int(g.directed2undirected.shape[0]) != e_d:
+        if e_d != 2 * e_u or g.directed2undirected.shape[0] != e_d:
             raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
 
     src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
     host_src = src_dev.type == "cpu"
     pin = host_src and device.type == "cuda"
 
+    # (name, per-graph tensors, inner width, total rows)
     int_fields = [
-        ("z", [g.atomic_number.reshape(-1) for g in graphs], N),
-        ("ag", [a.reshape(-1) for a in ag_l], 2 * Ed),
-        ("d2u", [g.directed2undirected.reshape(-1) for g in graphs], Ed),
-        ("u2d", [g.undirected2directed.reshape(-1) for g in graphs], Eu),
-        ("bg", [b.reshape(-1) for b in bg_l], 5 * A),
+        ("z", [g.atomic_number for g in graphs], 1, N),
+        ("ag", ag_l, 2, Ed),
+        ("d2u", [g.directed2undirected for g in graphs], 1, Ed),
+        ("u2d", [g.undirected2directed for g in graphs], 1, Eu),
+        ("bg", bg_l, 5, A),
     ]
     flt_fields = [
-        ("frac", [g.atom_frac_coord.detach().reshape(-1) for g in graphs], 3 * N),
-        ("image", [g.neighbor_image.detach().reshape(-1) for g in graphs], 3 * Ed),
-        ("lattice", [g.lattice.detach().reshape(-1) for g in graphs], 9 * B),
+        ("frac", [g.atom_frac_coord for g in graphs], 3, N),
+        ("image", [g.neighbor_image for g in graphs], 3, Ed),
+        ("lattice", [g.lattice for g in graphs], 3, 3 * B),
     ]
     counts_host = np.array([n_at, n_ed, n_eu, n_an], dtype=np.int32).reshape(-1)  # [4*B]
-    n_int = sum(f[2] for f in int_fields) + counts_host.size
-    n_flt = sum(f[2] for f in flt_fields)
+    n_int = sum(f[2] * f[3] for f in int_fields) + counts_host.size
+    n_flt = sum(f[2] * f[3] for f in flt_fields)
+
+    def as_np(t: Tensor) -> np.ndarray:
+        return t.detach().numpy() if t.requires_grad else t.numpy()
 
     def stage(fields, total, dtype, tail=None):
         """Concatenate all parts into one staging buffer and ship it with one copy.  Host
@@ -170,9 +182,12 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         if host_src:
             buf = _staging_buffer(total, dtype, pin)
             host = buf.numpy()
-            for name, parts, size in fields:
+            for name, parts, width, rows in fields:
+                size = width * rows
                 if size:
-                    np.concatenate([p.numpy() for p in parts], out=host[off : off + size], casting="unsafe")
+                    dst = host[off : off + size]
+                    np.concatenate([as_np(p) for p in parts], axis=0,
+                                   out=dst if width == 1 else dst.reshape(rows, width), casting="unsafe")
                 views[name] = (off, size)
                 off += size
             if tail is not None:
@@ -182,9 +197,10 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
             _mark_staging_in_flight(dtype, pin, device)
             return dbuf, views, host
         buf = torch.empty(total, dtype=dtype, device=src_dev)
-        for name, parts, size in fields:
+        for name, parts, width, rows in fields:
+            size = width * rows
             if size:
-                torch.cat([p.to(dtype) for p in parts], out=buf[off : off + size])
+                torch.cat([p.detach().reshape(-1).to(dtype) for p in parts], out=buf[off : off + size])
             views[name] = (off, size)
             off += size
         if tail is not None:

@@ -42,7 +42,8 @@ std::atomic<int> g_linear_impl{-1}, g_gated_impl{-1};
 int env_default(const char* name, int dflt) {
   const char* e = getenv(name);
   if (e == nullptr || e[0] == 0) return dflt;
-  return (e[0] == 't' || e[0] == '1') ? 1 : 0;
+  if (e[0] >= '0' && e[0] <= '9') return e[0] - '0';
+  return e[0] == 't' ? 1 : 0;
 }
 }  // namespace
 int linear_impl() {
@@ -60,7 +61,7 @@ int gated_impl() {
 extern "C" int chg_set_option(const char* name, int32_t value) {
   if (name == nullptr) return CHG_ERR_ARG;
   if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
-  if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value ? 1 : 0); return CHG_OK; }
+  if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
   chg::set_error("chg_set_option: unknown option %s", name);
   return CHG_ERR_ARG;
 }

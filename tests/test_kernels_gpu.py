@@ -38,7 +38,8 @@ def recorded(weights030):
     return _record(weights030, graphs, need_grad=True, need_magmom=True, need_atom_fea=True, need_crystal_fea=True)
 
 
-@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 0), (0, 1)], ids=["linear=tcgen05,gated=ffma", "linear=ffma,gated=tcgen05"])
+@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 0), (0, 1), (2, 2)],
+                         ids=["linear=tcgen05+tma,gated=ffma8x8", "linear=ffma,gated=tcgen05", "linear=tcgen05,gated=ffma4x8"])
 def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
     """Both implementations of every entry point (tcgen05 3xTF32 and FFMA) against the spec."""
     from chgnet_b200._lib import CudaKernels

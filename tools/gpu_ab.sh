@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the gated implementations on the bench workloads (no CPU baseline leg)
 mkdir -p gpurun_out
-for impl in ffma tc; do
+for impl in 0 2 1; do
 for wl in c2 c4; do
   CHG_GATED_IMPL=$impl timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${wl}_gated_${impl}.json 2> gpurun_out/bench_ab.err
   python - <<PY
