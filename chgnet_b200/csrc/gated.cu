@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
 }
 
 // =====================================================================================
-// AtomConv / BondConv, second generation: 128-row tiles, 8x8 register tiles.
+// AtomConv / BondConv, 8x8-tile variant (gated_impl = 2): 128-row tiles, 8x8 register tiles.
 //
 // ncu on the 4x8-tile kernels above showed them bound by shared-memory OPERAND DELIVERY, not by
 // the FMA pipe: every FMA needed 2 bytes from shared memory (an LDS.128 occupies the 128 B/clk
@@ -380,6 +380,9 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
 // gate) so that a thread's 8 rows x 8 columns share their A operand: (8 + 8) floats per 64 FMAs
 // = 1 byte per FMA.  The accumulators go back through the shared tile, and the epilogue runs in
 // the 16-lane-per-row layout (LayerNorm by shuffles, coalesced stores) as before.
+// Measured (B200, c4): 3-20 % SLOWER than the 4x8 kernels above — the extra tile round trip,
+// two more block barriers and the lower occupancy of the reverse kernel cost more than the
+// operand traffic saves; the default stays on the 4x8 kernels.
 // =====================================================================================
 constexpr int TM2 = 128;
 
@@ -772,9 +775,11 @@ extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && w2t && b2 && msg, "null pointer");
   FwdArgs a{pcn, pe, nullptr, nullptr, wag, center, nbr, d2u, n_edges, w2t, b2, ln, msg, nullptr, save_p};
   if (gated_impl() == 1) return atom_conv_fwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) return launch_fwd<ATOM>(a, as_stream(stream));  // first-generation 4x8 tiles
-  static int slots = 0;
-  return launch2(gated2_fwd_kernel<ATOM>, a, slots, as_stream(stream));
+  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+    static int slots = 0;
+    return launch2(gated2_fwd_kernel<ATOM>, a, slots, as_stream(stream));
+  }
+  return launch_fwd<ATOM>(a, as_stream(stream));
 }
 
 extern "C" int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag, const int32_t* center,
@@ -786,9 +791,11 @@ extern "C" int chg_atom_conv_bwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && save_p && g_agg && w2 && g_pre && g_w, "null pointer");
   BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, w2, ln, g_pre, g_w, nullptr};
   if (gated_impl() == 1) return atom_conv_bwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) return launch_bwd<ATOM>(a, as_stream(stream));
-  static int slots = 0;
-  return launch2(gated2_bwd_kernel<ATOM>, a, slots, as_stream(stream));
+  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+    static int slots = 0;
+    return launch2(gated2_bwd_kernel<ATOM>, a, slots, as_stream(stream));
+  }
+  return launch_bwd<ATOM>(a, as_stream(stream));
 }
 
 extern "C" int chg_bond_conv_fwd(const float* pij, const float* px, const float* pa, const float* wbg,
@@ -800,9 +807,11 @@ extern "C" int chg_bond_conv_fwd(const float* pij, const float* px, const float*
   CHG_CHECK_ARG(pij && px && pa && wbg && ang_atom && ang_i && ang_j && w2t && b2 && upd, "null pointer");
   FwdArgs a{pij, px, pa, nullptr, wbg, ang_i, ang_j, ang_atom, n_angles, w2t, b2, ln, upd, save_pre, save_p};
   if (gated_impl() == 1) return bond_conv_fwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) return launch_fwd<BOND>(a, as_stream(stream));
-  static int slots = 0;
-  return launch2(gated2_fwd_kernel<BOND>, a, slots, as_stream(stream));
+  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+    static int slots = 0;
+    return launch2(gated2_fwd_kernel<BOND>, a, slots, as_stream(stream));
+  }
+  return launch_fwd<BOND>(a, as_stream(stream));
 }
 
 extern "C" int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg, const int32_t* ang_i,
@@ -814,9 +823,11 @@ extern "C" int chg_bond_conv_bwd(const float* save_pre, const float* save_p, con
   BwdArgs a{nullptr, nullptr, wbg, ang_i, ang_j, nullptr, n_angles, save_pre, save_p, g_agg, w2, ln,
             g_pre, gw_i, gw_j};
   if (gated_impl() == 1) return bond_conv_bwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) return launch_bwd<BOND>(a, as_stream(stream));
-  static int slots = 0;
-  return launch2(gated2_bwd_kernel<BOND>, a, slots, as_stream(stream));
+  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+    static int slots = 0;
+    return launch2(gated2_bwd_kernel<BOND>, a, slots, as_stream(stream));
+  }
+  return launch_bwd<BOND>(a, as_stream(stream));
 }
 
 extern "C" int chg_angle_update_fwd(const float* pij, const float* px, const float* pa, const float* ang,

@@ -141,8 +141,9 @@ extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int3
   CHG_CHECK_ARG(n_out > 0 && n_out % 64 == 0, "n_out must be a positive multiple of 64");
   if (m == 0) return CHG_OK;
   CHG_CHECK_ARG(x && wt && y, "null pointer");
-  // tcgen05 paths: TMA-fed kernel for k <= 128 (impl 1), register-staged kernel for k = 256 or impl 2
-  if (linear_impl() == 1 && k <= 128)
+  // tcgen05 paths: 1 = register-staged kernel (default: fastest over the whole step), 2 = TMA-fed
+  // kernel (k <= 128; wins only on the largest calls)
+  if (linear_impl() == 2 && k <= 128)
     return linear_tma(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (linear_impl() >= 1) return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (n_out % 128 == 0 && k <= 128)

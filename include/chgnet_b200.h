@@ -42,9 +42,10 @@ const char* chg_last_error(void);
 int chg_abi_version(void);
 /* number of kernel launches issued by this library since load (host counter) */
 int64_t chg_launch_count(void);
-/* implementation switches for A/B measurements: name in {"linear_impl", "gated_impl"},
- * value 1 = tcgen05 / tensor-memory kernels, 0 = FFMA kernels (same results, same ABI).
- * Defaults: linear_impl = 1, gated_impl = 0 (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = tc|ffma). */
+/* implementation switches for A/B measurements (same results, same ABI):
+ *   "linear_impl": 0 FFMA, 1 tcgen05 register-staged (default), 2 tcgen05 + TMA row copies
+ *   "gated_impl" : 0 FFMA 4x8 tiles (default), 1 tcgen05, 2 FFMA 8x8 tiles
+ * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0|1|2 set the defaults).                      */
 int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */

@@ -12,7 +12,7 @@ from chgnet_b200._lib import CudaKernels
 m = CHGNet.from_file("tests/golden/chgnet_0.3.0_weights.npz", version="0.3.0").to("cuda")
 gs = graphgen.random_graphs(2, 8, 12, 9300)
 K = CudaKernels()
-for lin, gat in ((1, 0), (2, 1), (0, 0)):
+for lin, gat in ((1, 0), (2, 1), (0, 2)):
     K.set_option("linear_impl", lin); K.set_option("gated_impl", gat)
     out = m.predict_graph(gs, task="efsm", return_site_energies=True, return_crystal_feas=True)
     torch.cuda.synchronize()
