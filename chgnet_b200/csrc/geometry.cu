@@ -96,33 +96,59 @@ bond_basis_embed_kernel(const float* __restrict__ dist, const int32_t* __restric
   const float f_bg = lane < R ? freq_bg[lane] : 0.f;
   const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
   const float inv_ag = 1.f / rc_ag, inv_bg = 1.f / rc_bg;  // basis.py:108 multiplies by 1/cutoff
-  for (int u = warp; u < n_bonds; u += n_warps) {
-    const float d = dist[u2d[u]];
-    const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
-    // basis.py:110: norm * sin(freq * d_scaled) / d * envelope
-    const float b_ag = lane < R ? ea.env * (nrm_ag * sinf(f_ag * (d * inv_ag)) / d) : 0.f;
-    const float b_bg = lane < R ? eb.env * (nrm_bg * sinf(f_bg * (d * inv_bg)) / d) : 0.f;
-    float o0a = 0.f, o0b = 0.f, o1a = 0.f, o1b = 0.f, o2a = 0.f, o2b = 0.f;
-    const bool bg_live = eb.env != 0.f || !(d == d);  // warp-uniform; NaN propagates
+  // IT bonds per warp iteration: the weight rows read from shared memory are reused IT times and
+  // the IT x 6 accumulators give the FMA pipe independent work
+  constexpr int IT = 4;
+  for (int u0 = warp * IT; u0 < n_bonds; u0 += n_warps * IT) {
+    float b_ag[IT], b_bg[IT];
+    bool bg_live = false;  // warp-uniform
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      const float d = dist[u2d[min(u0 + q, n_bonds - 1)]];
+      const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
+      // basis.py:110: norm * sin(freq * d_scaled) / d * envelope
+      b_ag[q] = lane < R ? ea.env * (nrm_ag * sinf(f_ag * (d * inv_ag)) / d) : 0.f;
+      b_bg[q] = lane < R ? eb.env * (nrm_bg * sinf(f_bg * (d * inv_bg)) / d) : 0.f;
+      bg_live = bg_live || eb.env != 0.f || !(d == d);  // NaN propagates
+    }
+    float o[IT][6];
+#pragma unroll
+    for (int q = 0; q < IT; ++q)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[q][j] = 0.f;
     for (int k = 0; k < R; ++k) {
-      const float ba = __shfl_sync(0xffffffffu, b_ag, k);
       const float* w = s_w + k * 64;
-      o0a = fmaf(ba, w[lane], o0a);
-      o0b = fmaf(ba, w[lane + 32], o0b);
-      o1a = fmaf(ba, w[R * 64 + lane], o1a);
-      o1b = fmaf(ba, w[R * 64 + lane + 32], o1b);
+      const float w0a = w[lane], w0b = w[lane + 32], w1a = w[R * 64 + lane], w1b = w[R * 64 + lane + 32];
+#pragma unroll
+      for (int q = 0; q < IT; ++q) {
+        const float ba = __shfl_sync(0xffffffffu, b_ag[q], k);
+        o[q][0] = fmaf(ba, w0a, o[q][0]);
+        o[q][1] = fmaf(ba, w0b, o[q][1]);
+        o[q][2] = fmaf(ba, w1a, o[q][2]);
+        o[q][3] = fmaf(ba, w1b, o[q][3]);
+      }
       if (bg_live) {
-        const float bb = __shfl_sync(0xffffffffu, b_bg, k);
-        o2a = fmaf(bb, w[2 * R * 64 + lane], o2a);
-        o2b = fmaf(bb, w[2 * R * 64 + lane + 32], o2b);
+        const float w2a = w[2 * R * 64 + lane], w2b = w[2 * R * 64 + lane + 32];
+#pragma unroll
+        for (int q = 0; q < IT; ++q) {
+          const float bb = __shfl_sync(0xffffffffu, b_bg[q], k);
+          o[q][4] = fmaf(bb, w2a, o[q][4]);
+          o[q][5] = fmaf(bb, w2b, o[q][5]);
+        }
       }
     }
-    float* r0 = e0 + (size_t)u * 64;
-    float* r1 = wag + (size_t)u * 64;
-    float* r2 = wbg + (size_t)u * 64;
-    r0[lane] = o0a; r0[lane + 32] = o0b;
-    r1[lane] = o1a; r1[lane + 32] = o1b;
-    r2[lane] = o2a; r2[lane + 32] = o2b;
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      const int u = u0 + q;
+      if (u < n_bonds) {
+        float* r0 = e0 + (size_t)u * 64;
+        float* r1 = wag + (size_t)u * 64;
+        float* r2 = wbg + (size_t)u * 64;
+        r0[lane] = o[q][0]; r0[lane + 32] = o[q][1];
+        r1[lane] = o[q][2]; r1[lane + 32] = o[q][3];
+        r2[lane] = o[q][4]; r2[lane + 32] = o[q][5];
+      }
+    }
   }
 }
 
@@ -141,47 +167,68 @@ bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict_
   const int kl = lane < R ? lane : 0;
   const float f_ag = freq_ag[kl], f_bg = freq_bg[kl];
   const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
-  for (int u = warp; u < n_bonds; u += n_warps) {
-    const float d = dist[u2d[u]];
-    const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
-    const float* q0 = g_e0 + (size_t)u * 64;
-    const float* q1 = g_wag + (size_t)u * 64;
-    const float* q2 = g_wbg + (size_t)u * 64;
-    const float a0 = q0[lane], a1 = q0[lane + 32], b0 = q1[lane], b1 = q1[lane + 32];
-    const float c0 = q2[lane], c1 = q2[lane + 32];
-    const bool bg_live = eb.env != 0.f || eb.denv != 0.f || !(d == d);
+  constexpr int IT = 2;  // bonds per warp iteration
+  for (int u0 = warp * IT; u0 < n_bonds; u0 += n_warps * IT) {
+    float d[IT], a0[IT], a1[IT], b0[IT], b1[IT], c0[IT], c1[IT];
+    Envelope ea[IT], eb[IT];
+    bool bg_live = false;
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      const int u = min(u0 + q, n_bonds - 1);
+      d[q] = dist[u2d[u]];
+      ea[q] = envelope(d[q], rc_ag, p);
+      eb[q] = envelope(d[q], rc_bg, p);
+      const float* q0 = g_e0 + (size_t)u * 64;
+      const float* q1 = g_wag + (size_t)u * 64;
+      const float* q2 = g_wbg + (size_t)u * 64;
+      a0[q] = q0[lane]; a1[q] = q0[lane + 32];
+      b0[q] = q1[lane]; b1[q] = q1[lane + 32];
+      c0[q] = q2[lane]; c1[q] = q2[lane + 32];
+      bg_live = bg_live || eb[q].env != 0.f || eb[q].denv != 0.f || !(d[q] == d[q]);
+    }
     // lane k: gradient wrt basis function k
-    float gb_ag = 0.f, gb_bg = 0.f;
+    float gb_ag[IT], gb_bg[IT];
+#pragma unroll
+    for (int q = 0; q < IT; ++q) gb_ag[q] = gb_bg[q] = 0.f;
     for (int n = 0; n < 32; ++n) {
-      const float va = __shfl_sync(0xffffffffu, a0, n), vb = __shfl_sync(0xffffffffu, b0, n);
-      const float va2 = __shfl_sync(0xffffffffu, a1, n), vb2 = __shfl_sync(0xffffffffu, b1, n);
-      gb_ag = fmaf(va, s_w[n * R + kl], gb_ag);
-      gb_ag = fmaf(vb, s_w[(64 + n) * R + kl], gb_ag);
-      gb_ag = fmaf(va2, s_w[(n + 32) * R + kl], gb_ag);
-      gb_ag = fmaf(vb2, s_w[(64 + n + 32) * R + kl], gb_ag);
+      const float w00 = s_w[n * R + kl], w01 = s_w[(n + 32) * R + kl];
+      const float w10 = s_w[(64 + n) * R + kl], w11 = s_w[(64 + n + 32) * R + kl];
+#pragma unroll
+      for (int q = 0; q < IT; ++q) {
+        gb_ag[q] = fmaf(__shfl_sync(0xffffffffu, a0[q], n), w00, gb_ag[q]);
+        gb_ag[q] = fmaf(__shfl_sync(0xffffffffu, b0[q], n), w10, gb_ag[q]);
+        gb_ag[q] = fmaf(__shfl_sync(0xffffffffu, a1[q], n), w01, gb_ag[q]);
+        gb_ag[q] = fmaf(__shfl_sync(0xffffffffu, b1[q], n), w11, gb_ag[q]);
+      }
       if (bg_live) {
-        const float vc = __shfl_sync(0xffffffffu, c0, n), vc2 = __shfl_sync(0xffffffffu, c1, n);
-        gb_bg = fmaf(vc, s_w[(128 + n) * R + kl], gb_bg);
-        gb_bg = fmaf(vc2, s_w[(128 + n + 32) * R + kl], gb_bg);
+        const float w20 = s_w[(128 + n) * R + kl], w21 = s_w[(128 + n + 32) * R + kl];
+#pragma unroll
+        for (int q = 0; q < IT; ++q) {
+          gb_bg[q] = fmaf(__shfl_sync(0xffffffffu, c0[q], n), w20, gb_bg[q]);
+          gb_bg[q] = fmaf(__shfl_sync(0xffffffffu, c1[q], n), w21, gb_bg[q]);
+        }
       }
     }
     // d basis_k / dd = norm [ (w/rc) cos(w d/rc)/d - sin(w d/rc)/d^2 ] env + norm sin(w d/rc)/d env'
-    float contrib = 0.f;
-    if (lane < R) {
-      float s, c;
-      sincosf(f_ag * (d / rc_ag), &s, &c);
-      const float raw = nrm_ag * s / d;
-      const float draw = nrm_ag * ((f_ag / rc_ag) * c / d - s / (d * d));
-      contrib = gb_ag * fmaf(draw, ea.env, raw * ea.denv);
-      if (bg_live) {
-        sincosf(f_bg * (d / rc_bg), &s, &c);
-        const float raw2 = nrm_bg * s / d;
-        const float draw2 = nrm_bg * ((f_bg / rc_bg) * c / d - s / (d * d));
-        contrib += gb_bg * fmaf(draw2, eb.env, raw2 * eb.denv);
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      float contrib = 0.f;
+      if (lane < R) {
+        float sn, cs;
+        sincosf(f_ag * (d[q] / rc_ag), &sn, &cs);
+        const float raw = nrm_ag * sn / d[q];
+        const float draw = nrm_ag * ((f_ag / rc_ag) * cs / d[q] - sn / (d[q] * d[q]));
+        contrib = gb_ag[q] * fmaf(draw, ea[q].env, raw * ea[q].denv);
+        if (eb[q].env != 0.f || eb[q].denv != 0.f || !(d[q] == d[q])) {
+          sincosf(f_bg * (d[q] / rc_bg), &sn, &cs);
+          const float raw2 = nrm_bg * sn / d[q];
+          const float draw2 = nrm_bg * ((f_bg / rc_bg) * cs / d[q] - sn / (d[q] * d[q]));
+          contrib += gb_bg[q] * fmaf(draw2, eb[q].env, raw2 * eb[q].denv);
+        }
       }
+      contrib = sum32(contrib);
+      if (lane == 0 && u0 + q < n_bonds) g_dist[u0 + q] = contrib;
     }
-    contrib = sum32(contrib);
-    if (lane == 0) g_dist[u] = contrib;
   }
 }
 
@@ -211,23 +258,41 @@ angle_basis_embed_kernel(const float* __restrict__ rhat, const int32_t* __restri
   const bool is_sin = lane >= 1 && lane <= nf, is_cos = lane > nf && lane < nb;
   const float w = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
   const float inv_sqrt_pi = 0.5641895835477563f;
-  for (int a = warp; a < n_angles; a += n_warps) {
-    float ri[3], rj[3];
-    const float u = angle_cos(rhat, ang_di[a], ang_dj[a], ri, rj);
-    const float th = acosf(u);
-    float f = 0.f;
-    if (lane == 0) f = 0.7071067811865476f;
-    else if (is_sin) f = sinf(w * th);
-    else if (is_cos) f = cosf(w * th);
-    f *= inv_sqrt_pi;
-    float oa = 0.f, ob = 0.f;
-    for (int m = 0; m < nb; ++m) {
-      const float fm = __shfl_sync(0xffffffffu, f, m);
-      oa = fmaf(fm, s_w[m * 64 + lane], oa);
-      ob = fmaf(fm, s_w[m * 64 + lane + 32], ob);
+  constexpr int IT = 4;  // angles per warp iteration (weight rows reused, independent accumulators)
+  for (int a0i = warp * IT; a0i < n_angles; a0i += n_warps * IT) {
+    float f[IT];
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      const int a = min(a0i + q, n_angles - 1);
+      float ri[3], rj[3];
+      const float u = angle_cos(rhat, ang_di[a], ang_dj[a], ri, rj);
+      const float th = acosf(u);
+      float v = 0.f;
+      if (lane == 0) v = 0.7071067811865476f;
+      else if (is_sin) v = sinf(w * th);
+      else if (is_cos) v = cosf(w * th);
+      f[q] = v * inv_sqrt_pi;
     }
-    a0[(size_t)a * 64 + lane] = oa;
-    a0[(size_t)a * 64 + lane + 32] = ob;
+    float oa[IT], ob[IT];
+#pragma unroll
+    for (int q = 0; q < IT; ++q) oa[q] = ob[q] = 0.f;
+    for (int m = 0; m < nb; ++m) {
+      const float wa = s_w[m * 64 + lane], wb = s_w[m * 64 + lane + 32];
+#pragma unroll
+      for (int q = 0; q < IT; ++q) {
+        const float fm = __shfl_sync(0xffffffffu, f[q], m);
+        oa[q] = fmaf(fm, wa, oa[q]);
+        ob[q] = fmaf(fm, wb, ob[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < IT; ++q) {
+      const int a = a0i + q;
+      if (a < n_angles) {
+        a0[(size_t)a * 64 + lane] = oa[q];
+        a0[(size_t)a * 64 + lane + 32] = ob[q];
+      }
+    }
   }
 }
 
@@ -255,30 +320,43 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
     const int a_beg = ch * CHUNK, a_end = min(a_beg + CHUNK, n_angles);
     int cur_di = -1;
     double acc_i = 0.0;  // lanes 0..2: pending sum for g_rhat[cur_di][lane]
-    for (int a = a_beg; a < a_end; ++a) {
-      const int di = ang_di[a], dj = ang_dj[a];
-      float ri[3], rj[3];
-      const float u = angle_cos(rhat, di, dj, ri, rj);
-      const float th = acosf(u);
-      const float ga = g_a0[(size_t)a * 64 + lane], gb = g_a0[(size_t)a * 64 + lane + 32];
-      float gf = 0.f;  // lane m: dE/d f_m
-      for (int n = 0; n < 32; ++n) {
-        gf = fmaf(__shfl_sync(0xffffffffu, ga, n), s_w[n * nb + ml], gf);
-        gf = fmaf(__shfl_sync(0xffffffffu, gb, n), s_w[(n + 32) * nb + ml], gf);
+    for (int a = a_beg; a < a_end; a += 2) {  // two angles per pass share the weight reads
+      const int a2 = min(a + 1, a_end - 1);
+      const int di[2] = {ang_di[a], ang_di[a2]}, dj[2] = {ang_dj[a], ang_dj[a2]};
+      float ri[2][3], rj[2][3], u[2], th[2], ga[2], gb[2], gf[2] = {0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int aa = q == 0 ? a : a2;
+        u[q] = angle_cos(rhat, di[q], dj[q], ri[q], rj[q]);
+        th[q] = acosf(u[q]);
+        ga[q] = g_a0[(size_t)aa * 64 + lane];
+        gb[q] = g_a0[(size_t)aa * 64 + lane + 32];
       }
-      float g_th = 0.f;
-      if (is_sin) g_th = gf * wf * cosf(wf * th);
-      else if (is_cos) g_th = -gf * wf * sinf(wf * th);
-      g_th = sum32(g_th) * inv_sqrt_pi;
-      // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
-      const float g_u = -g_th / sqrtf(1.f - u * u) * (1.f - 1e-6f);
-      if (di != cur_di) {
-        if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
-        cur_di = di;
-        acc_i = 0.0;
+      for (int n = 0; n < 32; ++n) {  // lane m: dE/d f_m
+        const float w0 = s_w[n * nb + ml], w1 = s_w[(n + 32) * nb + ml];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          gf[q] = fmaf(__shfl_sync(0xffffffffu, ga[q], n), w0, gf[q]);
+          gf[q] = fmaf(__shfl_sync(0xffffffffu, gb[q], n), w1, gf[q]);
+        }
       }
-      if (lane < 3) acc_i += (double)(g_u * rj[lane]);
-      else if (lane < 6) atomicAdd(g_rhat + (size_t)dj * 3 + (lane - 3), (double)(g_u * ri[lane - 3]));
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q == 1 && a + 1 >= a_end) break;  // warp-uniform
+        float g_th = 0.f;
+        if (is_sin) g_th = gf[q] * wf * cosf(wf * th[q]);
+        else if (is_cos) g_th = -gf[q] * wf * sinf(wf * th[q]);
+        g_th = sum32(g_th) * inv_sqrt_pi;
+        // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
+        const float g_u = -g_th / sqrtf(1.f - u[q] * u[q]) * (1.f - 1e-6f);
+        if (di[q] != cur_di) {
+          if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
+          cur_di = di[q];
+          acc_i = 0.0;
+        }
+        if (lane < 3) acc_i += (double)(g_u * rj[q][lane]);
+        else if (lane < 6) atomicAdd(g_rhat + (size_t)dj[q] * 3 + (lane - 3), (double)(g_u * ri[q][lane - 3]));
+      }
     }
     if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
   }
@@ -398,7 +476,7 @@ extern "C" int chg_bond_basis_embed(const float* dist, const int32_t* u2d, int32
   if (n_bonds == 0) return CHG_OK;
   CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3t && e0 && wag && wbg, "null pointer");
   const int smem = 3 * n_radial * 64 * 4;
-  bond_basis_embed_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+  bond_basis_embed_kernel<<<warp_grid((n_bonds + 3) / 4), 256, smem, as_stream(stream)>>>(
       dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3t, e0, wag, wbg);
   CHG_LAUNCH_END();
 }
@@ -412,7 +490,7 @@ extern "C" int chg_bond_basis_bwd(const float* dist, const int32_t* u2d, int32_t
   if (n_bonds == 0) return CHG_OK;
   CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3 && g_e0 && g_wag && g_wbg && g_dist, "null pointer");
   const int smem = 3 * n_radial * 64 * 4;
-  bond_basis_bwd_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+  bond_basis_bwd_kernel<<<warp_grid((n_bonds + 1) / 2), 256, smem, as_stream(stream)>>>(
       dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist);
   CHG_LAUNCH_END();
 }
@@ -425,7 +503,7 @@ extern "C" int chg_angle_basis_embed(const float* rhat, const int32_t* ang_di, c
   if (n_angles == 0) return CHG_OK;
   CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && wt && a0, "null pointer");
   const int smem = (2 * n_freq + 1) * 64 * 4;
-  angle_basis_embed_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles,
+  angle_basis_embed_kernel<<<warp_grid((n_angles + 3) / 4), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles,
                                                                                   freq, n_freq, wt, a0);
   CHG_LAUNCH_END();
 }

@@ -145,7 +145,10 @@ extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int3
   // kernel (k <= 128; wins only on the largest calls)
   if (linear_impl() == 2 && k <= 128)
     return linear_tma(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
-  if (linear_impl() >= 1) return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
+  // below ~4k rows the tensor-core kernel's fixed cost (operand images, TMEM allocation) is not
+  // amortised: the FFMA kernel is faster there (tools/linear_ab.py)
+  if (linear_impl() >= 1 && m >= 4096)
+    return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (n_out % 128 == 0 && k <= 128)
     return launch_linear<128>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   return launch_linear<64>(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));

@@ -46,14 +46,35 @@ linear_tc_kernel(const float* __restrict__ x, const int32_t* __restrict__ x_rows
   const int col_base = blockIdx.y * NT;
   float* stage = s_stage_all + wg * STAGE_FLOATS;
 
-  // weight panel -> hi / lo operand images (element (n, kk) = wt[kk][col_base + n])
-  for (int i = tid; i < NT * k; i += NTHR) {
-    const int kk = i / NT, n = i % NT;
-    uint32_t hi, lo;
-    tc::split_tf32(__ldg(wt + (size_t)kk * n_out + col_base + n), hi, lo);
-    const uint32_t off = tc::kmajor_offset(n, kk, k);
-    *reinterpret_cast<uint32_t*>(s_bhi + off) = hi;
-    *reinterpret_cast<uint32_t*>(s_blo + off) = lo;
+  // weight panel -> hi / lo operand images (element (n, kk) = wt[kk][col_base + n]); float4 loads,
+  // all of a thread's loads issued before the first dependent store
+  {
+    constexpr int PER = 8;  // float4 per thread per round
+    const int n4 = NT / 4, total4 = n4 * k;
+    for (int base4 = 0; base4 < total4; base4 += NTHR * PER) {
+      float4 v[PER];
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i4 = base4 + q * NTHR + tid;
+        v[q] = i4 < total4 ? ldg4(wt + (size_t)(i4 / n4) * n_out + col_base + (i4 % n4) * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int i4 = base4 + q * NTHR + tid;
+        if (i4 < total4) {
+          const int kk = i4 / n4, n0 = (i4 % n4) * 4;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t hi, lo;
+            tc::split_tf32(f4at(v[q], e), hi, lo);
+            const uint32_t off = tc::kmajor_offset(n0 + e, kk, k);
+            *reinterpret_cast<uint32_t*>(s_bhi + off) = hi;
+            *reinterpret_cast<uint32_t*>(s_blo + off) = lo;
+          }
+        }
+      }
+    }
   }
   if (tid == 0) {
     tc::mbar_init(&s_bar[0], 1);

@@ -167,3 +167,27 @@ def test_large_cell_properties(model):
     assert np.abs(a["f"].sum(axis=0)).max() < 1e-3
     assert _maxabs(a["s"], a["s"].T) < 1e-3
     assert np.array_equal(a["e"], b["e"]) and _maxabs(a["f"], b["f"]) < 1e-5
+
+
+def test_v020_shaped_architecture_end_to_end(weights030):
+    """Constructor + pack_weights + kernels for the 0.2.0 architecture (9 radial / 9 angular functions,
+    no LayerNorm, mlp_out bias, two readout hidden layers, cutoff_coeff 5, 5 A atom-graph cutoff) with
+    random weights, against the oracle fed the SAME state_dict."""
+    from chgnet_b200.model import CHGNet
+    from oracle import chgnet_oracle as orc
+
+    torch.manual_seed(3)
+    m = CHGNet(num_radial=9, num_angular=9, gMLP_norm=None, readout_norm=None, mlp_hidden_dims=[64, 64],
+               cutoff_coeff=5, atom_graph_cutoff=5, mlp_out_bias=True, composition_model="MPtrj").to("cuda")
+    sd = m.state_dict()
+    assert len(sd) == 99 and m.n_params == 400438  # reference tests/test_model.py:236-310 (0.2.0 counts)
+    assert "atom_conv_layers.0.mlp_out.layers.1.bias" in sd and "readout_norm.weight" not in sd
+    w = {k: v.detach().cpu().numpy() for k, v in sd.items()}
+    args = dict(num_radial=9, num_angular=9, gMLP_norm=None, readout_norm=None, mlp_out_bias=True, cutoff_coeff=5,
+                atom_graph_cutoff=5.0)
+    graphs = graphgen.random_graphs(3, 8, 14, 7600, atom_graph_cutoff=5.0)
+    preds = m.predict_graph(graphs, task="efsm", batch_size=3)
+    ref = orc.predict_graph(w, graphs, "efsm", batch_size=3, dtype=torch.float64, args=args)
+    for p, r in zip(preds, ref):
+        for k, tol in TOL.items():
+            assert _maxabs(p[k], r[k]) < tol * 5, (k, _maxabs(p[k], r[k]))  # untrained weights: larger magnitudes
