@@ -108,7 +108,8 @@ class CudaKernels:
                 raise ChgnetB200Error("kernel arguments must be contiguous CUDA tensors")
 
     def set_option(self, name: str, value: int) -> None:
-        """A/B switches (include/chgnet_b200.h): 'linear_impl' 0 FFMA | 1 tcgen05 | 2 tcgen05+TMA,
+        """A/B switches (include/chgnet_b200.h): 'linear_impl' 0 FFMA | 1 tcgen05 | 2 tcgen05+TMA rows |
+        3 warp-specialised tcgen05 + TMA tensor maps (default),
         'gated_impl' 0 FFMA 4x8 | 1 tcgen05 | 2 FFMA 8x8."""
         if self.lib.chg_set_option(name.encode(), int(value)) != 0:
             raise ChgnetB200Error(self.lib.chg_last_error().decode())

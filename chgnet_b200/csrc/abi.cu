@@ -48,7 +48,7 @@ int env_default(const char* name, int dflt) {
 }  // namespace
 int linear_impl() {
   int v = g_linear_impl.load();
-  if (v < 0) { v = env_default("CHG_LINEAR_IMPL", 1); g_linear_impl.store(v); }
+  if (v < 0) { v = env_default("CHG_LINEAR_IMPL", 3); g_linear_impl.store(v); }
   return v;
 }
 int gated_impl() {
@@ -60,7 +60,7 @@ int gated_impl() {
 
 extern "C" int chg_set_option(const char* name, int32_t value) {
   if (name == nullptr) return CHG_ERR_ARG;
-  if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
+  if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 3 ? 3 : value)); return CHG_OK; }
   if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
   chg::set_error("chg_set_option: unknown option %s", name);
   return CHG_ERR_ARG;

@@ -128,6 +128,8 @@ int linear_tc(const float* x, const int32_t* x_rows, int m, int k, const float* 
               const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
 int linear_tma(const float* x, const int32_t* x_rows, int m, int k, const float* wt, const float* bias,
                const float* residual, const int32_t* y_rows, int n_out, float* y, cudaStream_t stream);
+int linear_ws(const float* x, int m, int k, const float* wt, const float* bias, const float* residual, int n_out,
+              float* y, cudaStream_t stream);
 
 }  // namespace chg
 
@@ -147,6 +149,10 @@ extern "C" int chg_linear(const float* x, const int32_t* x_rows, int32_t m, int3
     return linear_tma(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   // below ~4k rows the tensor-core kernel's fixed cost (operand images, TMEM allocation) is not
   // amortised: the FFMA kernel is faster there (tools/linear_ab.py)
+  if (linear_impl() == 3 && m >= 4096 && x_rows == nullptr && y_rows == nullptr) {  // warp-specialised + TMA maps
+    const int rc = linear_ws(x, m, k, wt, bias, residual, n_out, y, as_stream(stream));
+    if (rc <= 0) return rc;  // rc == 1: not applicable, fall through
+  }
   if (linear_impl() >= 1 && m >= 4096)
     return linear_tc(x, x_rows, m, k, wt, bias, residual, y_rows, n_out, y, as_stream(stream));
   if (n_out % 128 == 0 && k <= 128)

@@ -43,9 +43,11 @@ int chg_abi_version(void);
 /* number of kernel launches issued by this library since load (host counter) */
 int64_t chg_launch_count(void);
 /* implementation switches for A/B measurements (same results, same ABI):
- *   "linear_impl": 0 FFMA, 1 tcgen05 register-staged (default), 2 tcgen05 + TMA row copies
+ *   "linear_impl": 0 FFMA, 1 tcgen05 register-staged, 2 tcgen05 + TMA row copies,
+ *                  3 warp-specialised tcgen05 fed by 2-D TMA tensor maps (default; calls with
+ *                    row indirection or k = 256 use 1)
  *   "gated_impl" : 0 FFMA 4x8 tiles (default), 1 tcgen05, 2 FFMA 8x8 tiles
- * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0|1|2 set the defaults).                      */
+ * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3 / 0..2 set the defaults).                      */
 int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */

@@ -38,8 +38,9 @@ def recorded(weights030):
     return _record(weights030, graphs, need_grad=True, need_magmom=True, need_atom_fea=True, need_crystal_fea=True)
 
 
-@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 0), (0, 1), (2, 2)],
-                         ids=["linear=tcgen05,gated=ffma4x8", "linear=ffma,gated=tcgen05", "linear=tcgen05+tma,gated=ffma8x8"])
+@pytest.mark.parametrize("linear_impl,gated_impl", [(3, 0), (1, 0), (0, 1), (2, 2)],
+                         ids=["linear=tcgen05-ws,gated=ffma4x8", "linear=tcgen05,gated=ffma4x8", "linear=ffma,gated=tcgen05",
+                              "linear=tcgen05+tma,gated=ffma8x8"])
 def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
     """Both implementations of every entry point (tcgen05 3xTF32 and FFMA) against the spec."""
     from chgnet_b200._lib import CudaKernels
@@ -59,8 +60,39 @@ def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
         assert set(seen) == set(__import__("kernel_replay").OUT_ARGS), sorted(seen)
         print({k: f"{v:.2e}" for k, v in seen.items()})
     finally:
-        K.set_option("linear_impl", 1)
+        K.set_option("linear_impl", 3)
         K.set_option("gated_impl", 0)
+
+
+@pytest.mark.parametrize("impl", [3, 2, 1, 0], ids=["tcgen05-ws", "tcgen05+tma", "tcgen05", "ffma"])
+def test_linear_large_ragged_calls(impl):
+    """chg_linear at the sizes where the tensor-core kernels are dispatched (m >= 4096): ragged
+    last tile, every (k, n) the model uses, bias / residual / in-place residual, against fp64."""
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    K.set_option("linear_impl", impl)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    try:
+        for m in (4096, 5001, 70001):
+            for k, n in ((64, 128), (64, 256), (128, 64), (64, 64), (64, 192), (128, 128), (256, 64)):
+                for has_bias, res_mode in ((True, "none"), (False, "separate"), (True, "inplace")):
+                    x = torch.randn(m, k, device="cuda", generator=g)
+                    wt = torch.randn(k, n, device="cuda", generator=g) / k ** 0.5
+                    bias = torch.randn(n, device="cuda", generator=g) if has_bias else None
+                    res = torch.randn(m, n, device="cuda", generator=g) if res_mode != "none" else None
+                    want = x.double() @ wt.double()
+                    if bias is not None:
+                        want += bias.double()
+                    if res is not None:
+                        want += res.double()
+                    y = res if res_mode == "inplace" else torch.full((m, n), float("nan"), device="cuda")
+                    K.linear(x, wt, bias, res, y, None, None)
+                    torch.cuda.synchronize()
+                    err = float((y.double() - want).abs().max())
+                    assert err < 5e-5, (impl, m, k, n, has_bias, res_mode, err)
+    finally:
+        K.set_option("linear_impl", 3)
 
 
 def test_kernels_without_layernorm_and_small_basis(weights030):

@@ -59,7 +59,7 @@ def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, lin
         for k, tol in TOL.items():
             assert _maxabs(out[k], golden[f"limno2.oracle64.{k}"]) < tol, k
     finally:
-        K.set_option("linear_impl", 1)
+        K.set_option("linear_impl", 3)
         K.set_option("gated_impl", 0)
 
 

@@ -8,7 +8,7 @@ from chgnet_b200._lib import CudaKernels
 K = CudaKernels()
 torch.manual_seed(0)
 flush = torch.empty(64 << 20, device="cuda")
-for impl_id, impl in ((2, "tma"), (1, "tc"), (0, "ffma")):
+for impl_id, impl in ((3, "ws"), (1, "tc"), (0, "ffma")):
   K.set_option("linear_impl", impl_id)
   for (m, k, n, gather) in [(300, 64, 128, False), (422077, 64, 128, False), (52000, 64, 256, True), (10000, 64, 256, False),
                             (422077, 128, 64, False), (52000, 256, 64, True), (10000, 256, 64, False), (422077, 64, 64, False)]:
