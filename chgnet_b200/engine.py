@@ -79,8 +79,16 @@ class Engine:
         need_atom_fea: bool = False,
         need_crystal_fea: bool = False,
         keep_intermediates: bool = False,
+        train: bool = False,
     ) -> EngineOutput:
+        """Forward; with ``need_grad`` the reverse pass for F / sigma right after it.
+
+        ``train=True`` (reference trainer.py:398-411) saves what the PARAMETER gradients need and
+        returns without a reverse pass: call :meth:`param_grads` with the loss seeds afterwards.
+        """
         pw, K, hp = self.pw, self.K, self.pw.hp
+        if train:
+            need_grad = True
         N, Ed, Eu, A, B = b.n_atoms, b.n_edges, b.n_bonds, b.n_angles, b.n_graphs
         has_ang = A > 0
         n_conv = hp.n_conv
@@ -92,12 +100,22 @@ class Engine:
         rvec, dist, rhat = self._new(b, Ed, 3), self._new(b, Ed), self._new(b, Ed, 3)
         K.edge_geometry(b.frac, b.lattice, b.owner, b.center, b.nbr, b.image, rvec, dist, rhat)
         e, wag, wbg = self._new(b, Eu, 64), self._new(b, Eu, 64), self._new(b, Eu, 64)
-        K.bond_basis_embed(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
-                           hp.cutoff_coeff, pw.w3t, e, wag, wbg)
+        tr: dict = dict(x=[], e=[], ang=[], agg_a=[], agg_b=[]) if train else {}
+        if train:
+            tr["bb"] = self._new(b, Eu, 64)
+            K.bond_basis_embed(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                               hp.cutoff_coeff, pw.w3t, e, wag, wbg, tr["bb"])
+        else:
+            K.bond_basis_embed(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                               hp.cutoff_coeff, pw.w3t, e, wag, wbg)
         ang = None
         if has_ang:
             ang = self._new(b, A, 64)
-            K.angle_basis_embed(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang_t, ang)
+            if train:
+                tr["fb"] = self._new(b, A, 64)
+                K.angle_basis_embed(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang_t, ang, tr["fb"])
+            else:
+                K.angle_basis_embed(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang_t, ang)
         if keep_intermediates:
             inter.update(x0=x, e0=e, w_ag=wag, w_bg=wbg, a0=ang)
 
@@ -111,10 +129,16 @@ class Engine:
             pe = self._lin(b, e, gp.extra["we_t"], bias=gp.extra["b1"])
             msg = self._new(b, Ed, 64)
             save_p = self._new(b, Ed, 128) if need_grad else None
-            K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p)
+            if train:
+                save_pre = self._new(b, Ed, 128)
+                K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p, save_pre)
+            else:
+                K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p)
             agg = self._seg(b, msg, None, b.ptr_c, N)
             if need_grad:
                 saved_atom.append(dict(pcn=pcn, pe=pe, p=save_p))
+            if train:
+                saved_atom[-1].update(pre=save_pre, x=x, e=e, agg=agg)
             return self._lin(b, agg, gp.extra["wo_t"], bias=gp.extra["bo"], residual=x)
 
         # BondConv / AngleUpdate work in the compact space of the Es bond-graph bonds
@@ -140,11 +164,14 @@ class Engine:
                 agg = self._seg(b, upd, None, b.ptr_is, Es)
                 # e[sid] += Wo agg (+ bias); bonds outside the bond graph keep their features
                 # (with mlp_out bias the batch is built with identity compaction, Es == Eu)
-                if keep_intermediates:
+                e_in = e
+                if keep_intermediates or train:
                     e = e.clone()
                 K.linear(agg, gp.extra["wo_t"], gp.extra["bo"], e, e, None, sid)
                 if need_grad:
                     saved_bond.append(dict(pre=s_pre, p=s_p))
+                if train:
+                    saved_bond[-1].update(x=x, e=e_in, ang=ang, agg=agg)
                 if t < n_conv - 2:  # the last AngleUpdate is dead compute
                     ga = pw.angle[t]
                     pij = self._lin(b, e, ga.extra["wij_t"], bias=ga.extra["bij"], x_rows=sid)
@@ -153,9 +180,11 @@ class Engine:
                     ang_new = self._new(b, A, 64)
                     s_p = self._new(b, A, 128) if need_grad else None
                     K.angle_update_fwd(pij, px, pa, ang, b.ang_atom, b.ang_is, b.ang_js, ga.ln, ang_new, s_p)
-                    ang = ang_new
                     if need_grad:
                         saved_angle.append(dict(p=s_p))
+                    if train:
+                        saved_angle[-1].update(x=x, e=e, ang=ang)
+                    ang = ang_new
             if keep_intermediates:
                 inter[f"x{t + 1}"], inter[f"e{t + 1}"] = x, e
                 if t < n_conv - 2:
@@ -166,6 +195,7 @@ class Engine:
                 if need_magmom:
                     magmom = self._new(b, N)
                     K.magmom(x, pw.w_mag, pw.b_mag, magmom)
+                    tr["x_mag"] = x
         x = atom_conv(n_conv - 1, x, e)
 
         # ---- readout -----------------------------------------------------------
@@ -173,7 +203,7 @@ class Engine:
         h_out = self._new(b, N, 64) if (need_crystal_fea or keep_intermediates) else None
         energy = self._zeros(b, B, dtype=torch.float64)
         e_ref = self._zeros(b, B, dtype=torch.float64)
-        g_x = self._new(b, N, 64) if need_grad else None
+        g_x = self._new(b, N, 64) if (need_grad and not train) else None
         K.readout(x, b.z, b.owner, pw.readout_ln, pw.mlp_wt, pw.mlp_w, pw.mlp_b, pw.w_last, pw.b_last,
                   pw.atom_ref, site_e, h_out, energy, e_ref, g_x)
         crystal_fea = None
@@ -187,8 +217,72 @@ class Engine:
                            crystal_fea=crystal_fea, extras=inter)
         if not need_grad:
             return out
+        st = dict(b=b, x_last=x, g_x=g_x, wag=wag, wbg_s=wbg_s, dist=dist, rvec=rvec, rhat=rhat, tr=tr,
+                  saved_atom=saved_atom, saved_bond=saved_bond, saved_angle=saved_angle)
+        if train:
+            out.extras["train_state"] = st
+            return out
+        self._reverse(st, out, None)
+        return out
 
-        # ======================= reverse pass (inputs only) ======================
+    # ------------------------------------------------------------------ reverse
+    def param_grads(self, out: EngineOutput, seed_energy: Tensor, seed_magmom: Tensor | None = None) -> dict:
+        """Training reverse pass (replaces ``loss.backward()``, trainer.py:409-410) for losses on the
+        energies and magnetic moments: dL/d(parameter) for ``seed_energy[g] = dL/d(E_g)`` (E_g the
+        extensive model energy of graph g) and ``seed_magmom[i] = dL/d(m_i)``.
+
+        Returns gradients in the packed layouts, keyed like ``weights.unpack_grads`` expects.  Losses on
+        forces / stresses need the second-order pass (reverse of this reverse pass), which is not
+        built yet; asking for them raises in ``chgnet_b200.trainer``.
+        """
+        st = out.extras.pop("train_state")
+        grads: dict = {}
+        self._reverse(st, out, dict(seed_energy=seed_energy, seed_magmom=seed_magmom, grads=grads))
+        return grads
+
+    def _wgrad(self, b, x, g, n, *, x_rows=None, g_rows=None, x_silu=False, colsum=False):
+        out = self._new(b, 64, n)
+        cs = self._new(b, n) if colsum else None
+        self.K.wgrad(x, g, out, cs, x_rows, g_rows, x_silu)
+        return (out, cs) if colsum else out
+
+    def _colsum(self, b, a, bmul=None, rowscale=None) -> Tensor:
+        out = self._zeros(b, a.shape[1], dtype=torch.float64)
+        self.K.colsum(a, out, bmul, rowscale)
+        return out.to(self.pw.emb.dtype)
+
+    def _reverse(self, st: dict, out: EngineOutput, train: dict | None) -> None:
+        pw, K, hp = self.pw, self.K, self.pw.hp
+        b: DeviceBatch = st["b"]
+        N, Ed, Eu, A, B = b.n_atoms, b.n_edges, b.n_bonds, b.n_angles, b.n_graphs
+        has_ang = A > 0
+        n_conv = hp.n_conv
+        Es, sid = b.n_short, b.short_ids
+        wag, wbg_s, dist, rvec, rhat, tr = st["wag"], st["wbg_s"], st["dist"], st["rvec"], st["rhat"], st["tr"]
+        saved_atom, saved_bond, saved_angle = st["saved_atom"], st["saved_bond"], st["saved_angle"]
+        G = train["grads"] if train is not None else None
+        use_ln = pw.atom[0].ln is not None
+
+        def ln_acc():
+            return self._zeros(b, 256, dtype=torch.float64) if (G is not None and use_ln) else None
+
+        g_x = st["g_x"]
+        if train is not None:
+            # readout reverse with the loss seed, and the readout / magmom parameter gradients
+            L = pw.mlp_wt.shape[0]
+            seed_atom = train["seed_energy"].to(pw.emb.dtype)[b.owner.long()].contiguous()
+            g_x = self._new(b, N, 64)
+            h_all, gz_all = self._new(b, L + 1, N, 64), self._new(b, L, N, 64)
+            g_h0, xhat = self._new(b, N, 64), self._new(b, N, 64)
+            K.readout_bwd(st["x_last"], pw.readout_ln, pw.mlp_wt, pw.mlp_w, pw.mlp_b, pw.w_last, seed_atom, g_x,
+                          h_all, gz_all, g_h0, xhat)
+            G["mlp_wt"] = torch.stack([self._wgrad(b, h_all[l], gz_all[l], 64) for l in range(L)])
+            G["mlp_b"] = torch.stack([self._colsum(b, gz_all[l]) for l in range(L)])
+            G["w_last"] = self._colsum(b, h_all[L], rowscale=seed_atom)
+            G["b_last"] = seed_atom.sum()
+            if pw.readout_ln is not None:
+                G["readout_ln"] = torch.stack([self._colsum(b, g_h0, xhat), self._colsum(b, g_h0)])
+
         g_e = None  # d(sum E)/d e at the current level
         g_wag = self._zeros(b, Eu, 64)
         g_wbg = self._zeros(b, Es, 64) if has_ang else None  # compact; expanded at the end
@@ -198,49 +292,96 @@ class Engine:
             """dst + x_in @ wt (dst None -> plain product)."""
             return self._lin(b, x_in, wt, residual=dst)
 
+        def w2_grads(key: str, pre: Tensor, g_p: Tensor, g_ln: Tensor | None) -> None:
+            """second-layer / LayerNorm parameter gradients of one GatedMLP (block-diagonal core | gate)"""
+            w2t, b2 = self._new(b, 64, 128), self._new(b, 128)
+            K.wgrad(pre[:, :64], g_p[:, :64], w2t[:, :64], b2[:64], None, None, True)
+            K.wgrad(pre[:, 64:], g_p[:, 64:], w2t[:, 64:], b2[64:], None, None, True)
+            G[f"{key}.w2t"], G[f"{key}.b2"] = w2t, b2
+            if g_ln is not None:
+                G[f"{key}.ln"] = g_ln.to(w2t.dtype).view(4, 64)
+
         def atom_conv_bwd(t: int, g_xout: Tensor, g_e: Tensor | None) -> tuple[Tensor, Tensor]:
             gp, sv = pw.atom[t], saved_atom[t]
             g_agg = self._lin(b, g_xout, gp.extra["wo"])
             g_pre, g_w = self._new(b, Ed, 128), self._new(b, Ed, 64)
-            K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
-                            g_pre, g_w)
+            if G is None:
+                K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
+                                g_pre, g_w)
+            else:
+                g_p, g_ln = self._new(b, Ed, 128), ln_acc()
+                K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
+                                g_pre, g_w, g_p, g_ln)
+                w2_grads(f"atom.{t}", sv["pre"], g_p, g_ln)
+                G[f"atom.{t}.wo_t"] = self._wgrad(b, sv["agg"], g_xout, 64)
+                if gp.extra["bo"] is not None:
+                    G[f"atom.{t}.bo"] = self._colsum(b, g_xout)
             sp = self._new(b, N, 256)
             K.segment_sum(g_pre, None, b.ptr_c, 0, sp[:, :128])
             K.segment_sum(g_pre, b.perm_n, b.ptr_n, 0, sp[:, 128:])
             g_xin = acc(g_xout, sp, gp.extra["wcn_b"])
             spe = self._seg(b, g_pre, b.perm_u, b.ptr_u, Eu)
+            if G is not None:
+                G[f"atom.{t}.wcn_t"] = self._wgrad(b, sv["x"], sp, 256)
+                G[f"atom.{t}.we_t"], G[f"atom.{t}.b1"] = self._wgrad(b, sv["e"], spe, 128, colsum=True)
             g_e = acc(g_e, spe, gp.extra["we_b"])
             K.segment_sum(g_w, b.perm_u, b.ptr_u, 1, g_wag)
             return g_xin, g_e
 
-        def angle_scatter(g_pre: Tensor, g_x: Tensor, g_e: Tensor | None, ex: dict) -> tuple[Tensor, Tensor]:
+        def angle_scatter(g_pre: Tensor, g_x: Tensor, g_e: Tensor | None, ex: dict, key: str = "",
+                          sv: dict | None = None) -> tuple[Tensor, Tensor]:
             """Push dE/dpre of an angle-indexed GatedMLP back to e (via i and j) and x."""
             sp = self._new(b, Es, 256)
             K.segment_sum(g_pre, None, b.ptr_is, 0, sp[:, :128])
             K.segment_sum(g_pre, b.perm_js, b.ptr_js, 0, sp[:, 128:])
             K.linear(sp, ex["wij_b"], None, g_e, g_e, None, sid)  # g_e[sid] += sp @ Wij
             spx = self._seg(b, g_pre, b.perm_x, b.ptr_x, N)
+            if G is not None:  # first-layer blocks: bonds i|j (bias rides on i), centre atom, angle
+                G[f"{key}.wij_t"] = self._wgrad(b, sv["e"], sp, 256, x_rows=sid)
+                G[f"{key}.wx_t"] = self._wgrad(b, sv["x"], spx, 128)
+                G[f"{key}.w1a_t"], G[f"{key}.b1"] = self._wgrad(b, sv["ang"], g_pre, 128, colsum=True)
             g_x = acc(g_x, spx, ex["wx_b"])
             return g_x, g_e
 
         g_x, g_e = atom_conv_bwd(n_conv - 1, g_x, None)
+        if train is not None and train["seed_magmom"] is not None:
+            # m = |site_wise(x)| on the output of AtomConv n_conv-2 (model.py:477-487)
+            g_lin = self._new(b, N)
+            K.magmom_bwd(tr["x_mag"], pw.w_mag, pw.b_mag, train["seed_magmom"].to(pw.emb.dtype).contiguous(), g_x, g_lin)
+            G["w_mag"] = self._colsum(b, tr["x_mag"], rowscale=g_lin)
+            G["b_mag"] = g_lin.sum()
         for t in reversed(range(n_conv - 1)):
             if has_ang:
                 if t < n_conv - 2:  # AngleUpdate_t: a_{t+1} = a_t + G0(e_{t+1}, a_t, x_{t+1})
                     ga = pw.angle[t]
                     g_pre = self._new(b, A, 128)
-                    K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.ln, g_pre)
+                    if G is None:
+                        K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.ln, g_pre)
+                    else:
+                        g_ln = ln_acc()
+                        K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.ln, g_pre, g_ln)
+                        if g_ln is not None:
+                            G[f"angle.{t}.ln"] = g_ln.to(g_pre.dtype).view(4, 64)
                     g_a = acc(g_a, g_pre, ga.extra["w1a_b"])  # residual + through the angle block
-                    g_x, g_e = angle_scatter(g_pre, g_x, g_e, ga.extra)
+                    g_x, g_e = angle_scatter(g_pre, g_x, g_e, ga.extra, f"angle.{t}", saved_angle[t])
                 # BondConv_t: e_{t+1} = e_t + Wo agg(G(e_t, a_t, x_{t+1}) w_i w_j)
                 gp, sv = pw.bond[t], saved_bond[t]
                 g_agg = self._lin(b, g_e, gp.extra["wo"], x_rows=sid)
                 g_pre = self._new(b, A, 128)
                 gw_i, gw_j = self._new(b, A, 64), self._new(b, A, 64)
-                K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
-                                gw_i, gw_j)
+                if G is None:
+                    K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
+                                    gw_i, gw_j)
+                else:
+                    g_p, g_ln = self._new(b, A, 128), ln_acc()
+                    K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
+                                    gw_i, gw_j, g_p, g_ln)
+                    w2_grads(f"bond.{t}", sv["pre"], g_p, g_ln)
+                    G[f"bond.{t}.wo_t"] = self._wgrad(b, sv["agg"], g_e, 64, g_rows=sid)
+                    if gp.extra["bo"] is not None:
+                        G[f"bond.{t}.bo"] = self._colsum(b, g_e)  # identity compaction when a bias exists
                 g_a = acc(g_a, g_pre, gp.extra["w1a_b"])
-                g_x, g_e = angle_scatter(g_pre, g_x, g_e, gp.extra)
+                g_x, g_e = angle_scatter(g_pre, g_x, g_e, gp.extra, f"bond.{t}", sv)
                 K.segment_sum(gw_i, None, b.ptr_is, 1, g_wbg)
                 K.segment_sum(gw_j, b.perm_js, b.ptr_js, 1, g_wbg)
             g_x, g_e = atom_conv_bwd(t, g_x, g_e)
@@ -250,6 +391,26 @@ class Engine:
         g_wbg_full = self._zeros(b, Eu, 64)
         if has_ang:
             K.scatter_rows(g_wbg, sid, g_wbg_full)
+        if G is not None:
+            # embeddings, basis weights and the learnable basis frequencies (basis.py:23-27, 74-80)
+            R, NA = pw.freq_ag.shape[0], pw.wang.shape[1]
+            order = torch.argsort(b.z.long(), stable=True).int()
+            zptr = torch.zeros(95, dtype=torch.int32, device=b.z.device)
+            zptr[1:] = torch.cumsum(torch.bincount(b.z.long() - 1, minlength=94), 0)
+            G["emb"] = self._new(b, 94, 64)
+            K.segment_sum(g_x, order, zptr, 0, G["emb"])
+            G["w3t"] = torch.stack([self._wgrad(b, tr["bb"], g_e, 64)[:R], self._wgrad(b, tr["bb"], g_wag, 64)[:R],
+                                    self._wgrad(b, tr["bb"], g_wbg_full, 64)[32 : 32 + R]])
+            g_freq = self._zeros(b, 2, R, dtype=torch.float64)
+            K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                             hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg_full, g_dist, g_freq)
+            G["freq_ag"], G["freq_bg"] = g_freq[0].to(g_e.dtype), g_freq[1].to(g_e.dtype)
+            if has_ang:
+                G["wang_t"] = self._wgrad(b, tr["fb"], g_a, 64)[:NA]
+                g_fa = self._zeros(b, pw.freq_ang.shape[0], dtype=torch.float64)
+                K.angle_basis_bwd(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, g_a, None, g_fa)
+                G["freq_ang"] = g_fa.to(g_e.dtype)
+            return
         K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
                          hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg_full, g_dist)
         g_rhat = self._zeros(b, Ed, 3, dtype=torch.float64)
@@ -259,4 +420,3 @@ class Engine:
         virial = self._zeros(b, B, 9, dtype=torch.float64)
         K.force_virial(rvec, dist, rhat, g_rhat, g_dist, b.d2u, b.u2d, b.center, b.nbr, b.owner, force, virial)
         out.force, out.virial = force, virial
-        return out

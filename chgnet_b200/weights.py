@@ -211,3 +211,83 @@ def pack_weights(state_dict: dict, model_args: dict | None = None, device=None, 
             else torch.zeros(94, device=device, dtype=dtype)
         ),
     )
+
+
+def unpack_grads(G: dict, state_dict: dict) -> dict[str, Tensor]:
+    """Inverse of :func:`pack_weights` for GRADIENTS: the packed-layout gradients produced by
+    ``Engine.param_grads`` -> one tensor per ``state_dict`` name (same shapes).
+
+    Parameters the loss cannot reach get zeros (``angle_layers.{n_conv-2}`` is dead compute in
+    the reference, model.py:470-496; ``composition_model`` is frozen, composition_model.py:127-131).
+    """
+    sd = state_dict
+    out: dict[str, Tensor] = {}
+    any_g = G["emb"]
+
+    def put(name: str, val) -> None:
+        if name in sd:
+            out[name] = torch.as_tensor(val, dtype=any_g.dtype, device=any_g.device).reshape(sd[name].shape)
+
+    def gated(prefix: str, key: str, first: str, second: str | None, blocks: list[tuple[str, int, int]]) -> None:
+        """blocks: (packed key, core column offset, gate column offset) per 64-wide input block, in
+        the reference's concatenation order."""
+        if f"{key}.{blocks[0][0]}" not in G:
+            return
+        put(f"{prefix}.mlp_core.{first}.weight", torch.cat([G[f"{key}.{k}"][:, c : c + 64].T for k, c, _ in blocks], dim=1))
+        put(f"{prefix}.mlp_gate.{first}.weight", torch.cat([G[f"{key}.{k}"][:, g : g + 64].T for k, _, g in blocks], dim=1))
+        put(f"{prefix}.mlp_core.{first}.bias", G[f"{key}.b1"][:64])
+        put(f"{prefix}.mlp_gate.{first}.bias", G[f"{key}.b1"][64:])
+        if second is not None:
+            put(f"{prefix}.mlp_core.{second}.weight", G[f"{key}.w2t"][:, :64].T)
+            put(f"{prefix}.mlp_gate.{second}.weight", G[f"{key}.w2t"][:, 64:].T)
+            put(f"{prefix}.mlp_core.{second}.bias", G[f"{key}.b2"][:64])
+            put(f"{prefix}.mlp_gate.{second}.bias", G[f"{key}.b2"][64:])
+        if f"{key}.ln" in G:
+            for i, nm in enumerate(("bn1.weight", "bn1.bias", "bn2.weight", "bn2.bias")):
+                put(f"{prefix}.{nm}", G[f"{key}.ln"][i])
+
+    n_conv = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("atom_conv_layers."))
+    for t in range(n_conv):
+        gated(f"atom_conv_layers.{t}.twoBody_atom", f"atom.{t}", "layers.0", "layers.3",
+              [("wcn_t", 0, 64), ("we_t", 0, 64), ("wcn_t", 128, 192)])
+        if f"atom.{t}.wo_t" in G:
+            put(f"atom_conv_layers.{t}.mlp_out.layers.1.weight", G[f"atom.{t}.wo_t"].T)
+            if f"atom.{t}.bo" in G:
+                put(f"atom_conv_layers.{t}.mlp_out.layers.1.bias", G[f"atom.{t}.bo"])
+    ij_a_x = [("wij_t", 0, 64), ("wij_t", 128, 192), ("w1a_t", 0, 64), ("wx_t", 0, 64)]
+    for t in range(n_conv - 1):
+        gated(f"bond_conv_layers.{t}.twoBody_bond", f"bond.{t}", "layers.0", "layers.3", ij_a_x)
+        if f"bond.{t}.wo_t" in G:
+            put(f"bond_conv_layers.{t}.mlp_out.layers.1.weight", G[f"bond.{t}.wo_t"].T)
+            if f"bond.{t}.bo" in G:
+                put(f"bond_conv_layers.{t}.mlp_out.layers.1.bias", G[f"bond.{t}.bo"])
+        gated(f"angle_layers.{t}.twoBody_bond", f"angle.{t}", "layers.1", None, ij_a_x)
+
+    put("atom_embedding.embedding.weight", G["emb"])
+    put("bond_embedding.weight", G["w3t"][0].T)
+    put("bond_weights_ag.weight", G["w3t"][1].T)
+    put("bond_weights_bg.weight", G["w3t"][2].T)
+    put("bond_basis_expansion.rbf_expansion_ag.frequencies", G["freq_ag"])
+    put("bond_basis_expansion.rbf_expansion_bg.frequencies", G["freq_bg"])
+    if "wang_t" in G:
+        put("angle_embedding.weight", G["wang_t"].T)
+        put("angle_basis_expansion.fourier_expansion.frequencies", G["freq_ang"])
+    if "readout_ln" in G:
+        put("readout_norm.weight", G["readout_ln"][0])
+        put("readout_norm.bias", G["readout_ln"][1])
+    hidden_idx = sorted(
+        int(k.split(".")[2]) for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight") and sd[k].shape[0] == 64
+    )
+    last_idx = max(int(k.split(".")[2]) for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight"))
+    for l, i in enumerate(hidden_idx):
+        put(f"mlp.layers.{i}.weight", G["mlp_wt"][l].T)
+        put(f"mlp.layers.{i}.bias", G["mlp_b"][l])
+    put(f"mlp.layers.{last_idx}.weight", G["w_last"])
+    put(f"mlp.layers.{last_idx}.bias", G["b_last"])
+    if "w_mag" in G:
+        put("site_wise.weight", G["w_mag"])
+        put("site_wise.bias", G["b_mag"])
+    for name, v in sd.items():
+        if name not in out and torch.is_floating_point(torch.as_tensor(v)):
+            out[name] = torch.zeros(tuple(v.shape), dtype=any_g.dtype, device=any_g.device)
+    return out

@@ -192,14 +192,19 @@ def forward(
     return_atom_feas: bool = False,
     return_crystal_feas: bool = False,
     return_intermediates: bool = False,
+    train: bool = False,
 ) -> dict:
     """CHGNet.forward restated (reference model.py:330-542, 792-913).
+
+    ``train=True`` is the reference's training mode: ``weights`` is a dict of torch tensors
+    (leaf parameters), forces/stresses are taken with ``create_graph=True`` (model.py:518, 529)
+    and nothing is detached, so a loss on e/f/s/m back-propagates to the parameters.
 
     Returns the reference's dict: e [B] (eV/atom if intensive), f list[n_i,3],
     s list[3,3] GPa, m list[n_i], atoms_per_graph, plus optional extras.
     """
     a = {**DEFAULT_ARGS, **(args or {})}
-    w = _t(weights, dtype)
+    w = dict(weights) if train else _t(weights, dtype)
     R = a["num_radial"]
     p = int(a["cutoff_coeff"])
     n_conv = a["n_conv"]
@@ -317,10 +322,10 @@ def forward(
         inter["site_e_model"] = site_e
 
     if want_f:  # model.py:517-524
-        grads = torch.autograd.grad(energy.sum(), pos_list, retain_graph=want_s)
+        grads = torch.autograd.grad(energy.sum(), pos_list, retain_graph=want_s or train, create_graph=train)
         out["f"] = [-gr for gr in grads]
     if want_s:  # model.py:527-535
-        grads = torch.autograd.grad(energy.sum(), strain_list)
+        grads = torch.autograd.grad(energy.sum(), strain_list, retain_graph=train, create_graph=train)
         out["s"] = [gr * (EV_A3_TO_GPA / v.detach()) for gr, v in zip(grads, vols)]
 
     # AtomRef (composition_model.py:175-205) + intensive normalisation (model.py:538-540)
@@ -334,18 +339,19 @@ def forward(
         ]
     )
     comp_e = (comp @ wref).to(dtype)
-    e_out = energy.detach()
+    e_out = energy if train else energy.detach()
     if a["is_intensive"]:
         e_out = e_out / atoms_per_graph
     out["e"] = e_out + comp_e
     if return_site_energies:
         shift = wref[z_all - 1].to(dtype)
         out["site_energies"] = list(torch.split(site_e.detach() + shift, atoms_per_graph.tolist()))
-    for k in ("m", "atom_fea"):
-        if k in out:
-            out[k] = [v.detach() for v in out[k]]
-    if "crystal_fea" in out:
-        out["crystal_fea"] = out["crystal_fea"].detach()
+    if not train:
+        for k in ("m", "atom_fea"):
+            if k in out:
+                out[k] = [v.detach() for v in out[k]]
+        if "crystal_fea" in out:
+            out["crystal_fea"] = out["crystal_fea"].detach()
     if return_intermediates:
         out["intermediates"] = {k: (v.detach() if v is not None else None) for k, v in inter.items()}
     return out

@@ -54,10 +54,12 @@ def _gate_fwd(p, ln):
     return core * gate, (y1, y2, core, gate, xh1, xh2, r1, r2)
 
 
-def _gate_bwd(g_out, saved, ln):
+def _gate_bwd(g_out, saved, ln, g_ln=None):
     y1, y2, core, gate, xh1, xh2, r1, r2 = saved
     gy1 = g_out * gate * _dsilu(y1)
     gy2 = g_out * core * gate * (1 - gate)
+    if ln is not None and g_ln is not None:  # training: d/d(gamma1, beta1, gamma2, beta2), accumulated
+        g_ln += torch.stack([(gy1 * xh1).sum(0), gy1.sum(0), (gy2 * xh2).sum(0), gy2.sum(0)]).reshape(-1).to(g_ln.dtype)
     if ln is not None:
         gy1 = _ln_bwd(gy1, xh1, r1, ln[0])
         gy2 = _ln_bwd(gy2, xh2, r2, ln[2])
@@ -84,6 +86,20 @@ def _rbf(d, freq, rc, p):
     return raw * env, draw * env + raw * denv
 
 
+def _rbf_dfreq(d, freq, rc, p):
+    """d(basis_k)/d(freq_k) [M,R]: sqrt(2/rc) cos(w d/rc)/rc * env."""
+    d = d[:, None]
+    x = d / rc
+    nrm = math.sqrt(2.0 / rc)
+    if p != 0:
+        a, b, cc = -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
+        env = 1 + a * x**p + b * x ** (p + 1) + cc * x ** (p + 2)
+        env = torch.where(x < 1, env, torch.zeros_like(env))
+    else:
+        env = torch.ones_like(x)
+    return nrm * torch.cos(freq * x) / rc * env
+
+
 class SpecKernels:
     """Drop-in for ``chgnet_b200._lib.CudaKernels`` in CPU tests."""
 
@@ -105,29 +121,40 @@ class SpecKernels:
         rvec.copy_(r), dist.copy_(d), rhat.copy_(r / d[:, None])
 
     # ---- K1b
-    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg):
+    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg, basis_out=None):
         du = dist[u2d.long()]
         bag, _ = _rbf(du, freq_ag, rc_ag, p)
         bbg, _ = _rbf(du, freq_bg, rc_bg, p)
         e0.copy_(bag @ w3t[0]), wag.copy_(bag @ w3t[1]), wbg.copy_(bbg @ w3t[2])
+        if basis_out is not None:  # training: [Eu][64] = ag basis in columns 0.., bg basis in columns 32..
+            R = freq_ag.shape[0]
+            basis_out.zero_()
+            basis_out[:, :R] = bag
+            basis_out[:, 32 : 32 + R] = bbg
 
-    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist):
+    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist, g_freq=None):
         du = dist[u2d.long()]
         _, dag = _rbf(du, freq_ag, rc_ag, p)
         _, dbg = _rbf(du, freq_bg, rc_bg, p)
         gb_ag = g_e0 @ w3[0] + g_wag @ w3[1]
         gb_bg = g_wbg @ w3[2]
         g_dist.copy_((gb_ag * dag).sum(dim=1) + (gb_bg * dbg).sum(dim=1))
+        if g_freq is not None:  # training: d/d(freq_ag), d/d(freq_bg) as fp64 [2][R], accumulated
+            g_freq[0] += (gb_ag * _rbf_dfreq(du, freq_ag, rc_ag, p)).sum(dim=0).to(g_freq.dtype)
+            g_freq[1] += (gb_bg * _rbf_dfreq(du, freq_bg, rc_bg, p)).sum(dim=0).to(g_freq.dtype)
 
     # ---- K2
-    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0):
+    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0, basis_out=None):
         u = (rhat[ang_di.long()] * rhat[ang_dj.long()]).sum(dim=1) * (1 - 1e-6)
         th = torch.acos(u)
         arg = th[:, None] * freq[None, :]
         f = torch.cat([torch.full_like(th[:, None], 1 / math.sqrt(2.0)), torch.sin(arg), torch.cos(arg)], dim=1)
         a0.copy_((f / math.sqrt(math.pi)) @ wt)
+        if basis_out is not None:  # training: [A][64], Fourier basis in columns 0..2F, zero padding after
+            basis_out.zero_()
+            basis_out[:, : f.shape[1]] = f / math.sqrt(math.pi)
 
-    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat):
+    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat, g_freq=None):
         ri, rj = rhat[ang_di.long()], rhat[ang_dj.long()]
         u = (ri * rj).sum(dim=1) * (1 - 1e-6)
         th = torch.acos(u)
@@ -136,6 +163,10 @@ class SpecKernels:
         gf = (g_a0 @ w) / math.sqrt(math.pi)  # [A, 2F+1]
         g_th = (gf[:, 1 : 1 + nf] * torch.cos(arg) * freq).sum(dim=1) - (gf[:, 1 + nf :] * torch.sin(arg) * freq).sum(dim=1)
         g_u = -g_th / torch.sqrt(1 - u * u) * (1 - 1e-6)
+        if g_freq is not None:  # training: d/d(freq) fp64 [F], accumulated
+            g_freq += ((gf[:, 1 : 1 + nf] * torch.cos(arg) - gf[:, 1 + nf :] * torch.sin(arg)) * th[:, None]).sum(dim=0).to(g_freq.dtype)
+        if g_rhat is None:
+            return
         g_rhat.index_add_(0, ang_di.long(), (g_u[:, None] * rj).to(g_rhat.dtype))
         g_rhat.index_add_(0, ang_dj.long(), (g_u[:, None] * ri).to(g_rhat.dtype))
 
@@ -163,7 +194,9 @@ class SpecKernels:
     def _atom_pre(self, pcn, pe, center, nbr, d2u):
         return pcn[center.long(), :128] + pe[d2u.long()] + pcn[nbr.long(), 128:]
 
-    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p):
+    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p, save_pre=None):
+        if save_pre is not None:
+            save_pre.copy_(self._atom_pre(pcn, pe, center, nbr, d2u))
         h = _silu(self._atom_pre(pcn, pe, center, nbr, d2u))
         p = torch.cat([h[:, :64] @ w2t[:, :64], h[:, 64:] @ w2t[:, 64:]], dim=1) + b2
         out, _ = _gate_fwd(p, ln)
@@ -171,12 +204,14 @@ class SpecKernels:
         if save_p is not None:
             save_p.copy_(p)
 
-    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w):
+    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w, g_p_out=None, g_ln=None):
         pre = self._atom_pre(pcn, pe, center, nbr, d2u)
         out, saved = _gate_fwd(save_p, ln)
         g_msg = g_agg[center.long()]
         g_w.copy_(g_msg * out)
-        g_p = _gate_bwd(g_msg * wag[d2u.long()], saved, ln)
+        g_p = _gate_bwd(g_msg * wag[d2u.long()], saved, ln, g_ln)
+        if g_p_out is not None:
+            g_p_out.copy_(g_p)
         g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
         g_pre.copy_(g_h * _dsilu(pre))
 
@@ -208,13 +243,15 @@ class SpecKernels:
         if save_p is not None:
             save_p.copy_(p)
 
-    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j):
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j, g_p_out=None, g_ln=None):
         out, saved = _gate_fwd(save_p, ln)
         wi, wj = wbg[ang_i.long()], wbg[ang_j.long()]
         g_upd = g_agg[ang_i.long()]
         gw_i.copy_(g_upd * out * wj)
         gw_j.copy_(g_upd * out * wi)
-        g_p = _gate_bwd(g_upd * wi * wj, saved, ln)
+        g_p = _gate_bwd(g_upd * wi * wj, saved, ln, g_ln)
+        if g_p_out is not None:
+            g_p_out.copy_(g_p)
         g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
         g_pre.copy_(g_h * _dsilu(save_pre))
 
@@ -226,11 +263,89 @@ class SpecKernels:
         if save_p is not None:
             save_p.copy_(p)
 
-    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre):
+    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre, g_ln=None):
         _, saved = _gate_fwd(save_p, ln)
         if g_ang_in is None:
             g_ang_in = torch.zeros_like(save_p[:, :64])
-        g_pre.copy_(_gate_bwd(g_ang_in, saved, ln))
+        g_pre.copy_(_gate_bwd(g_ang_in, saved, ln, g_ln))
+
+    # ---- training-only kernels (reference trainer.py:398-411: loss.backward() + optimizer.step())
+    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False):
+        """out[64][n] = act(x[x_rows])^T @ g[g_rows]; colsum[n] = sum_rows g[g_rows].  x, g, out may be
+        column-slice views (unit column stride)."""
+        xs = x if x_rows is None else x[x_rows.long()]
+        gs = g if g_rows is None else g[g_rows.long()]
+        if x_silu:
+            xs = _silu(xs)
+        out.copy_(xs.T @ gs)
+        if colsum is not None:
+            colsum.copy_(gs.sum(dim=0))
+
+    def colsum(self, a, out, b=None, rowscale=None):
+        """out[n] (fp64) = sum_rows a * b * rowscale[:, None]."""
+        v = a.to(out.dtype)
+        if b is not None:
+            v = v * b.to(out.dtype)
+        if rowscale is not None:
+            v = v * rowscale.to(out.dtype)[:, None]
+        out.copy_(v.sum(dim=0))
+
+    def readout_bwd(self, x, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, g_x, h_all, gz_all, g_h0, xhat):
+        """Reverse of the readout MLP with a per-atom seed dL/d(site energy); also returns what the
+        parameter gradients need: h_all[l] = input of linear l (l = L: input of the last linear),
+        gz_all[l] = dL/d(pre-activation l), g_h0 = dL/d(LayerNorm output), xhat."""
+        if ln is not None:
+            h0, xh, rstd = _ln_fwd(x, ln[0], ln[1])
+            xhat.copy_(xh)
+        else:
+            h0 = x
+        acts, h = [], h0
+        L = mlp_wt.shape[0]
+        for l in range(L):
+            h_all[l].copy_(h)
+            zl = h @ mlp_wt[l] + mlp_b[l]
+            acts.append(zl)
+            h = _silu(zl)
+        h_all[L].copy_(h)
+        g = w_last[None, :] * seed[:, None]
+        for l in reversed(range(L)):
+            gz = g * _dsilu(acts[l])
+            gz_all[l].copy_(gz)
+            g = gz @ mlp_w[l]
+        g_h0.copy_(g)
+        if ln is not None:
+            g = _ln_bwd(g, xh, rstd, ln[0])
+        g_x.copy_(g)
+
+    def magmom_bwd(self, x, w, b, g_m, g_x, g_lin):
+        """m = |x.w + b|: g_lin[i] = dL/d(x_i.w + b) = sign * g_m[i]; g_x += g_lin (x) w."""
+        g_lin.copy_(torch.sign(x @ w + b) * g_m)
+        g_x.add_(g_lin[:, None] * w[None, :])
+
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+        """torch.optim.Adam (no amsgrad) on one flat buffer; L2 weight decay added to the gradient."""
+        gg = g + weight_decay * p if weight_decay != 0 else g
+        m.mul_(beta1).add_(gg, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+        bc1, bc2 = 1 - beta1**step, 1 - beta2**step
+        p.sub_(lr / bc1 * m / ((v / bc2).sqrt() + eps))
+
+    def loss_terms(self, pred, target, kind, delta, g_pred, sums):
+        """One CombinedLoss term (trainer.py:779-869) over a flat vector with NaN-masked targets:
+        sums (fp64 [3]) += [sum loss_i, sum |err_i|, count]; g_pred = d loss_i / d pred_i (0 where masked).
+        kind 0 MSE, 1 MAE, 2 Huber(delta)."""
+        valid = ~torch.isnan(target)
+        err = torch.where(valid, pred - torch.nan_to_num(target), torch.zeros_like(pred))
+        if kind == 0:
+            li, gi = err**2, 2 * err
+        elif kind == 1:
+            li, gi = err.abs(), torch.sign(err)
+        else:
+            small = err.abs() <= delta
+            li = torch.where(small, 0.5 * err**2, delta * (err.abs() - 0.5 * delta))
+            gi = torch.where(small, err, delta * torch.sign(err))
+        g_pred.copy_(torch.where(valid, gi, torch.zeros_like(gi)))
+        sums += torch.stack([li.sum(), err.abs().sum(), valid.sum().to(li.dtype)]).to(sums.dtype)
 
     # ---- K7
     def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph, e_ref, g_x):
