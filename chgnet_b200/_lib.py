@@ -16,29 +16,36 @@ from torch import Tensor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libchgnet_b200.so")
 
-P, I, F = c_void_p, c_int32, c_float
+P, I, F, I64 = c_void_p, c_int32, c_float, c_int64
 
 # name -> argument ctypes (the trailing stream pointer included); mirrors the header 1:1
 SIGNATURES: dict[str, list] = {
     "chg_embed_atoms": [P, P, I, P, P],
     "chg_edge_geometry": [P, P, P, P, P, P, I, P, P, P, P],
-    "chg_bond_basis_embed": [P, P, I, P, P, I, F, F, I, P, P, P, P, P],
-    "chg_bond_basis_bwd": [P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
-    "chg_angle_basis_embed": [P, P, P, I, P, I, P, P, P],
-    "chg_angle_basis_bwd": [P, P, P, I, P, I, P, P, P, P],
+    "chg_bond_basis_embed": [P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
+    "chg_bond_basis_bwd": [P, P, I, P, P, I, F, F, I, P, P, P, P, P, P, P],
+    "chg_angle_basis_embed": [P, P, P, I, P, I, P, P, P, P],
+    "chg_angle_basis_bwd": [P, P, P, I, P, I, P, P, P, P, P],
     "chg_linear": [P, P, I, I, P, P, P, P, I, P, P],
     "chg_gather_rows": [P, P, I, I, P, P],
     "chg_scatter_rows": [P, P, I, I, P, P],
-    "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P],
-    "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
     "chg_segment_sum": [P, I, P, P, I, I, I, P, I, P],
     "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P],
-    "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P],
+    "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
     "chg_angle_update_fwd": [P, P, P, P, P, P, P, I, P, P, P, P],
-    "chg_angle_update_bwd": [P, P, I, P, P, P],
+    "chg_angle_update_bwd": [P, P, I, P, P, P, P],
     "chg_readout": [P, P, P, I, P, P, P, P, I, P, F, P, P, P, P, P, P, P],
     "chg_magmom": [P, I, P, F, P, P],
     "chg_force_virial": [P, P, P, P, P, P, P, P, P, P, I, P, P, P],
+    # training
+    "chg_wgrad": [P, I, P, I, P, I, P, I, I, P, I, P, P, P],
+    "chg_colsum": [P, I, P, I, P, I, I, P, P],
+    "chg_readout_bwd": [P, I, P, P, P, P, I, P, P, P, P, P, P, P, P],
+    "chg_magmom_bwd": [P, I, P, F, P, P, P, P],
+    "chg_loss_terms": [P, P, I, I, F, P, P, P],
+    "chg_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P],
 }
 
 _lib = None
@@ -68,6 +75,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.chg_launch_count.argtypes = []
     lib.chg_set_option.restype = c_int32
     lib.chg_set_option.argtypes = [c_char_p, c_int32]
+    lib.chg_wgrad_workspace_floats.restype = c_int64
+    lib.chg_wgrad_workspace_floats.argtypes = [c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32
@@ -128,26 +137,28 @@ class CudaKernels:
         self._call("chg_edge_geometry", _p(frac), _p(lattice), _p(owner), _p(center), _p(nbr), _p(image),
                    center.shape[0], _p(rvec), _p(dist), _p(rhat))
 
-    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg):
-        self._chk(dist, u2d, freq_ag, freq_bg, w3t, e0, wag, wbg)
+    def bond_basis_embed(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0, wag, wbg, basis_out=None):
+        self._chk(dist, u2d, freq_ag, freq_bg, w3t, e0, wag, wbg, basis_out)
         self._call("chg_bond_basis_embed", _p(dist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
-                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3t), _p(e0), _p(wag), _p(wbg))
+                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3t), _p(e0), _p(wag), _p(wbg),
+                   _p(basis_out))
 
-    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist):
-        self._chk(dist, u2d, freq_ag, freq_bg, w3, g_e0, g_wag, g_wbg, g_dist)
+    def bond_basis_bwd(self, dist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist,
+                       g_freq=None):
+        self._chk(dist, u2d, freq_ag, freq_bg, w3, g_e0, g_wag, g_wbg, g_dist, g_freq)
         self._call("chg_bond_basis_bwd", _p(dist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
                    freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3), _p(g_e0), _p(g_wag), _p(g_wbg),
-                   _p(g_dist))
+                   _p(g_dist), _p(g_freq))
 
-    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0):
-        self._chk(rhat, ang_di, ang_dj, freq, wt, a0)
+    def angle_basis_embed(self, rhat, ang_di, ang_dj, freq, wt, a0, basis_out=None):
+        self._chk(rhat, ang_di, ang_dj, freq, wt, a0, basis_out)
         self._call("chg_angle_basis_embed", _p(rhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
-                   freq.shape[0], _p(wt), _p(a0))
+                   freq.shape[0], _p(wt), _p(a0), _p(basis_out))
 
-    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat):
-        self._chk(rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat)
+    def angle_basis_bwd(self, rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat, g_freq=None):
+        self._chk(rhat, ang_di, ang_dj, freq, w, g_a0, g_rhat, g_freq)
         self._call("chg_angle_basis_bwd", _p(rhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
-                   freq.shape[0], _p(w), _p(g_a0), _p(g_rhat))
+                   freq.shape[0], _p(w), _p(g_a0), _p(g_rhat), _p(g_freq))
 
     def linear(self, x, wt, bias, residual, y, x_rows=None, y_rows=None):
         self._chk(x, wt, bias, residual, y, x_rows, y_rows)
@@ -163,15 +174,15 @@ class CudaKernels:
         self._chk(src, idx, dst)
         self._call("chg_scatter_rows", _p(src), _p(idx), idx.shape[0], src.shape[1], _p(dst))
 
-    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p):
-        self._chk(pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p)
+    def atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p, save_pre=None):
+        self._chk(pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p, save_pre)
         self._call("chg_atom_conv_fwd", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), center.shape[0],
-                   _p(w2t), _p(b2), _p(ln), _p(msg), _p(save_p))
+                   _p(w2t), _p(b2), _p(ln), _p(msg), _p(save_p), _p(save_pre))
 
-    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w):
-        self._chk(pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w)
+    def atom_conv_bwd(self, pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w, g_p=None, g_ln=None):
+        self._chk(pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w, g_p, g_ln)
         self._call("chg_atom_conv_bwd", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), center.shape[0],
-                   _p(save_p), _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(g_w))
+                   _p(save_p), _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(g_w), _p(g_p), _p(g_ln))
 
     def segment_sum(self, data, perm, ptr, accumulate, out):
         self._chk(data, perm, ptr)
@@ -186,19 +197,66 @@ class CudaKernels:
         self._call("chg_bond_conv_fwd", _p(pij), _p(px), _p(pa), _p(wbg), _p(ang_atom), _p(ang_i), _p(ang_j),
                    ang_i.shape[0], _p(w2t), _p(b2), _p(ln), _p(upd), _p(save_pre), _p(save_p))
 
-    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j):
-        self._chk(save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j)
+    def bond_conv_bwd(self, save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j, g_p=None,
+                      g_ln=None):
+        self._chk(save_pre, save_p, wbg, ang_i, ang_j, g_agg, w2, ln, g_pre, gw_i, gw_j, g_p, g_ln)
         self._call("chg_bond_conv_bwd", _p(save_pre), _p(save_p), _p(wbg), _p(ang_i), _p(ang_j), ang_i.shape[0],
-                   _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(gw_i), _p(gw_j))
+                   _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(gw_i), _p(gw_j), _p(g_p), _p(g_ln))
 
     def angle_update_fwd(self, pij, px, pa, ang, ang_atom, ang_i, ang_j, ln, ang_new, save_p):
         self._chk(pij, px, pa, ang, ang_atom, ang_i, ang_j, ln, ang_new, save_p)
         self._call("chg_angle_update_fwd", _p(pij), _p(px), _p(pa), _p(ang), _p(ang_atom), _p(ang_i), _p(ang_j),
                    ang_i.shape[0], _p(ln), _p(ang_new), _p(save_p))
 
-    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre):
-        self._chk(save_p, g_ang_in, ln, g_pre)
-        self._call("chg_angle_update_bwd", _p(save_p), _p(g_ang_in), save_p.shape[0], _p(ln), _p(g_pre))
+    def angle_update_bwd(self, save_p, g_ang_in, ln, g_pre, g_ln=None):
+        self._chk(save_p, g_ang_in, ln, g_pre, g_ln)
+        self._call("chg_angle_update_bwd", _p(save_p), _p(g_ang_in), save_p.shape[0], _p(ln), _p(g_pre), _p(g_ln))
+
+    # ------------------------------------------------------------------ training
+    @staticmethod
+    def _chk_rows(*tensors: Tensor | None) -> None:
+        for t in tensors:
+            if t is not None and (not t.is_cuda or t.stride(-1) != 1):
+                raise ChgnetB200Error("kernel arguments must be CUDA tensors with unit column stride")
+
+    def _workspace(self, n_out: int, device) -> Tensor:
+        need = int(self.lib.chg_wgrad_workspace_floats(n_out))
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != device:
+            ws = torch.empty(int(self.lib.chg_wgrad_workspace_floats(256)), dtype=torch.float32, device=device)
+            self._ws = ws
+        return ws
+
+    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False):
+        self._chk_rows(x, g, out)
+        self._chk(colsum, x_rows, g_rows)
+        m = x_rows.shape[0] if x_rows is not None else (g_rows.shape[0] if g_rows is not None else x.shape[0])
+        self._call("chg_wgrad", _p(x), x.stride(0), _p(x_rows), int(bool(x_silu)), _p(g), g.stride(0), _p(g_rows), m,
+                   out.shape[1], _p(out), out.stride(0), _p(colsum), _p(self._workspace(out.shape[1], x.device)))
+
+    def colsum(self, a, out, b=None, rowscale=None):
+        self._chk_rows(a, b)
+        self._chk(out, rowscale)
+        self._call("chg_colsum", _p(a), a.stride(0), _p(b), b.stride(0) if b is not None else 0, _p(rowscale),
+                   a.shape[0], a.shape[1], _p(out))
+
+    def readout_bwd(self, x, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, g_x, h_all, gz_all, g_h0, xhat):
+        self._chk(x, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, g_x, h_all, gz_all, g_h0, xhat)
+        self._call("chg_readout_bwd", _p(x), x.shape[0], _p(ln), _p(mlp_wt), _p(mlp_w), _p(mlp_b), mlp_wt.shape[0],
+                   _p(w_last), _p(seed), _p(g_x), _p(h_all), _p(gz_all), _p(g_h0), _p(xhat))
+
+    def magmom_bwd(self, x, w, b, g_m, g_x, g_lin):
+        self._chk(x, w, g_m, g_x, g_lin)
+        self._call("chg_magmom_bwd", _p(x), x.shape[0], _p(w), float(b), _p(g_m), _p(g_x), _p(g_lin))
+
+    def loss_terms(self, pred, target, kind, delta, g_pred, sums):
+        self._chk(pred, target, g_pred, sums)
+        self._call("chg_loss_terms", _p(pred), _p(target), pred.numel(), int(kind), float(delta), _p(g_pred), _p(sums))
+
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+        self._chk(p, g, m, v)
+        self._call("chg_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                   float(eps), float(weight_decay), int(step))
 
     def readout(self, x, z, owner, ln, mlp_wt, mlp_w, mlp_b, w_last, b_last, atom_ref, site_e, h_out, e_graph,
                 e_ref, g_x):

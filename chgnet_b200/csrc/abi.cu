@@ -67,5 +67,5 @@ extern "C" int chg_set_option(const char* name, int32_t value) {
 }
 
 extern "C" const char* chg_last_error(void) { return chg::g_err; }
-extern "C" int chg_abi_version(void) { return 1; }
+extern "C" int chg_abi_version(void) { return 2; }
 extern "C" int64_t chg_launch_count(void) { return chg::g_launches.load(std::memory_order_relaxed); }

@@ -203,7 +203,9 @@ struct BwdSmem {
   static constexpr int TOTAL_BYTES = (IDX_OFF + 3 * TM) * 4;
 };
 
-template <int MODE>
+// TRAIN adds what the parameter gradients need (reference trainer.py:409 loss.backward()): dL/dp rows
+// for the second-layer weight gradients and the LayerNorm affine gradients, reduced per CTA.
+template <int MODE, bool TRAIN>
 __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
   using L = BwdSmem<MODE>;
   extern __shared__ __align__(16) float smem[];
@@ -219,6 +221,9 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
 
   if (L::HAS_W2) copy_to_smem(s_w2, a.w2, 128 * 64, tid);
   if (use_ln) s_ln[tid] = a.ln[tid];
+  float ln_acc[16];  // TRAIN: this thread's 4 columns x (gamma1, beta1, gamma2, beta2)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ln_acc[j] = 0.f;
 
   const int n_tiles = (a.n_rows + TM - 1) / TM;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -295,6 +300,15 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
         gy2[j] = gj * core[j] * gate[j] * (1.f - gate[j]);
       }
       if (use_ln) {
+        if (TRAIN && valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ln_acc[j] = fmaf(gy1[j], xh1[j], ln_acc[j]);
+            ln_acc[4 + j] += gy1[j];
+            ln_acc[8 + j] = fmaf(gy2[j], xh2[j], ln_acc[8 + j]);
+            ln_acc[12 + j] += gy2[j];
+          }
+        }
         // g_p = rstd * (gx - mean(gx) - xhat * mean(gx * xhat)), gx = gy * gamma
         float gx[4], sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -321,6 +335,10 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
       }
       const float4 gpc = make_float4(gy1[0], gy1[1], gy1[2], gy1[3]);
       const float4 gpg = make_float4(gy2[0], gy2[1], gy2[2], gy2[3]);
+      if (TRAIN && L::HAS_W2 && valid && a.g_p != nullptr) {
+        stg4(a.g_p + (size_t)g * 128 + c0, gpc);
+        stg4(a.g_p + (size_t)g * 128 + 64 + c0, gpg);
+      }
       if (L::HAS_W2) {
         sts4(s_g + row * HS + c0, gpc);
         sts4(s_g + row * HS + 64 + c0, gpg);
@@ -367,6 +385,20 @@ __global__ void __launch_bounds__(NTHR, 2) gated_bwd_kernel(const BwdArgs a) {
         }
       }
     }
+  }
+  if (TRAIN && use_ln && a.g_ln != nullptr) {
+    // reduce the 16 row-groups (ty) of every column in shared memory, then one fp64 atomic per column
+    __syncthreads();
+    float* s_red = smem;  // [16 ty][256]; the weight / tile regions are free now
+#pragma unroll
+    for (int which = 0; which < 4; ++which)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_red[ty * 256 + which * 64 + c0 + j] = ln_acc[which * 4 + j];
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) tot += s_red[r * 256 + tid];
+    atomicAdd(a.g_ln + tid, (double)tot);
   }
 }
 
@@ -735,18 +767,26 @@ int launch_fwd(const FwdArgs& a, cudaStream_t stream) {
   CHG_LAUNCH_END();
 }
 
-template <int MODE>
-int launch_bwd(const BwdArgs& a, cudaStream_t stream) {
+template <int MODE, bool TRAIN>
+int launch_bwd_t(const BwdArgs& a, cudaStream_t stream) {
   if (a.n_rows == 0) return CHG_OK;
-  constexpr int smem = BwdSmem<MODE>::TOTAL_BYTES;
+  // the TRAIN epilogue reduces through 16 x 256 floats of shared memory
+  constexpr int smem = TRAIN ? (BwdSmem<MODE>::TOTAL_BYTES > 16 * 256 * 4 ? BwdSmem<MODE>::TOTAL_BYTES : 16 * 256 * 4)
+                             : BwdSmem<MODE>::TOTAL_BYTES;
   static int slots = 0;
   if (slots == 0) {
-    CHG_CUDA(cudaFuncSetAttribute(gated_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    slots = resident_ctas(gated_bwd_kernel<MODE>, smem);
+    CHG_CUDA(cudaFuncSetAttribute(gated_bwd_kernel<MODE, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    slots = resident_ctas(gated_bwd_kernel<MODE, TRAIN>, smem);
   }
   const int n_tiles = (a.n_rows + TM - 1) / TM;
-  gated_bwd_kernel<MODE><<<min(n_tiles, slots), NTHR, smem, stream>>>(a);
+  gated_bwd_kernel<MODE, TRAIN><<<min(n_tiles, slots), NTHR, smem, stream>>>(a);
   CHG_LAUNCH_END();
+}
+
+template <int MODE>
+int launch_bwd(const BwdArgs& a, cudaStream_t stream) {
+  if (a.g_p != nullptr || a.g_ln != nullptr) return launch_bwd_t<MODE, true>(a, stream);
+  return launch_bwd_t<MODE, false>(a, stream);
 }
 
 template <typename KernelT, typename ArgsT>
@@ -769,13 +809,15 @@ using namespace chg::gated;
 
 extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float* wag, const int32_t* center,
                                  const int32_t* nbr, const int32_t* d2u, int32_t n_edges, const float* w2t,
-                                 const float* b2, const float* ln, float* msg, float* save_p, void* stream) {
+                                 const float* b2, const float* ln, float* msg, float* save_p, float* save_pre,
+                                 void* stream) {
   CHG_CHECK_ARG(n_edges >= 0, "negative size");
   if (n_edges == 0) return CHG_OK;
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && w2t && b2 && msg, "null pointer");
-  FwdArgs a{pcn, pe, nullptr, nullptr, wag, center, nbr, d2u, n_edges, w2t, b2, ln, msg, nullptr, save_p};
-  if (gated_impl() == 1) return atom_conv_fwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+  FwdArgs a{pcn, pe, nullptr, nullptr, wag, center, nbr, d2u, n_edges, w2t, b2, ln, msg, save_pre, save_p};
+  const bool train = save_pre != nullptr;  // training extras exist in the default implementation only
+  if (gated_impl() == 1 && !train) return atom_conv_fwd_tc(a, as_stream(stream));
+  if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;
     return launch2(gated2_fwd_kernel<ATOM>, a, slots, as_stream(stream));
   }
@@ -785,13 +827,14 @@ extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float*
 extern "C" int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag, const int32_t* center,
                                  const int32_t* nbr, const int32_t* d2u, int32_t n_edges, const float* save_p,
                                  const float* g_agg, const float* w2, const float* ln, float* g_pre, float* g_w,
-                                 void* stream) {
+                                 float* g_p, double* g_ln, void* stream) {
   CHG_CHECK_ARG(n_edges >= 0, "negative size");
   if (n_edges == 0) return CHG_OK;
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && save_p && g_agg && w2 && g_pre && g_w, "null pointer");
-  BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, w2, ln, g_pre, g_w, nullptr};
-  if (gated_impl() == 1) return atom_conv_bwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+  BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, w2, ln, g_pre, g_w, nullptr, g_p, g_ln};
+  const bool train = g_p != nullptr || g_ln != nullptr;
+  if (gated_impl() == 1 && !train) return atom_conv_bwd_tc(a, as_stream(stream));
+  if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;
     return launch2(gated2_bwd_kernel<ATOM>, a, slots, as_stream(stream));
   }
@@ -816,14 +859,16 @@ extern "C" int chg_bond_conv_fwd(const float* pij, const float* px, const float*
 
 extern "C" int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg, const int32_t* ang_i,
                                  const int32_t* ang_j, int32_t n_angles, const float* g_agg, const float* w2,
-                                 const float* ln, float* g_pre, float* gw_i, float* gw_j, void* stream) {
+                                 const float* ln, float* g_pre, float* gw_i, float* gw_j, float* g_p, double* g_ln,
+                                 void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
   CHG_CHECK_ARG(save_pre && save_p && wbg && ang_i && ang_j && g_agg && w2 && g_pre && gw_i && gw_j, "null pointer");
   BwdArgs a{nullptr, nullptr, wbg, ang_i, ang_j, nullptr, n_angles, save_pre, save_p, g_agg, w2, ln,
-            g_pre, gw_i, gw_j};
-  if (gated_impl() == 1) return bond_conv_bwd_tc(a, as_stream(stream));
-  if (gated_impl() == 2) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
+            g_pre, gw_i, gw_j, g_p, g_ln};
+  const bool train = g_p != nullptr || g_ln != nullptr;
+  if (gated_impl() == 1 && !train) return bond_conv_bwd_tc(a, as_stream(stream));
+  if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;
     return launch2(gated2_bwd_kernel<BOND>, a, slots, as_stream(stream));
   }
@@ -842,11 +887,11 @@ extern "C" int chg_angle_update_fwd(const float* pij, const float* px, const flo
 }
 
 extern "C" int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles, const float* ln,
-                                    float* g_pre, void* stream) {
+                                    float* g_pre, double* g_ln, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   if (n_angles == 0) return CHG_OK;
   CHG_CHECK_ARG(save_p && g_pre, "null pointer");
   BwdArgs a{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_angles, nullptr, save_p, g_ang_in,
-            nullptr, ln, g_pre, nullptr, nullptr};
+            nullptr, ln, g_pre, nullptr, nullptr, nullptr, g_ln};
   return launch_bwd<ANGLE>(a, as_stream(stream));
 }

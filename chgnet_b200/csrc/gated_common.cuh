@@ -44,6 +44,9 @@ struct BwdArgs {
   float* g_pre;   // [rows][128]
   float* g_w0;    // ATOM: g_w; BOND: gw_i
   float* g_w1;    // BOND: gw_j
+  // training only (parameter gradients); both null in inference
+  float* g_p;     // [rows][128] dL/dp (second-layer output, before LayerNorm) or null
+  double* g_ln;   // [4][64] accumulated dL/d(gamma1, beta1, gamma2, beta2) or null
 };
 
 // LayerNorm statistics of one 64-wide row spread over 16 lanes (4 values each)

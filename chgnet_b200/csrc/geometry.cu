@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256)
 bond_basis_embed_kernel(const float* __restrict__ dist, const int32_t* __restrict__ u2d, int n_bonds,
                         const float* __restrict__ freq_ag, const float* __restrict__ freq_bg, int R, float rc_ag,
                         float rc_bg, int p, const float* __restrict__ w3t, float* __restrict__ e0,
-                        float* __restrict__ wag, float* __restrict__ wbg) {
+                        float* __restrict__ wag, float* __restrict__ wbg, float* __restrict__ basis_out) {
   extern __shared__ __align__(16) float s_w[];  // [3][R][64]
   for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3t[i];
   __syncthreads();
@@ -110,6 +110,10 @@ bond_basis_embed_kernel(const float* __restrict__ dist, const int32_t* __restric
       b_ag[q] = lane < R ? ea.env * (nrm_ag * sinf(f_ag * (d * inv_ag)) / d) : 0.f;
       b_bg[q] = lane < R ? eb.env * (nrm_bg * sinf(f_bg * (d * inv_bg)) / d) : 0.f;
       bg_live = bg_live || eb.env != 0.f || !(d == d);  // NaN propagates
+      if (basis_out != nullptr && u0 + q < n_bonds) {  // training: [ag basis | bg basis], 32 columns each
+        basis_out[(size_t)(u0 + q) * 64 + lane] = b_ag[q];
+        basis_out[(size_t)(u0 + q) * 64 + 32 + lane] = b_bg[q];
+      }
     }
     float o[IT][6];
 #pragma unroll
@@ -157,7 +161,7 @@ bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict_
                       const float* __restrict__ freq_ag, const float* __restrict__ freq_bg, int R, float rc_ag,
                       float rc_bg, int p, const float* __restrict__ w3, const float* __restrict__ g_e0,
                       const float* __restrict__ g_wag, const float* __restrict__ g_wbg,
-                      float* __restrict__ g_dist) {
+                      float* __restrict__ g_dist, double* __restrict__ g_freq) {
   extern __shared__ __align__(16) float s_w[];  // [3][64][R]
   for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3[i];
   __syncthreads();
@@ -168,6 +172,7 @@ bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict_
   const float f_ag = freq_ag[kl], f_bg = freq_bg[kl];
   const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
   constexpr int IT = 2;  // bonds per warp iteration
+  double gf_ag = 0.0, gf_bg = 0.0;  // training: lane k accumulates dL/d freq_k
   for (int u0 = warp * IT; u0 < n_bonds; u0 += n_warps * IT) {
     float d[IT], a0[IT], a1[IT], b0[IT], b1[IT], c0[IT], c1[IT];
     Envelope ea[IT], eb[IT];
@@ -219,8 +224,12 @@ bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict_
         const float raw = nrm_ag * sn / d[q];
         const float draw = nrm_ag * ((f_ag / rc_ag) * cs / d[q] - sn / (d[q] * d[q]));
         contrib = gb_ag[q] * fmaf(draw, ea[q].env, raw * ea[q].denv);
+        const bool live_q = u0 + q < n_bonds;
+        // d basis_k / d freq_k = norm cos(w d/rc) / rc * env
+        if (g_freq != nullptr && live_q) gf_ag += (double)(gb_ag[q] * (nrm_ag * cs / rc_ag) * ea[q].env);
         if (eb[q].env != 0.f || eb[q].denv != 0.f || !(d[q] == d[q])) {
           sincosf(f_bg * (d[q] / rc_bg), &sn, &cs);
+          if (g_freq != nullptr && live_q) gf_bg += (double)(gb_bg[q] * (nrm_bg * cs / rc_bg) * eb[q].env);
           const float raw2 = nrm_bg * sn / d[q];
           const float draw2 = nrm_bg * ((f_bg / rc_bg) * cs / d[q] - sn / (d[q] * d[q]));
           contrib += gb_bg[q] * fmaf(draw2, eb[q].env, raw2 * eb[q].denv);
@@ -229,6 +238,10 @@ bond_basis_bwd_kernel(const float* __restrict__ dist, const int32_t* __restrict_
       contrib = sum32(contrib);
       if (lane == 0 && u0 + q < n_bonds) g_dist[u0 + q] = contrib;
     }
+  }
+  if (g_freq != nullptr && lane < R) {
+    atomicAdd(g_freq + lane, gf_ag);
+    atomicAdd(g_freq + R + lane, gf_bg);
   }
 }
 
@@ -247,7 +260,7 @@ __device__ __forceinline__ float angle_cos(const float* __restrict__ rhat, int d
 __global__ void __launch_bounds__(256)
 angle_basis_embed_kernel(const float* __restrict__ rhat, const int32_t* __restrict__ ang_di,
                          const int32_t* __restrict__ ang_dj, int n_angles, const float* __restrict__ freq, int nf,
-                         const float* __restrict__ wt, float* __restrict__ a0) {
+                         const float* __restrict__ wt, float* __restrict__ a0, float* __restrict__ basis_out) {
   extern __shared__ __align__(16) float s_w[];  // [2nf+1][64]
   const int nb = 2 * nf + 1;
   for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = wt[i];
@@ -272,6 +285,10 @@ angle_basis_embed_kernel(const float* __restrict__ rhat, const int32_t* __restri
       else if (is_sin) v = sinf(w * th);
       else if (is_cos) v = cosf(w * th);
       f[q] = v * inv_sqrt_pi;
+      if (basis_out != nullptr && a0i + q < n_angles) {  // training: basis in columns 0..2nf, zeros after
+        basis_out[(size_t)(a0i + q) * 64 + lane] = f[q];
+        basis_out[(size_t)(a0i + q) * 64 + 32 + lane] = 0.f;
+      }
     }
     float oa[IT], ob[IT];
 #pragma unroll
@@ -299,7 +316,8 @@ angle_basis_embed_kernel(const float* __restrict__ rhat, const int32_t* __restri
 __global__ void __launch_bounds__(256)
 angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict__ ang_di,
                        const int32_t* __restrict__ ang_dj, int n_angles, const float* __restrict__ freq, int nf,
-                       const float* __restrict__ w, const float* __restrict__ g_a0, double* __restrict__ g_rhat) {
+                       const float* __restrict__ w, const float* __restrict__ g_a0, double* __restrict__ g_rhat,
+                       double* __restrict__ g_freq) {
   extern __shared__ __align__(16) float s_w[];  // [64][2nf+1]
   const int nb = 2 * nf + 1;
   for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = w[i];
@@ -316,6 +334,7 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
   // atomic per component when di changes (cuts same-address fp64 atomics by the run length).
   constexpr int CHUNK = 16;
   const int n_chunks = (n_angles + CHUNK - 1) / CHUNK;
+  double gfr = 0.0;  // training: sin lane k and cos lane k both accumulate into dL/d freq_k
   for (int ch = warp; ch < n_chunks; ch += n_warps) {
     const int a_beg = ch * CHUNK, a_end = min(a_beg + CHUNK, n_angles);
     int cur_di = -1;
@@ -346,7 +365,12 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
         float g_th = 0.f;
         if (is_sin) g_th = gf[q] * wf * cosf(wf * th[q]);
         else if (is_cos) g_th = -gf[q] * wf * sinf(wf * th[q]);
+        if (g_freq != nullptr) {  // d sin(w th)/dw = th cos(w th), d cos(w th)/dw = -th sin(w th)
+          if (is_sin) gfr += (double)(gf[q] * th[q] * cosf(wf * th[q]) * inv_sqrt_pi);
+          else if (is_cos) gfr -= (double)(gf[q] * th[q] * sinf(wf * th[q]) * inv_sqrt_pi);
+        }
         g_th = sum32(g_th) * inv_sqrt_pi;
+        if (g_rhat == nullptr) continue;
         // d theta / d u' = -1/sqrt(1-u'^2); u' = (1-1e-6) u
         const float g_u = -g_th / sqrtf(1.f - u[q] * u[q]) * (1.f - 1e-6f);
         if (di[q] != cur_di) {
@@ -358,7 +382,11 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
         else if (lane < 6) atomicAdd(g_rhat + (size_t)dj[q] * 3 + (lane - 3), (double)(g_u * ri[q][lane - 3]));
       }
     }
-    if (cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
+    if (g_rhat != nullptr && cur_di >= 0 && lane < 3) atomicAdd(g_rhat + (size_t)cur_di * 3 + lane, acc_i);
+  }
+  if (g_freq != nullptr) {
+    if (is_sin) atomicAdd(g_freq + lane - 1, gfr);
+    else if (is_cos) atomicAdd(g_freq + lane - 1 - nf, gfr);
   }
 }
 
@@ -470,54 +498,55 @@ extern "C" int chg_edge_geometry(const float* frac, const float* lattice, const 
 
 extern "C" int chg_bond_basis_embed(const float* dist, const int32_t* u2d, int32_t n_bonds, const float* freq_ag,
                                     const float* freq_bg, int32_t n_radial, float rc_ag, float rc_bg, int32_t p,
-                                    const float* w3t, float* e0, float* wag, float* wbg, void* stream) {
+                                    const float* w3t, float* e0, float* wag, float* wbg, float* basis_out,
+                                    void* stream) {
   CHG_CHECK_ARG(n_bonds >= 0, "negative size");
   CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
   if (n_bonds == 0) return CHG_OK;
   CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3t && e0 && wag && wbg, "null pointer");
   const int smem = 3 * n_radial * 64 * 4;
   bond_basis_embed_kernel<<<warp_grid((n_bonds + 3) / 4), 256, smem, as_stream(stream)>>>(
-      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3t, e0, wag, wbg);
+      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3t, e0, wag, wbg, basis_out);
   CHG_LAUNCH_END();
 }
 
 extern "C" int chg_bond_basis_bwd(const float* dist, const int32_t* u2d, int32_t n_bonds, const float* freq_ag,
                                   const float* freq_bg, int32_t n_radial, float rc_ag, float rc_bg, int32_t p,
                                   const float* w3, const float* g_e0, const float* g_wag, const float* g_wbg,
-                                  float* g_dist, void* stream) {
+                                  float* g_dist, double* g_freq, void* stream) {
   CHG_CHECK_ARG(n_bonds >= 0, "negative size");
   CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
   if (n_bonds == 0) return CHG_OK;
   CHG_CHECK_ARG(dist && u2d && freq_ag && freq_bg && w3 && g_e0 && g_wag && g_wbg && g_dist, "null pointer");
   const int smem = 3 * n_radial * 64 * 4;
   bond_basis_bwd_kernel<<<warp_grid((n_bonds + 1) / 2), 256, smem, as_stream(stream)>>>(
-      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist);
+      dist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3, g_e0, g_wag, g_wbg, g_dist, g_freq);
   CHG_LAUNCH_END();
 }
 
 extern "C" int chg_angle_basis_embed(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
                                      int32_t n_angles, const float* freq, int32_t n_freq, const float* wt, float* a0,
-                                     void* stream) {
+                                     float* basis_out, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
   if (n_angles == 0) return CHG_OK;
   CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && wt && a0, "null pointer");
   const int smem = (2 * n_freq + 1) * 64 * 4;
   angle_basis_embed_kernel<<<warp_grid((n_angles + 3) / 4), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles,
-                                                                                  freq, n_freq, wt, a0);
+                                                                                  freq, n_freq, wt, a0, basis_out);
   CHG_LAUNCH_END();
 }
 
 extern "C" int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj, int32_t n_angles,
                                    const float* freq, int32_t n_freq, const float* w, const float* g_a0,
-                                   double* g_rhat, void* stream) {
+                                   double* g_rhat, double* g_freq, void* stream) {
   CHG_CHECK_ARG(n_angles >= 0, "negative size");
   CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
   if (n_angles == 0) return CHG_OK;
-  CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && w && g_a0 && g_rhat, "null pointer");
+  CHG_CHECK_ARG(rhat && ang_di && ang_dj && freq && w && g_a0 && (g_rhat || g_freq), "null pointer");
   const int smem = (2 * n_freq + 1) * 64 * 4;
   angle_basis_bwd_kernel<<<warp_grid((n_angles + 15) / 16), 256, smem, as_stream(stream)>>>(rhat, ang_di, ang_dj, n_angles, freq,
-                                                                                n_freq, w, g_a0, g_rhat);
+                                                                                n_freq, w, g_a0, g_rhat, g_freq);
   CHG_LAUNCH_END();
 }
 

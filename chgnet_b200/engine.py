@@ -203,7 +203,7 @@ class Engine:
         h_out = self._new(b, N, 64) if (need_crystal_fea or keep_intermediates) else None
         energy = self._zeros(b, B, dtype=torch.float64)
         e_ref = self._zeros(b, B, dtype=torch.float64)
-        g_x = self._new(b, N, 64) if (need_grad and not train) else None
+        g_x = self._new(b, N, 64) if need_grad else None
         K.readout(x, b.z, b.owner, pw.readout_ln, pw.mlp_wt, pw.mlp_w, pw.mlp_b, pw.w_last, pw.b_last,
                   pw.atom_ref, site_e, h_out, energy, e_ref, g_x)
         crystal_fea = None
@@ -226,6 +226,11 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ reverse
+    def input_grads(self, out: EngineOutput) -> None:
+        """Forces / virial of a ``train=True`` forward (values only; the state is kept for
+        :meth:`param_grads`)."""
+        self._reverse(out.extras["train_state"], out, None)
+
     def param_grads(self, out: EngineOutput, seed_energy: Tensor, seed_magmom: Tensor | None = None) -> dict:
         """Training reverse pass (replaces ``loss.backward()``, trainer.py:409-410) for losses on the
         energies and magnetic moments: dL/d(parameter) for ``seed_energy[g] = dL/d(E_g)`` (E_g the

@@ -31,7 +31,7 @@ from chgnet_b200 import PredTask
 from chgnet_b200.batch import DeviceBatch, build_batch
 from chgnet_b200.engine import EV_A3_TO_GPA, Engine
 from chgnet_b200.graph import CrystalGraph, is_graph_like
-from chgnet_b200.weights import pack_weights
+from chgnet_b200.weights import pack_weights, unpack_grads
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
@@ -156,6 +156,26 @@ def _init_param(shape, kind: str, a: dict) -> Tensor:
         cm = a.get("composition_model")
         return _atomref_table(cm if isinstance(cm, str) else "MPtrj")
     raise AssertionError(kind)
+
+
+class _ParamGradBridge(torch.autograd.Function):
+    """Joins the kernel engine to autograd: backward = the engine's training reverse pass."""
+
+    @staticmethod
+    def forward(ctx, model, eng_out, names, e, m, *params):
+        ctx.model, ctx.eng_out, ctx.names = model, eng_out, names
+        ctx.has_m = m is not None
+        return e.clone(), (m.clone() if m is not None else e.new_zeros(0))
+
+    @staticmethod
+    def backward(ctx, g_e, g_m):
+        model, out = ctx.model, ctx.eng_out
+        engine = model._get_engine()
+        n = torch.tensor(model.last_batch.atoms_per_graph, device=g_e.device, dtype=g_e.dtype)
+        seed_e = g_e / n if model.is_intensive else g_e  # d/d(extensive model energy)
+        G = engine.param_grads(out, seed_e.contiguous(), g_m.contiguous() if ctx.has_m else None)
+        grads = unpack_grads(G, model.state_dict())
+        return (None, None, None, None, None, *[grads[k] for k in ctx.names])
 
 
 class _Node(nn.Module):
@@ -313,17 +333,26 @@ class CHGNet(nn.Module):
             self._engine_key = key
         return self._engine
 
+    def mark_params_updated(self) -> None:
+        """Call after changing parameter storage in place from outside autograd (e.g. the fused Adam
+        kernel): the packed kernel weights are rebuilt on the next forward."""
+        self._engine_key = None
+
     # ------------------------------------------------------------------ forward
-    def _run(self, graphs, task, return_site_energies, return_atom_feas, return_crystal_feas) -> dict[str, Any]:
+    def _run(self, graphs, task, return_site_energies, return_atom_feas, return_crystal_feas,
+             train: bool = False) -> dict[str, Any]:
         """One batch through the kernel engine; returns BATCHED device tensors."""
         engine = self._get_engine()
         need_grad = "f" in task or "s" in task
         # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
         compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
-        batch = build_batch(graphs, self.device, with_reverse=need_grad, compact_bonds=compact)
+        batch = build_batch(graphs, self.device, with_reverse=need_grad or train, compact_bonds=compact)
         self.last_batch = batch
         out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
-                         need_crystal_fea=return_crystal_feas)
+                         need_crystal_fea=return_crystal_feas, train=train)
+        if train and need_grad:  # forces / stresses of a training step: values only (see forward)
+            engine.input_grads(out)
+        self._last_out = out
         n_dev = torch.tensor(batch.atoms_per_graph, device=self.device)
         raw: dict[str, Any] = {"atoms_per_graph": n_dev}
         if return_atom_feas:
@@ -359,11 +388,23 @@ class CHGNet(nn.Module):
         """Prediction for a list of CrystalGraphs (reference model.py:330-387): ``e`` Tensor[B],
         ``f`` / ``m`` / ``site_energies`` / ``atom_fea`` lists of per-graph tensors, ``s`` list of
         [3,3], ``crystal_fea`` Tensor[B,64], ``atoms_per_graph``."""
-        if self.training and torch.is_grad_enabled() and not getattr(self, "_warned_train", False):
-            warnings.warn("chgnet_b200 (round 1) returns tensors without autograd history: "
-                          "inference only, parameter gradients are not available yet", stacklevel=2)
-            self._warned_train = True
-        raw = self._run(graphs, task, return_site_energies, return_atom_feas, return_crystal_feas)
+        train = self.training and torch.is_grad_enabled()
+        raw = self._run(graphs, task, return_site_energies, return_atom_feas, return_crystal_feas, train=train)
+        if train:
+            # ``e`` and ``m`` carry autograd history to the parameters (the reference's training mode,
+            # model.py:518 / trainer.py:398-410); ``f`` and ``s`` are values only: a loss on them needs
+            # the second-order pass, which is not built yet (DESIGN.md §9)
+            if ("f" in task or "s" in task) and not getattr(self, "_warned_train", False):
+                warnings.warn("chgnet_b200: forces / stresses returned in training mode carry no autograd "
+                              "history; only losses on e and m reach the parameters", stacklevel=2)
+                self._warned_train = True
+            names = [n for n, p in self.named_parameters() if p.requires_grad]
+            params = [p for _, p in self.named_parameters() if p.requires_grad]
+            m_in = raw.get("m")
+            e, m = _ParamGradBridge.apply(self, self._last_out, names, raw["e"], m_in, *params)
+            raw["e"] = e
+            if m_in is not None:
+                raw["m"] = m
         n_list = self.last_batch.atoms_per_graph
         pred: dict[str, Any] = {}
         for key, val in raw.items():

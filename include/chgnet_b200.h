@@ -65,24 +65,31 @@ int chg_edge_geometry(const float* frac, const float* lattice, const int32_t* at
 int chg_bond_basis_embed(const float* dist, const int32_t* u2d, int32_t n_bonds,
                          const float* freq_ag, const float* freq_bg, int32_t n_radial,
                          float rc_ag, float rc_bg, int32_t p, const float* w3t,
-                         float* e0, float* wag, float* wbg, void* stream);
+                         float* e0, float* wag, float* wbg,
+                         float* basis_out /* training: [Eu][64] = ag basis | bg basis, or NULL */,
+                         void* stream);
 /* reverse of K1b: g_dist[u] = d(E)/d(d_u).  w3 = [3][64][n_radial] (PyTorch layout) */
 int chg_bond_basis_bwd(const float* dist, const int32_t* u2d, int32_t n_bonds,
                        const float* freq_ag, const float* freq_bg, int32_t n_radial,
                        float rc_ag, float rc_bg, int32_t p, const float* w3,
                        const float* g_e0, const float* g_wag, const float* g_wbg,
-                       float* g_dist, void* stream);
+                       float* g_dist,
+                       double* g_freq /* training: [2][n_radial] += dL/d(freq_ag, freq_bg), or NULL */,
+                       void* stream);
 
 /* ---- K2: Fourier angle basis fused with angle_embedding
  * (model.py:864-870, encoders.py:144-146, basis.py:35-40, model.py:439).
  * n_basis = 2*n_freq+1; wt = [n_basis][64]                                        */
 int chg_angle_basis_embed(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
                           int32_t n_angles, const float* freq, int32_t n_freq,
-                          const float* wt, float* a0, void* stream);
+                          const float* wt, float* a0,
+                          float* basis_out /* training: [A][64], basis in columns 0..2*n_freq, or NULL */,
+                          void* stream);
 /* reverse of K2: g_rhat[e] += dE/d rhat_e (fp64 atomics); w = [64][n_basis]        */
 int chg_angle_basis_bwd(const float* rhat, const int32_t* ang_di, const int32_t* ang_dj,
                         int32_t n_angles, const float* freq, int32_t n_freq,
-                        const float* w, const float* g_a0, double* g_rhat, void* stream);
+                        const float* w, const float* g_a0, double* g_rhat /* may be NULL if g_freq */,
+                        double* g_freq /* training: [n_freq] += dL/d(freq), or NULL */, void* stream);
 
 /* ---- dense feature mixing: y[yr(r)] = x[xr(r)] @ wt (+ bias) (+ residual[yr(r)]), r < m
  * x [.][k], wt [k][n_out], k in {64,128,256}, n_out multiple of 64; xr = x_rows ?
@@ -108,13 +115,15 @@ int chg_scatter_rows(const float* src, const int32_t* idx, int32_t n, int32_t wi
 int chg_atom_conv_fwd(const float* pcn, const float* pe, const float* wag,
                       const int32_t* center, const int32_t* nbr, const int32_t* d2u,
                       int32_t n_edges, const float* w2t, const float* b2, const float* ln,
-                      float* msg, float* save_p, void* stream);
+                      float* msg, float* save_p, float* save_pre /* training: [Ed][128] or NULL */,
+                      void* stream);
 /* reverse: g_pre[e][128] = dE/dpre, g_w[e][64] = dE/d wag row contribution        */
 int chg_atom_conv_bwd(const float* pcn, const float* pe, const float* wag,
                       const int32_t* center, const int32_t* nbr, const int32_t* d2u,
                       int32_t n_edges, const float* save_p, const float* g_agg,
                       const float* w2, const float* ln, float* g_pre, float* g_w,
-                      void* stream);
+                      float* g_p /* training: [Ed][128] dL/dp, or NULL */,
+                      double* g_ln /* training: [4][64] += dL/d(ln), or NULL */, void* stream);
 
 /* ---- K4s/K5s: segmented gather-reduce (functions.py:25-37 without atomics)
  * out[r] (+)= sum_{k in [ptr[r],ptr[r+1])} data[perm ? perm[k] : k], width 64|128 */
@@ -136,7 +145,8 @@ int chg_bond_conv_fwd(const float* pij, const float* px, const float* pa, const 
 int chg_bond_conv_bwd(const float* save_pre, const float* save_p, const float* wbg,
                       const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles,
                       const float* g_agg, const float* w2, const float* ln, float* g_pre,
-                      float* gw_i, float* gw_j, void* stream);
+                      float* gw_i, float* gw_j, float* g_p /* training, or NULL */,
+                      double* g_ln /* training, or NULL */, void* stream);
 
 /* ---- K6: AngleUpdate (layers.py:348-360): ang_new = ang + G0(pre), no hidden layer    */
 int chg_angle_update_fwd(const float* pij, const float* px, const float* pa, const float* ang,
@@ -146,7 +156,8 @@ int chg_angle_update_fwd(const float* pij, const float* px, const float* pa, con
 /* g_ang_in may be NULL (zero).  g_pre = dE/dpre; dE/d ang = g_ang_in + g_pre @ W1a
  * (chg_linear with residual).                                                       */
 int chg_angle_update_bwd(const float* save_p, const float* g_ang_in, int32_t n_angles,
-                         const float* ln, float* g_pre, void* stream);
+                         const float* ln, float* g_pre, double* g_ln /* training, or NULL */,
+                         void* stream);
 
 /* ---- K7: readout (model.py:497-509) + AtomRef sum (composition_model.py:175-205)
  * h = LN(x); site_e = MLP(h); e_graph[owner] += site_e (fp64); e_ref[owner] +=
@@ -170,6 +181,43 @@ int chg_force_virial(const float* rvec, const float* dist, const float* rhat,
                      const int32_t* u2d, const int32_t* center, const int32_t* nbr,
                      const int32_t* atom_owner, int32_t n_edges, double* force,
                      double* virial, void* stream);
+
+/* ======================= training (reference trainer.py:398-411, 779-869) =======================
+ * The reverse pass over activations is the one above (seeded with the loss instead of 1); these
+ * entry points add the parameter gradients, the loss terms and the optimizer step.  Losses on
+ * energies and magnetic moments are covered; losses on forces / stresses need the second-order
+ * pass and are not built yet.                                                       */
+
+/* dL/dW^T: out[k][j] = sum_r act(x[xr(r)][k]) * g[gr(r)][j],  k < 64, j < n_out (multiple of 64);
+ * colsum[j] = sum_r g[gr(r)][j] (bias gradient) or NULL.  x_silu != 0 applies SiLU to x (second
+ * GatedMLP layer: the hidden activations are recomputed from the saved pre-activations).
+ * ldx / ldg / ldo are row strides in floats (column-slice views are allowed).  Deterministic:
+ * per-CTA partials in `workspace` (>= chg_wgrad_workspace_floats(n_out) floats), summed in fp64. */
+int64_t chg_wgrad_workspace_floats(int32_t n_out);
+int chg_wgrad(const float* x, int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
+              int32_t ldg, const int32_t* g_rows, int32_t m, int32_t n_out, float* out, int32_t ldo,
+              float* colsum, float* workspace, void* stream);
+/* out[c] += sum_r a[r][c] * (bmul ? bmul[r][c] : 1) * (rowscale ? rowscale[r] : 1), n in {64,128,256} */
+int chg_colsum(const float* a, int32_t lda, const float* bmul, int32_t ldb, const float* rowscale,
+               int32_t m, int32_t n, double* out, void* stream);
+/* reverse of the readout MLP with seed[i] = dL/d(site energy i); returns g_x = dL/dx and, for the
+ * parameter gradients, h_all [n_hidden+1][N][64] (input of every linear), gz_all [n_hidden][N][64]
+ * (dL/d pre-activation), g_h0 [N][64] (dL/d LayerNorm output), xhat [N][64]                       */
+int chg_readout_bwd(const float* x, int32_t n_atoms, const float* ln, const float* mlp_wt,
+                    const float* mlp_w, const float* mlp_b, int32_t n_hidden, const float* w_last,
+                    const float* seed, float* g_x, float* h_all, float* gz_all, float* g_h0,
+                    float* xhat, void* stream);
+/* m = |x.w + b|: g_lin[i] = sign(x_i.w + b) g_m[i];  g_x[i] += g_lin[i] w                          */
+int chg_magmom_bwd(const float* x, int32_t n_atoms, const float* w, float b, const float* g_m,
+                   float* g_x, float* g_lin, void* stream);
+/* one CombinedLoss term (trainer.py:797-867) over a flat vector, NaN targets masked:
+ * sums[0..2] += (sum loss_i, sum |err_i|, count); g_pred[i] = d loss_i / d pred_i.
+ * kind 0 MSE, 1 MAE, 2 Huber(delta)                                                               */
+int chg_loss_terms(const float* pred, const float* target, int32_t n, int32_t kind, float delta,
+                   float* g_pred, double* sums, void* stream);
+/* torch.optim.Adam (trainer.py:178-189) on one flat fp32 buffer; step counts from 1               */
+int chg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t step, void* stream);
 
 #ifdef __cplusplus
 }

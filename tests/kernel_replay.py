@@ -11,24 +11,31 @@ from oracle.kernel_specs import SpecKernels
 OUT_ARGS = {
     "embed_atoms": [2],
     "edge_geometry": [6, 7, 8],
-    "bond_basis_embed": [8, 9, 10],
-    "bond_basis_bwd": [11],
-    "angle_basis_embed": [5],
-    "angle_basis_bwd": [6],
+    "bond_basis_embed": [8, 9, 10, 11],
+    "bond_basis_bwd": [11, 12],
+    "angle_basis_embed": [5, 6],
+    "angle_basis_bwd": [6, 7],
     "linear": [4],
     "gather_rows": [2],
     "scatter_rows": [2],
-    "atom_conv_fwd": [9, 10],
-    "atom_conv_bwd": [10, 11],
+    "atom_conv_fwd": [9, 10, 11],
+    "atom_conv_bwd": [10, 11, 12, 13],
     "segment_sum": [4],
     "bond_conv_fwd": [10, 11, 12],
-    "bond_conv_bwd": [8, 9, 10],
+    "bond_conv_bwd": [8, 9, 10, 11, 12],
     "angle_update_fwd": [8, 9],
-    "angle_update_bwd": [3],
+    "angle_update_bwd": [3, 4],
     "readout": [10, 11, 12, 13, 14],
     "magmom": [3],
     "force_virial": [10, 11],
+    # training (trailing optional outputs above are training-only too)
+    "wgrad": [2, 3],
+    "colsum": [1],
+    "readout_bwd": [7, 8, 9, 10, 11],
+    "magmom_bwd": [4, 5],
 }
+TRAIN_KERNELS = {"wgrad", "colsum", "readout_bwd", "magmom_bwd"}
+INFER_KERNELS = set(OUT_ARGS) - TRAIN_KERNELS
 
 
 class RecordingKernels(SpecKernels):
@@ -41,7 +48,8 @@ class RecordingKernels(SpecKernels):
             def wrapped(*args):
                 snap = [a.detach().clone().contiguous() if isinstance(a, torch.Tensor) else a for a in args]
                 attr(*args)
-                outs = {i: args[i].detach().clone().contiguous() for i in OUT_ARGS[name] if args[i] is not None}
+                outs = {i: args[i].detach().clone().contiguous() for i in OUT_ARGS[name]
+                        if i < len(args) and args[i] is not None}
                 self.calls.append((name, snap, outs))
             return wrapped
         return attr

@@ -57,11 +57,72 @@ def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
             for idx, want in outs.items():
                 err = _close(name, idx, args[idx], want)
                 seen[name] = max(seen.get(name, 0.0), err)
-        assert set(seen) == set(__import__("kernel_replay").OUT_ARGS), sorted(seen)
+        assert set(seen) == __import__("kernel_replay").INFER_KERNELS, sorted(seen)
         print({k: f"{v:.2e}" for k, v in seen.items()})
     finally:
         K.set_option("linear_impl", 3)
         K.set_option("gated_impl", 0)
+
+
+def test_every_training_kernel_matches_its_spec(weights030):
+    """Training reverse pass (parameter gradients): every call of a real train step, replayed."""
+    import kernel_replay
+    from chgnet_b200._lib import CudaKernels
+    from kernel_replay import RecordingKernels
+
+    graphs = graphgen.random_graphs(3, 10, 16, 9500)
+    sd = {k: torch.as_tensor(v) for k, v in weights030.items()}
+    pw = pack_weights(sd, None, device="cpu")
+    rec = RecordingKernels()
+    eng = Engine(pw, rec)
+    out = eng.run(build_batch(graphs, "cpu"), need_grad=True, need_magmom=True, train=True)
+    gen = torch.Generator().manual_seed(11)
+    n_atoms = sum(g.atomic_number.shape[0] for g in graphs)
+    eng.param_grads(out, torch.randn(len(graphs), generator=gen), torch.randn(n_atoms, generator=gen))
+    K = CudaKernels()
+    seen = {}
+    for name, snap, outs in rec.calls:
+        args = [a.cuda() if isinstance(a, torch.Tensor) else a for a in snap]
+        getattr(K, name)(*args)
+        torch.cuda.synchronize()
+        for idx, want in outs.items():
+            seen[name] = max(seen.get(name, 0.0), _close(name, idx, args[idx], want))
+    assert kernel_replay.TRAIN_KERNELS <= set(seen), sorted(seen)
+    print({k: f"{v:.2e}" for k, v in seen.items()})
+
+
+def test_loss_terms_and_adam_match_torch():
+    """chg_loss_terms vs torch.nn.{MSE,L1,Huber}Loss with NaN masks (trainer.py:797-867) and
+    chg_adam_step vs torch.optim.Adam (trainer.py:178-189)."""
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    pred = torch.randn(5000, device="cuda", generator=g)
+    target = pred + 0.3 * torch.randn(5000, device="cuda", generator=g)
+    target[::7] = float("nan")
+    valid = ~torch.isnan(target)
+    for kind, crit in ((0, torch.nn.MSELoss()), (1, torch.nn.L1Loss()), (2, torch.nn.HuberLoss(delta=0.1))):
+        p = pred.clone().requires_grad_(True)
+        loss = crit(target[valid], p[valid])
+        loss.backward()
+        g_pred, sums = torch.empty_like(pred), torch.zeros(3, dtype=torch.float64, device="cuda")
+        K.loss_terms(pred, target, kind, 0.1, g_pred, sums)
+        n = float(sums[2])
+        assert n == float(valid.sum())
+        assert float(sums[0]) / n == pytest.approx(float(loss), rel=1e-5)
+        assert float(sums[1]) / n == pytest.approx(float((pred - target)[valid].abs().mean()), rel=1e-5)
+        assert float((g_pred / n - p.grad).abs().max()) < 1e-7
+    p0 = torch.randn(100_003, device="cuda", generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 4):
+        grad = torch.randn(p0.shape, device="cuda", generator=g)
+        ref.grad = grad.clone()
+        opt.step()
+        K.adam_step(p, grad, m, v, 1e-2, 0.9, 0.999, 1e-8, 1e-3, step)
+        assert float((p - ref.detach()).abs().max()) < 2e-6
 
 
 @pytest.mark.parametrize("impl", [3, 2, 1, 0], ids=["tcgen05-ws", "tcgen05+tma", "tcgen05", "ffma"])

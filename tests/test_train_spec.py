@@ -53,3 +53,106 @@ def test_param_grads_match_oracle_autograd(weights030, compact):
         assert err <= 1e-9 * max(scale, 1.0), (k, err, scale)
     # the dead AngleUpdate really has zero gradient in the reference too
     assert float(want["angle_layers.2.twoBody_bond.mlp_core.layers.1.weight"].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# CombinedLoss + data-parallel gradient: 2 ranks over gloo vs the reference loss on the full batch
+# ---------------------------------------------------------------------------------------------
+def _labels(graphs, seed):
+    gen = torch.Generator().manual_seed(seed)
+    e_t = torch.randn(len(graphs), generator=gen, dtype=torch.float64)
+    e_t[1] = float("nan")  # a missing energy label
+    m_t = [torch.rand(g.atomic_number.shape[0], generator=gen, dtype=torch.float64) for g in graphs]
+    m_t[2] = None  # a structure without magmom labels (trainer.py:846-851)
+    return e_t, m_t
+
+
+def _reference_loss_grads(weights, graphs, e_t, m_t, criterion):
+    """CombinedLoss semantics (trainer.py:797-867, allow_missing_labels=True) on the oracle."""
+    crit = {"MSE": torch.nn.MSELoss(), "MAE": torch.nn.L1Loss(), "Huber": torch.nn.HuberLoss(delta=0.1)}[criterion]
+    P = {k: torch.as_tensor(np.asarray(v)).double().requires_grad_(k != "composition_model.fc.weight")
+         for k, v in weights.items()}
+    out = orc.forward(P, graphs, "em", dtype=torch.float64, train=True)
+    valid = ~torch.isnan(e_t)
+    loss = 1.0 * crit(e_t[valid], out["e"][valid])
+    mp_, mt_ = [], []
+    for mp, mt in zip(out["m"], m_t):
+        if mt is not None:
+            mp_.append(mp), mt_.append(mt)
+    loss = loss + 0.1 * crit(torch.cat(mt_), torch.cat(mp_))
+    names = [k for k, v in P.items() if v.requires_grad]
+    gr = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    return float(loss.detach()), {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(names, gr)}
+
+
+def _rank_grads(weights, graphs, e_t, m_t, criterion, group=None):
+    from chgnet_b200.trainer import LossConfig, loss_and_grads
+
+    sd = {k: torch.as_tensor(np.asarray(v)).double() for k, v in weights.items()}
+    eng = Engine(pack_weights(sd, None, device="cpu", dtype=torch.float64), SpecKernels())
+    b = build_batch(graphs, "cpu")
+    b.frac, b.lattice, b.image = b.frac.double(), b.lattice.double(), b.image.double()
+    m_flat = torch.cat([torch.full((g.atomic_number.shape[0],), float("nan"), dtype=torch.float64) if m is None else m
+                        for g, m in zip(graphs, m_t)])
+    report, G = loss_and_grads(eng, b, LossConfig("em", criterion), e_t, m_flat, True, group)
+    return report, unpack_grads(G, sd)
+
+
+@pytest.mark.parametrize("criterion", ["MSE", "MAE", "Huber"])
+def test_combined_loss_gradients_match_reference_loss(weights030, criterion):
+    graphs = graphgen.random_graphs(4, 6, 9, 8200)
+    e_t, m_t = _labels(graphs, 5)
+    want_loss, want = _reference_loss_grads(weights030, graphs, e_t, m_t, criterion)
+    report, got = _rank_grads(weights030, graphs, e_t, m_t, criterion)
+    # the oracle (like the reference, composition_model.py:191) rounds the AtomRef energy to fp32
+    assert report["loss"] == pytest.approx(want_loss, rel=1e-6)
+    assert report["e_MAE_size"] == 3 and report["m_MAE_size"] == sum(g.atomic_number.shape[0] for g, m in zip(graphs, m_t) if m is not None)
+    for k, w in want.items():
+        assert float((got[k] - w).abs().max()) <= 1e-6 * max(float(w.abs().max()), 1.0), k
+
+
+def _ddp_worker(rank, world, port, q):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        from chgnet_b200.batch import graph_cost, partition_graphs
+
+        w = orc.load_weights_npz(os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz"))
+        graphs = graphgen.random_graphs(4, 6, 9, 8200)
+        e_t, m_t = _labels(graphs, 5)
+        mine = partition_graphs([graph_cost(g) for g in graphs], world)[rank]
+        report, grads = _rank_grads(w, [graphs[i] for i in mine], e_t[mine], [m_t[i] for i in mine], "MSE")
+        flat = torch.cat([grads[k].reshape(-1) for k in sorted(grads) if k != "composition_model.fc.weight"])
+        dist.all_reduce(flat)  # the one collective of a training step
+        q.put((rank, report["loss"], flat.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_equals_global_batch(weights030):
+    import os
+
+    import torch.multiprocessing as mp
+
+    graphs = graphgen.random_graphs(4, 6, 9, 8200)
+    e_t, m_t = _labels(graphs, 5)
+    want_loss, want = _reference_loss_grads(weights030, graphs, e_t, m_t, "MSE")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=600) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    keys = sorted(want)
+    flat_want = torch.cat([want[k].reshape(-1) for k in keys]).numpy()
+    for _, loss, flat in got:
+        assert loss == pytest.approx(want_loss, rel=1e-6)  # global-batch means on every rank
+        assert flat.shape == flat_want.shape
+        assert np.abs(flat - flat_want).max() <= 1e-6 * max(np.abs(flat_want).max(), 1.0)
