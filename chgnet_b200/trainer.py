@@ -133,11 +133,17 @@ class Trainer:
         self.names = [n for n, _ in named]
         self.shapes = [tuple(p.shape) for _, p in named]
         self.sizes = [p.numel() for _, p in named]
-        self.flat = torch.cat([p.detach().reshape(-1) for _, p in named]).contiguous()
-        off = 0
-        for (_, p), sz in zip(named, self.sizes):
-            p.data = self.flat[off:off + sz].view(p.shape)
-            off += sz
+        # every parameter starts on a 64-byte boundary (the kernels read weights as float4); the
+        # padding stays zero under Adam (zero gradient, zero moments)
+        self.offsets, off = [], 0
+        for sz in self.sizes:
+            self.offsets.append(off)
+            off += (sz + 15) // 16 * 16
+        dev = named[0][1].device
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for (_, p), o, sz in zip(named, self.offsets, self.sizes):
+            self.flat[o:o + sz] = p.detach().reshape(-1)
+            p.data = self.flat[o:o + sz].view(p.shape)
         self.flat_grad = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
@@ -155,11 +161,13 @@ class Trainer:
         return e_t, m_t
 
     def flatten_grads(self, grads: dict[str, Tensor]) -> Tensor:
-        off = 0
-        for name, sz in zip(self.names, self.sizes):
-            self.flat_grad[off:off + sz] = grads[name].reshape(-1)
-            off += sz
+        for name, o, sz in zip(self.names, self.offsets, self.sizes):
+            self.flat_grad[o:o + sz] = grads[name].reshape(-1)
         return self.flat_grad
+
+    def grads_by_name(self) -> dict[str, Tensor]:
+        """views of the (all-reduced) flat gradient buffer, one per parameter"""
+        return {n: self.flat_grad[o:o + sz].view(sh) for n, o, sz, sh in zip(self.names, self.offsets, self.sizes, self.shapes)}
 
     def train_step(self, graphs, targets: dict) -> dict:
         """prediction -> CombinedLoss -> parameter gradients -> (all-reduce) -> Adam; returns the report."""
