@@ -56,7 +56,176 @@ def make_workload(name: str, rank: int):
     if name == "c4":
         z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000 + rank)
         return [graphgen.make_crystal_graph(z, frac, lat, graph_id="LiMnO2-10x5x25")], "LiMnO2 10x5x25 supercell, 10,000 atoms, sigma=0.02 A"
+    if name == "c5":
+        return graphgen.random_graphs(128, 20, 40, 5000 + 1000 * rank), "fine-tune batch=128 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A; targets 'em' (MSE), Adam lr 1e-3"
     raise SystemExit(f"unknown workload {name}")
+
+
+def train_labels(preds, seed: int):
+    """labels = prediction + uniform noise (+-0.1 eV/atom, +-0.03 muB)"""
+    gen = torch.Generator().manual_seed(seed)
+    e = torch.tensor([float(p["e"]) for p in preds]) + (torch.rand(len(preds), generator=gen) - 0.5) * 0.2
+    m = [torch.as_tensor(p["m"]) + (torch.rand(len(p["m"]), generator=gen) - 0.5) * 0.06 for p in preds]
+    return e, m
+
+
+def run_reference_train(args) -> None:
+    """--impl reference --workload c5: one reference training step (trainer.py:398-411) on the host
+    cores: oracle forward (train mode) -> CombinedLoss('em', MSE) -> backward -> torch Adam."""
+    from oracle import chgnet_oracle as orc
+
+    graphs, desc = make_workload("c5", 0)
+    sample = graphs[: max(1, min(len(graphs), args.cpu_sample))]
+    w = orc.load_weights_npz(WEIGHTS)
+    base = orc.predict_graph(w, sample, "em", batch_size=len(sample))
+    e_t, m_t = train_labels(base, 5)
+    P = {k: torch.as_tensor(np.asarray(v)).float().requires_grad_(k != "composition_model.fc.weight") for k, v in w.items()}
+    opt = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=1e-3)
+    crit = torch.nn.MSELoss()
+
+    def step():
+        opt.zero_grad()
+        out = orc.forward(P, sample, "em", train=True)
+        loss = crit(e_t, out["e"]) + 0.1 * crit(torch.cat(m_t), torch.cat(out["m"]))
+        loss.backward()
+        opt.step()
+
+    threads = pick_cpu_threads(step)
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = len(sample) / dt
+    sdesc = f"first {len(sample)} graphs of the batch per step; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep)"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_structures_per_sec_EM", "value": value, "unit": "structures/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c5: {desc}", "task": "train em"},
+        "cpu_baseline": {"value": value, "unit": "structures/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sdesc},
+        "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_train(args, rank: int, world: int, local_rank: int) -> None:
+    """--workload c5: one fine-tuning step per 'step' (forward, CombinedLoss, parameter gradients,
+    one gradient all-reduce over NCCL, fused Adam, weight re-pack)."""
+    import contextlib
+    import io
+
+    import torch.distributed as dist
+
+    from chgnet_b200.batch import build_batch
+    from chgnet_b200.model import CHGNet
+    from chgnet_b200.trainer import Trainer, loss_and_grads
+    from chgnet_b200.weights import unpack_grads
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev)
+    graphs, desc = make_workload("c5", rank)
+    c = counts(graphs)
+    base = model.predict_graph(graphs, task="em", batch_size=len(graphs))
+    e_t, m_t = train_labels(base, 5 + rank)
+    trainer = Trainer(model, targets="em", criterion="MSE", learning_rate=1e-3)
+    flush = L2Flush(dev)
+    K = model._get_engine().K
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = build_batch(graphs, dev, with_reverse=True)
+    e_dev = e_t.to(dev)
+    m_dev = torch.cat(m_t).to(dev)
+
+    def step_resident():
+        engine = model._get_engine()  # re-packs the weights the previous Adam step changed
+        report_, G = loss_and_grads(engine, batch, trainer.cfg, e_dev, m_dev, model.is_intensive, None)
+        fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
+        if world > 1:
+            dist.all_reduce(fg)
+        trainer.step_count += 1
+        K.adam_step(trainer.flat, fg, trainer.exp_avg, trainer.exp_avg_sq, trainer.lr, 0.9, 0.999, 1e-8, 0.0, trainer.step_count)
+        model.mark_params_updated()
+        return report_
+
+    for _ in range(max(args.warmup, 3)):
+        flush()
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = K.launches
+    elapsed_ms = 0.0
+    for _ in range(args.steps):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rep_last = step_resident()
+        e.record()
+        e.synchronize()
+        elapsed_ms += s.elapsed_time(e)
+    barrier()
+    launches = K.launches - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+
+    # end to end: Trainer.train_step from host graphs + host labels, report read back every step
+    targets = {"e": e_t, "m": m_t}
+    for _ in range(2):
+        trainer.train_step(graphs, targets)
+    h2d = int(build_batch(graphs, dev, with_reverse=True).h2d_bytes) + 4 * (len(e_t) + int(m_dev.numel()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush()
+        trainer.train_step(graphs, targets)
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+    peaks, peak_kind = measured_peaks()
+    sc_ms, sc_bytes = time_scatter_kernel(K, batch)
+    achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
+    roofline = {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth", "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "us_per_launch": round(sc_ms * 1e3, 2),
+                "algorithmic_bytes": sc_bytes, "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+    ek = EventKernels(K)
+    from chgnet_b200.engine import Engine
+
+    eng2 = Engine(model._get_engine().pw, ek)
+    out2 = eng2.run(batch, need_grad=True, need_magmom=True, train=True)
+    eng2.param_grads(out2, torch.ones(c["graphs"], device=dev), torch.ones(c["atoms"], device=dev))
+    shares = ek.table()
+    total = c["graphs"] * world
+    print(json.dumps({
+        "metric": "train_structures_per_sec_EM", "value": total / (ms_per_step * 1e-3), "unit": "structures/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c5: {desc}", "task": "train em", "per_gpu": c, "weights": "CHGNet 0.3.0",
+                   "l2": "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations",
+                   "parallelism": f"graph-sharded x{world}, one all-reduce of the flat gradient buffer per step",
+                   "note": "force / stress loss terms are not built yet: this is the 'em' training step, not the C5 'efsm' one"},
+        "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "structures/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48, "api": "Trainer.train_step(list[CrystalGraph] on host, labels on host)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
+        "last_report": rep_last, "kernel_shares": shares}), flush=True)
+    if world > 1:
+        dist.barrier()
 
 
 def counts(graphs):
@@ -441,7 +610,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("CHGNET_BENCH_WORKLOAD", "c2"), choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default=os.environ.get("CHGNET_BENCH_WORKLOAD", "c2"), choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cpu-sample", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scatter-only", action="store_true", help="run only the AtomConv scatter kernel timing (ncu target)")
@@ -450,6 +619,10 @@ def main() -> None:
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
+        if args.workload == "c5":
+            if rank == 0:
+                run_reference_train(args)
+            return
         run_reference(args, rank, world)
         return
     if not torch.cuda.is_available():
@@ -460,7 +633,7 @@ def main() -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_train if args.workload == "c5" else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

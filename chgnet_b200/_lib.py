@@ -220,10 +220,10 @@ class CudaKernels:
                 raise ChgnetB200Error("kernel arguments must be CUDA tensors with unit column stride")
 
     def _workspace(self, n_out: int, device) -> Tensor:
-        need = int(self.lib.chg_wgrad_workspace_floats(n_out))
         ws = getattr(self, "_ws", None)
-        if ws is None or ws.numel() < need or ws.device != device:
-            ws = torch.empty(int(self.lib.chg_wgrad_workspace_floats(256)), dtype=torch.float32, device=device)
+        if ws is None or ws.device != device:
+            need = max(int(self.lib.chg_wgrad_workspace_floats(n)) for n in (64, 128, 256))
+            ws = torch.empty(need, dtype=torch.float32, device=device)
             self._ws = ws
         return ws
 

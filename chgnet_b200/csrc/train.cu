@@ -9,6 +9,8 @@
 //   * chg_loss_terms, chg_adam_step.
 // All reductions over rows go through per-CTA partials and a second pass in fp64, so the
 // gradients are deterministic (no floating-point atomics on the weight gradients).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace chg {
@@ -16,7 +18,7 @@ namespace {
 
 // ---- wgrad: out[64][n] = act(X[xr])^T . G[gr] -----------------------------------------------
 constexpr int WG_ROWS = 32;  // rows staged per step
-constexpr int WG_MAX_CHUNKS = 512;
+constexpr int WG_MAX_CHUNKS = 1024;
 
 template <bool SILU>
 __global__ void __launch_bounds__(256)
@@ -39,26 +41,40 @@ wgrad_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ x
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int step = s_beg; step < s_end; ++step) {
+  // register-staged software pipeline: the global loads of step s+1 are in flight while step s
+  // is multiplied out of shared memory
+  float4 xr[2], gr[2];
+  auto fetch = [&](int step) {
     const int base = step * WG_ROWS;
-    __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int f4 = tid + h * 256;  // 512 float4 per tile
       const int r = f4 >> 4, c = (f4 & 15) * 4;
       const int row = base + r;
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+      xr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gr[h] = xr[h];
       if (row < m) {
-        const int xr = x_rows != nullptr ? x_rows[row] : row;
-        const int gr = g_rows != nullptr ? g_rows[row] : row;
-        xv = ldg4(x + (size_t)xr * ldx + c);
-        gv = ldg4(g + (size_t)gr * ldg + col_base + c);
-        if (SILU) xv = make_float4(silu_f(xv.x), silu_f(xv.y), silu_f(xv.z), silu_f(xv.w));
+        const int xi = x_rows != nullptr ? x_rows[row] : row;
+        const int gi = g_rows != nullptr ? g_rows[row] : row;
+        xr[h] = ldg4(x + (size_t)xi * ldx + c);
+        gr[h] = ldg4(g + (size_t)gi * ldg + col_base + c);
       }
+    }
+  };
+  if (s_beg < s_end) fetch(s_beg);
+  for (int step = s_beg; step < s_end; ++step) {
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f4 = tid + h * 256;
+      const int r = f4 >> 4, c = (f4 & 15) * 4;
+      float4 xv = xr[h];
+      if (SILU) xv = make_float4(silu_f(xv.x), silu_f(xv.y), silu_f(xv.z), silu_f(xv.w));
       sts4(&s_x[r][c], xv);
-      sts4(&s_g[r][c], gv);
+      sts4(&s_g[r][c], gr[h]);
     }
     __syncthreads();
+    if (step + 1 < s_end) fetch(step + 1);
 #pragma unroll 8
     for (int r = 0; r < WG_ROWS; ++r) {
       const float4 xv = lds4(&s_x[r][k0]);
@@ -306,7 +322,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 using namespace chg;
 
 extern "C" int64_t chg_wgrad_workspace_floats(int32_t n_out) {
-  return (int64_t)WG_MAX_CHUNKS * (64 * (int64_t)n_out + n_out);
+  // chunks(n) * (64 n + n) with chunks(n) <= min(WG_MAX_CHUNKS, 2 * 256 / n * SMs): largest at n = 256 on 148+ SMs
+  const int64_t chunks = std::min<int64_t>(WG_MAX_CHUNKS, (int64_t)sm_count() * 2 * std::max(1, 256 / n_out));
+  return chunks * (64 * (int64_t)n_out + n_out);
 }
 
 extern "C" int chg_wgrad(const float* x, int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
@@ -318,7 +336,8 @@ extern "C" int chg_wgrad(const float* x, int32_t ldx, const int32_t* x_rows, int
   CHG_CHECK_ARG(ldx >= 64 && ldx % 4 == 0 && ldg >= n_out && ldg % 4 == 0 && ldo >= n_out, "bad leading dimension");
   CHG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g | (uintptr_t)workspace) & 15) == 0, "x, g, workspace must be 16-byte aligned");
   const int steps = (m + WG_ROWS - 1) / WG_ROWS;
-  const int n_chunks = max(1, min(min(steps, sm_count() * 2), WG_MAX_CHUNKS));
+  // narrow outputs get more row chunks (more CTAs per SM in flight: the kernel is latency bound)
+  const int n_chunks = max(1, min(min(steps, sm_count() * 2 * max(1, 256 / n_out)), WG_MAX_CHUNKS));
   float* partial = workspace;
   float* cs_partial = colsum != nullptr ? workspace + (size_t)n_chunks * 64 * n_out : nullptr;
   dim3 grid(n_chunks, n_out / 64);
