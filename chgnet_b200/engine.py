@@ -226,12 +226,19 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ reverse
-    def input_grads(self, out: EngineOutput) -> None:
+    def input_grads(self, out: EngineOutput, record: bool = False) -> None:
         """Forces / virial of a ``train=True`` forward (values only; the state is kept for
-        :meth:`param_grads`)."""
-        self._reverse(out.extras["train_state"], out, None)
+        :meth:`param_grads`).  ``record=True`` also keeps the adjoints dE/d(intermediate) that the
+        second-order pass of a force / stress loss needs."""
+        st = out.extras["train_state"]
+        n = self.pw.hp.n_conv
+        rec = dict(atom=[None] * n, bond=[None] * (n - 1), angle=[None] * (n - 1)) if record else None
+        self._reverse(st, out, None, rec)
+        if record:
+            st["rec"] = rec
 
-    def param_grads(self, out: EngineOutput, seed_energy: Tensor, seed_magmom: Tensor | None = None) -> dict:
+    def param_grads(self, out: EngineOutput, seed_energy: Tensor, seed_magmom: Tensor | None = None,
+                    seed_force: Tensor | None = None, seed_stress: Tensor | None = None) -> dict:
         """Training reverse pass (replaces ``loss.backward()``, trainer.py:409-410) for losses on the
         energies and magnetic moments: dL/d(parameter) for ``seed_energy[g] = dL/d(E_g)`` (E_g the
         extensive model energy of graph g) and ``seed_magmom[i] = dL/d(m_i)``.
@@ -242,8 +249,232 @@ class Engine:
         """
         st = out.extras.pop("train_state")
         grads: dict = {}
+        if seed_force is not None or seed_stress is not None:
+            if "rec" not in st:
+                raise RuntimeError("call input_grads(out, record=True) before param_grads with force / stress seeds")
+            self._second_order(st, dict(seed_energy=seed_energy, seed_magmom=seed_magmom, seed_force=seed_force,
+                                        seed_stress=seed_stress, grads=grads))
+            return grads
         self._reverse(st, out, dict(seed_energy=seed_energy, seed_magmom=seed_magmom, grads=grads))
         return grads
+
+    # ------------------------------------------------------------------ second order
+    def _second_order(self, st: dict, train: dict) -> None:
+        """Parameter gradients of a loss that also depends on forces and stresses (reference
+        model.py:518-535 ``create_graph=True`` + trainer.py:409 ``loss.backward()``).
+
+        With F = -dE/dcart and sigma = (c/V) dE/d(strain), the force / stress part of the loss gradient is
+        d/dtheta of  T = sum_e <dE/dr_e, rdot_e>,  rdot_e = -(gF[c] - gF[n]) + r_e . (gS c/V)  held fixed.
+        T is evaluated by a TANGENT pass (forward mode along rdot through every kernel of the forward
+        pass), and differentiated by one more reverse pass over (primal, tangent).  The adjoint of every
+        tangent quantity equals the ordinary adjoint lambda = dE/d(.) recorded by the force pass, so this
+        reverse pass only propagates the adjoints of the PRIMAL intermediates ("bar"), seeded with the
+        energy / magmom loss, and adds the second-order source terms inside the nonlinear kernels.
+        """
+        pw, K, hp = self.pw, self.K, self.pw.hp
+        b: DeviceBatch = st["b"]
+        N, Ed, Eu, A, B = b.n_atoms, b.n_edges, b.n_bonds, b.n_angles, b.n_graphs
+        has_ang = A > 0
+        n_conv = hp.n_conv
+        Es, sid = b.n_short, b.short_ids
+        wag, wbg_s, dist, rvec, rhat, tr, rec = st["wag"], st["wbg_s"], st["dist"], st["rvec"], st["rhat"], st["tr"], st["rec"]
+        saved_atom, saved_bond, saved_angle = st["saved_atom"], st["saved_bond"], st["saved_angle"]
+        G = train["grads"]
+        dt = pw.emb.dtype
+        use_ln = pw.atom[0].ln is not None
+
+        def ln_acc():
+            return self._zeros(b, 256, dtype=torch.float64) if use_ln else None
+
+        def lin(x, wt, residual=None, x_rows=None):
+            return self._lin(b, x, wt, None, residual, x_rows)
+
+        def wsum(x, g, n, xd, lam, **kw):
+            """x^T g + xd^T lam : weight gradient of a linear op and of its tangent"""
+            return self._wgrad(b, x, g, n, **kw) + self._wgrad(b, xd, lam, n, **kw)
+
+        # ---------------- tangent pass ----------------
+        u_atom = self._zeros(b, N, 3) if train["seed_force"] is None else (-train["seed_force"]).to(dt).contiguous()
+        w_graph = self._zeros(b, B, 9)
+        if train["seed_stress"] is not None:
+            scale = (EV_A3_TO_GPA / b.volume.to(torch.float64))[:, None, None]
+            w_graph = (train["seed_stress"].to(torch.float64).view(B, 3, 3) * scale).to(dt).reshape(B, 9).contiguous()
+        ddist, drhat = self._new(b, Ed), self._new(b, Ed, 3)
+        K.edge_tangent(rvec, dist, rhat, b.center, b.nbr, b.owner, u_atom, w_graph, ddist, drhat)
+        e_d, wag_d, wbg_d, tb = (self._new(b, Eu, 64) for _ in range(4))
+        K.bond_basis_tangent(dist, ddist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                             hp.cutoff_coeff, pw.w3t, e_d, wag_d, wbg_d, tb)
+        ang_d = tfb = wbg_s_d = None
+        if has_ang:
+            ang_d, tfb = self._new(b, A, 64), self._new(b, A, 64)
+            K.angle_basis_tangent(rhat, drhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang_t, ang_d, tfb)
+            wbg_s_d = self._new(b, Es, 64)
+            K.gather_rows(wbg_d, sid, wbg_s_d)
+        x_d = self._zeros(b, N, 64)
+        t_atom, t_bond, t_angle = [None] * n_conv, [None] * (n_conv - 1), [None] * (n_conv - 1)
+
+        def atom_tan(t, x_d, e_d):
+            gp, sv = pw.atom[t], saved_atom[t]
+            pcn_d, pe_d = lin(x_d, gp.extra["wcn_t"]), lin(e_d, gp.extra["we_t"])
+            msg_d, pre_d, p_d = self._new(b, Ed, 64), self._new(b, Ed, 128), self._new(b, Ed, 128)
+            K.atom_conv_tan(pcn_d, pe_d, wag, wag_d, b.center, b.nbr, b.d2u, sv["pre"], sv["p"], gp.w2t, gp.ln,
+                            msg_d, pre_d, p_d)
+            agg_d = self._seg(b, msg_d, None, b.ptr_c, N)
+            t_atom[t] = dict(x_d=x_d, e_d=e_d, pre_d=pre_d, p_d=p_d, agg_d=agg_d)
+            return lin(agg_d, gp.extra["wo_t"], residual=x_d)
+
+        for t in range(n_conv - 1):
+            x_d = atom_tan(t, x_d, e_d)
+            if has_ang:
+                gp, sv = pw.bond[t], saved_bond[t]
+                pij_d = lin(e_d, gp.extra["wij_t"], x_rows=sid)
+                px_d, pa_d = lin(x_d, gp.extra["wx_t"]), lin(ang_d, gp.extra["w1a_t"])
+                upd_d, pre_d, p_d = self._new(b, A, 64), self._new(b, A, 128), self._new(b, A, 128)
+                K.bond_conv_tan(pij_d, px_d, pa_d, wbg_s, wbg_s_d, b.ang_atom, b.ang_is, b.ang_js, sv["pre"], sv["p"],
+                                gp.w2t, gp.ln, upd_d, pre_d, p_d)
+                agg_d = self._seg(b, upd_d, None, b.ptr_is, Es)
+                t_bond[t] = dict(x_d=x_d, e_d=e_d, ang_d=ang_d, pre_d=pre_d, p_d=p_d, agg_d=agg_d)
+                e_d = e_d.clone()
+                K.linear(agg_d, gp.extra["wo_t"], None, e_d, e_d, None, sid)
+                if t < n_conv - 2:
+                    ga, sva = pw.angle[t], saved_angle[t]
+                    pij_d = lin(e_d, ga.extra["wij_t"], x_rows=sid)
+                    px_d, pa_d = lin(x_d, ga.extra["wx_t"]), lin(ang_d, ga.extra["w1a_t"])
+                    ang_new_d, p_d = self._new(b, A, 64), self._new(b, A, 128)
+                    K.angle_update_tan(pij_d, px_d, pa_d, ang_d, b.ang_atom, b.ang_is, b.ang_js, sva["p"], ga.ln,
+                                       ang_new_d, p_d)
+                    t_angle[t] = dict(x_d=x_d, e_d=e_d, ang_d=ang_d, p_d=p_d)
+                    ang_d = ang_new_d
+        x_d = atom_tan(n_conv - 1, x_d, e_d)
+
+        # ---------------- reverse over (primal, tangent) ----------------
+        L = pw.mlp_wt.shape[0]
+        seed_atom = train["seed_energy"].to(dt)[b.owner.long()].contiguous()
+        bar_x = self._new(b, N, 64)
+        h_all, hd_all = self._new(b, L + 1, N, 64), self._new(b, L + 1, N, 64)
+        gz_all, zbar_all = self._new(b, L, N, 64), self._new(b, L, N, 64)
+        g_h0, hbar0, xhat, xhatd = (self._new(b, N, 64) for _ in range(4))
+        K.readout_bwd2(st["x_last"], x_d, pw.readout_ln, pw.mlp_wt, pw.mlp_w, pw.mlp_b, pw.w_last, seed_atom, bar_x,
+                       h_all, hd_all, gz_all, zbar_all, g_h0, hbar0, xhat, xhatd)
+        G["mlp_wt"] = torch.stack([wsum(h_all[l], zbar_all[l], 64, hd_all[l], gz_all[l]) for l in range(L)])
+        G["mlp_b"] = torch.stack([self._colsum(b, zbar_all[l]) for l in range(L)])
+        G["w_last"] = self._colsum(b, h_all[L], rowscale=seed_atom) + self._colsum(b, hd_all[L])
+        G["b_last"] = seed_atom.sum()
+        if pw.readout_ln is not None:
+            G["readout_ln"] = torch.stack([self._colsum(b, hbar0, xhat) + self._colsum(b, g_h0, xhatd),
+                                           self._colsum(b, hbar0)])
+
+        bar_e = None
+        bar_wag = self._zeros(b, Eu, 64)
+        bar_wbg = self._zeros(b, Es, 64) if has_ang else None
+        bar_a = None
+
+        def acc(dst, x_in, wt):
+            return self._lin(b, x_in, wt, residual=dst)
+
+        def w2_grads(key, pre, u, pre_d, g_p_lam, g_ln):
+            w2t, b2, tmp = self._new(b, 64, 128), self._new(b, 128), self._new(b, 64, 128)
+            for h in (slice(0, 64), slice(64, 128)):
+                K.wgrad(pre[:, h], u[:, h], w2t[:, h], b2[h], None, None, True)       # silu(pre)^T u
+                K.wgrad(pre[:, h], g_p_lam[:, h], tmp[:, h], None, None, None, False, pre_d[:, h])  # hdot^T lambda(p)
+            G[f"{key}.w2t"], G[f"{key}.b2"] = w2t + tmp, b2
+            if g_ln is not None:
+                G[f"{key}.ln"] = g_ln.to(dt).view(4, 64)
+
+        def atom_bwd2(t, bar_xout, bar_e):
+            gp, sv, la, tt = pw.atom[t], saved_atom[t], rec["atom"][t], t_atom[t]
+            G[f"atom.{t}.wo_t"] = wsum(sv["agg"], bar_xout, 64, tt["agg_d"], la["g_xout"])
+            if gp.extra["bo"] is not None:
+                G[f"atom.{t}.bo"] = self._colsum(b, bar_xout)
+            bar_agg = self._lin(b, bar_xout, gp.extra["wo"])
+            bar_pre, bar_w, u, g_ln = self._new(b, Ed, 128), self._new(b, Ed, 64), self._new(b, Ed, 128), ln_acc()
+            K.atom_conv_bwd2(sv["pre"], sv["p"], tt["pre_d"], tt["p_d"], la["g_p"], wag, wag_d, b.center, b.d2u,
+                             la["g_agg"], bar_agg, gp.w2, gp.ln, bar_pre, bar_w, u, g_ln)
+            w2_grads(f"atom.{t}", sv["pre"], u, tt["pre_d"], la["g_p"], g_ln)
+            sp = self._new(b, N, 256)
+            K.segment_sum(bar_pre, None, b.ptr_c, 0, sp[:, :128])
+            K.segment_sum(bar_pre, b.perm_n, b.ptr_n, 0, sp[:, 128:])
+            spe = self._seg(b, bar_pre, b.perm_u, b.ptr_u, Eu)
+            G[f"atom.{t}.wcn_t"] = wsum(sv["x"], sp, 256, tt["x_d"], la["sp"])
+            G[f"atom.{t}.we_t"] = wsum(sv["e"], spe, 128, tt["e_d"], la["spe"])
+            G[f"atom.{t}.b1"] = self._colsum(b, spe)
+            K.segment_sum(bar_w, b.perm_u, b.ptr_u, 1, bar_wag)
+            return acc(bar_xout, sp, gp.extra["wcn_b"]), acc(bar_e, spe, gp.extra["we_b"])
+
+        def angle_scatter2(bar_pre, bar_x, bar_e, ex, key, sv, la, tt):
+            sp = self._new(b, Es, 256)
+            K.segment_sum(bar_pre, None, b.ptr_is, 0, sp[:, :128])
+            K.segment_sum(bar_pre, b.perm_js, b.ptr_js, 0, sp[:, 128:])
+            if bar_e is None:
+                bar_e = self._zeros(b, Eu, 64)
+            K.linear(sp, ex["wij_b"], None, bar_e, bar_e, None, sid)
+            spx = self._seg(b, bar_pre, b.perm_x, b.ptr_x, N)
+            G[f"{key}.wij_t"] = wsum(sv["e"], sp, 256, tt["e_d"], la["sp"], x_rows=sid)
+            G[f"{key}.wx_t"] = wsum(sv["x"], spx, 128, tt["x_d"], la["spx"])
+            G[f"{key}.w1a_t"] = wsum(sv["ang"], bar_pre, 128, tt["ang_d"], la["g_pre"])
+            G[f"{key}.b1"] = self._colsum(b, bar_pre)
+            return acc(bar_x, spx, ex["wx_b"]), bar_e
+
+        bar_x, bar_e = atom_bwd2(n_conv - 1, bar_x, None)
+        if train["seed_magmom"] is not None:
+            g_lin = self._new(b, N)
+            K.magmom_bwd(tr["x_mag"], pw.w_mag, pw.b_mag, train["seed_magmom"].to(dt).contiguous(), bar_x, g_lin)
+            G["w_mag"] = self._colsum(b, tr["x_mag"], rowscale=g_lin)
+            G["b_mag"] = g_lin.sum()
+        for t in reversed(range(n_conv - 1)):
+            if has_ang:
+                if t < n_conv - 2:
+                    ga, sva, la, tt = pw.angle[t], saved_angle[t], rec["angle"][t], t_angle[t]
+                    bar_pre, g_ln = self._new(b, A, 128), ln_acc()
+                    K.angle_update_bwd2(sva["p"], tt["p_d"], la["g_ang_in"], bar_a, ga.ln, bar_pre, g_ln)
+                    if g_ln is not None:
+                        G[f"angle.{t}.ln"] = g_ln.to(dt).view(4, 64)
+                    bar_a = acc(bar_a, bar_pre, ga.extra["w1a_b"])
+                    bar_x, bar_e = angle_scatter2(bar_pre, bar_x, bar_e, ga.extra, f"angle.{t}", sva, la, tt)
+                gp, sv, la, tt = pw.bond[t], saved_bond[t], rec["bond"][t], t_bond[t]
+                if bar_e is None:
+                    bar_e = self._zeros(b, Eu, 64)
+                G[f"bond.{t}.wo_t"] = (self._wgrad(b, sv["agg"], bar_e, 64, g_rows=sid)
+                                       + self._wgrad(b, tt["agg_d"], la["g_eout"], 64, g_rows=sid))
+                if gp.extra["bo"] is not None:
+                    G[f"bond.{t}.bo"] = self._colsum(b, bar_e)
+                bar_agg = self._lin(b, bar_e, gp.extra["wo"], x_rows=sid)
+                bar_pre, u, g_ln = self._new(b, A, 128), self._new(b, A, 128), ln_acc()
+                bw_i, bw_j = self._new(b, A, 64), self._new(b, A, 64)
+                K.bond_conv_bwd2(sv["pre"], sv["p"], tt["pre_d"], tt["p_d"], la["g_p"], wbg_s, wbg_s_d, b.ang_is, b.ang_js,
+                                 la["g_agg"], bar_agg, gp.w2, gp.ln, bar_pre, bw_i, bw_j, u, g_ln)
+                w2_grads(f"bond.{t}", sv["pre"], u, tt["pre_d"], la["g_p"], g_ln)
+                bar_a = acc(bar_a, bar_pre, gp.extra["w1a_b"])
+                bar_x, bar_e = angle_scatter2(bar_pre, bar_x, bar_e, gp.extra, f"bond.{t}", sv, la, tt)
+                K.segment_sum(bw_i, None, b.ptr_is, 1, bar_wbg)
+                K.segment_sum(bw_j, b.perm_js, b.ptr_js, 1, bar_wbg)
+            bar_x, bar_e = atom_bwd2(t, bar_x, bar_e)
+
+        # ---------------- embeddings, basis weights, basis frequencies ----------------
+        R, NA = pw.freq_ag.shape[0], pw.wang.shape[1]
+        bar_wbg_full = self._zeros(b, Eu, 64)
+        if has_ang:
+            K.scatter_rows(bar_wbg, sid, bar_wbg_full)
+        order = torch.argsort(b.z.long(), stable=True).int()
+        zptr = torch.zeros(95, dtype=torch.int32, device=b.z.device)
+        zptr[1:] = torch.cumsum(torch.bincount(b.z.long() - 1, minlength=94), 0)
+        G["emb"] = self._new(b, 94, 64)
+        K.segment_sum(bar_x, order, zptr, 0, G["emb"])
+        bb = tr["bb"]
+        G["w3t"] = torch.stack([wsum(bb, bar_e, 64, tb, rec["g_e0"])[:R], wsum(bb, bar_wag, 64, tb, rec["g_wag"])[:R],
+                                wsum(bb, bar_wbg_full, 64, tb, rec["g_wbg_full"])[32 : 32 + R]])
+        g_freq = self._zeros(b, 2, R, dtype=torch.float64)
+        K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                         hp.cutoff_coeff, pw.w3, bar_e, bar_wag, bar_wbg_full, self._new(b, Eu), g_freq)
+        K.bond_basis_bwd2(dist, ddist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
+                          hp.cutoff_coeff, pw.w3, rec["g_e0"], rec["g_wag"], rec["g_wbg_full"], g_freq)
+        G["freq_ag"], G["freq_bg"] = g_freq[0].to(dt), g_freq[1].to(dt)
+        if has_ang:
+            G["wang_t"] = wsum(tr["fb"], bar_a, 64, tfb, rec["g_a0"])[:NA]
+            g_fa = self._zeros(b, pw.freq_ang.shape[0], dtype=torch.float64)
+            K.angle_basis_bwd(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, bar_a, None, g_fa)
+            K.angle_basis_bwd2(rhat, drhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, rec["g_a0"], g_fa)
+            G["freq_ang"] = g_fa.to(dt)
 
     def _wgrad(self, b, x, g, n, *, x_rows=None, g_rows=None, x_silu=False, colsum=False):
         out = self._new(b, 64, n)
@@ -256,7 +487,8 @@ class Engine:
         self.K.colsum(a, out, bmul, rowscale)
         return out.to(self.pw.emb.dtype)
 
-    def _reverse(self, st: dict, out: EngineOutput, train: dict | None) -> None:
+    def _reverse(self, st: dict, out: EngineOutput, train: dict | None, rec: dict | None = None) -> None:
+        """``rec`` (inference seeds only): keep the adjoints (lambda = dE/d.) the second-order pass needs."""
         pw, K, hp = self.pw, self.K, self.pw.hp
         b: DeviceBatch = st["b"]
         N, Ed, Eu, A, B = b.n_atoms, b.n_edges, b.n_bonds, b.n_angles, b.n_graphs
@@ -310,7 +542,12 @@ class Engine:
             gp, sv = pw.atom[t], saved_atom[t]
             g_agg = self._lin(b, g_xout, gp.extra["wo"])
             g_pre, g_w = self._new(b, Ed, 128), self._new(b, Ed, 64)
-            if G is None:
+            if rec is not None:
+                g_p = self._new(b, Ed, 128)
+                K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
+                                g_pre, g_w, g_p, None)
+                rec["atom"][t] = dict(g_xout=g_xout, g_agg=g_agg, g_p=g_p)
+            elif G is None:
                 K.atom_conv_bwd(sv["pcn"], sv["pe"], wag, b.center, b.nbr, b.d2u, sv["p"], g_agg, gp.w2, gp.ln,
                                 g_pre, g_w)
             else:
@@ -326,6 +563,8 @@ class Engine:
             K.segment_sum(g_pre, b.perm_n, b.ptr_n, 0, sp[:, 128:])
             g_xin = acc(g_xout, sp, gp.extra["wcn_b"])
             spe = self._seg(b, g_pre, b.perm_u, b.ptr_u, Eu)
+            if rec is not None:
+                rec["atom"][t].update(sp=sp, spe=spe)
             if G is not None:
                 G[f"atom.{t}.wcn_t"] = self._wgrad(b, sv["x"], sp, 256)
                 G[f"atom.{t}.we_t"], G[f"atom.{t}.b1"] = self._wgrad(b, sv["e"], spe, 128, colsum=True)
@@ -341,6 +580,8 @@ class Engine:
             K.segment_sum(g_pre, b.perm_js, b.ptr_js, 0, sp[:, 128:])
             K.linear(sp, ex["wij_b"], None, g_e, g_e, None, sid)  # g_e[sid] += sp @ Wij
             spx = self._seg(b, g_pre, b.perm_x, b.ptr_x, N)
+            if rec is not None:
+                rec[key.split(".")[0]][int(key.split(".")[1])].update(sp=sp, spx=spx, g_pre=g_pre)
             if G is not None:  # first-layer blocks: bonds i|j (bias rides on i), centre atom, angle
                 G[f"{key}.wij_t"] = self._wgrad(b, sv["e"], sp, 256, x_rows=sid)
                 G[f"{key}.wx_t"] = self._wgrad(b, sv["x"], spx, 128)
@@ -360,6 +601,8 @@ class Engine:
                 if t < n_conv - 2:  # AngleUpdate_t: a_{t+1} = a_t + G0(e_{t+1}, a_t, x_{t+1})
                     ga = pw.angle[t]
                     g_pre = self._new(b, A, 128)
+                    if rec is not None:
+                        rec["angle"][t] = dict(g_ang_in=g_a)
                     if G is None:
                         K.angle_update_bwd(saved_angle[t]["p"], g_a, ga.ln, g_pre)
                     else:
@@ -374,7 +617,12 @@ class Engine:
                 g_agg = self._lin(b, g_e, gp.extra["wo"], x_rows=sid)
                 g_pre = self._new(b, A, 128)
                 gw_i, gw_j = self._new(b, A, 64), self._new(b, A, 64)
-                if G is None:
+                if rec is not None:
+                    g_p = self._new(b, A, 128)
+                    K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
+                                    gw_i, gw_j, g_p, None)
+                    rec["bond"][t] = dict(g_eout=g_e.clone(), g_agg=g_agg, g_p=g_p)
+                elif G is None:
                     K.bond_conv_bwd(sv["pre"], sv["p"], wbg_s, b.ang_is, b.ang_js, g_agg, gp.w2, gp.ln, g_pre,
                                     gw_i, gw_j)
                 else:
@@ -416,6 +664,8 @@ class Engine:
                 K.angle_basis_bwd(rhat, b.ang_di, b.ang_dj, pw.freq_ang, pw.wang, g_a, None, g_fa)
                 G["freq_ang"] = g_fa.to(g_e.dtype)
             return
+        if rec is not None:
+            rec.update(g_e0=g_e, g_wag=g_wag, g_wbg_full=g_wbg_full, g_a0=g_a)
         K.bond_basis_bwd(dist, b.u2d, pw.freq_ag, pw.freq_bg, hp.atom_graph_cutoff, hp.bond_graph_cutoff,
                          hp.cutoff_coeff, pw.w3, g_e, g_wag, g_wbg_full, g_dist)
         g_rhat = self._zeros(b, Ed, 3, dtype=torch.float64)

@@ -100,6 +100,88 @@ def _rbf_dfreq(d, freq, rc, p):
     return nrm * torch.cos(freq * x) / rc * env
 
 
+
+# ---- second-order pieces (force / stress losses: d/dtheta of T = <dE/dr, rdot>) ------------------
+def _d2silu(x):
+    s = _sig(x)
+    return s * (1 - s) * (2 + x * (1 - 2 * s))
+
+
+def _dsig(x):
+    s = _sig(x)
+    return s * (1 - s)
+
+
+def _d2sig(x):
+    s = _sig(x)
+    return s * (1 - s) * (1 - 2 * s)
+
+
+def _ln_tan(pd, xhat, rstd):
+    """tangent of xhat = (p - mean) rstd along pd"""
+    return rstd * (pd - pd.mean(dim=1, keepdim=True) - xhat * (xhat * pd).mean(dim=1, keepdim=True))
+
+
+def _gate_tan(p, pd, ln):
+    """o = silu(LN1 p_core) sigmoid(LN2 p_gate) and its tangent along pd; cache for _gate_bwd2."""
+    pc, pg, pdc, pdg = p[:, :64], p[:, 64:], pd[:, :64], pd[:, 64:]
+    if ln is not None:
+        y1, xh1, r1 = _ln_fwd(pc, ln[0], ln[1])
+        y2, xh2, r2 = _ln_fwd(pg, ln[2], ln[3])
+        xd1, xd2 = _ln_tan(pdc, xh1, r1), _ln_tan(pdg, xh2, r2)
+        yd1, yd2 = ln[0] * xd1, ln[2] * xd2
+    else:
+        y1, y2, yd1, yd2 = pc, pg, pdc, pdg
+        xh1 = xh2 = r1 = r2 = xd1 = xd2 = None
+    o = _silu(y1) * _sig(y2)
+    od = _dsilu(y1) * _sig(y2) * yd1 + _silu(y1) * _dsig(y2) * yd2
+    return o, od, (y1, y2, yd1, yd2, xh1, xh2, r1, r2, xd1, xd2, pdc, pdg)
+
+
+def _gate_bwd2(go, a, cache, ln, g_ln=None):
+    """u = d/dp [ <go, o(p)> + <a, Do(p)[pd]> ] with go, a, pd held fixed; the LayerNorm affine
+    gradients of the same scalar are accumulated into g_ln ([4][64] flat: g1, b1, g2, b2)."""
+    y1, y2, yd1, yd2, xh1, xh2, r1, r2, xd1, xd2, pdc, pdg = cache
+    s, ds, d2s = _silu(y1), _dsilu(y1), _d2silu(y1)
+    t, dt, d2t = _sig(y2), _dsig(y2), _d2sig(y2)
+    gy1 = go * t * ds + a * (d2s * t * yd1 + ds * dt * yd2)
+    gy2 = go * s * dt + a * (ds * dt * yd1 + s * d2t * yd2)
+    k1, k2 = a * ds * t, a * s * dt  # d/d(ydot)
+    if ln is None:
+        return torch.cat([gy1, gy2], dim=1)
+
+    def branch(gy, kap, gamma, xh, r, xd, pd):
+        kk = kap * gamma
+        v = gy * gamma + r * (-kk * (xh * pd).mean(dim=1, keepdim=True) - (kk * xh).sum(dim=1, keepdim=True) * pd / 64)
+        q = r * (v - v.mean(dim=1, keepdim=True) - xh * (v * xh).mean(dim=1, keepdim=True))
+        return q - r * xh * (kk * xd).sum(dim=1, keepdim=True) / 64
+
+    if g_ln is not None:
+        g_ln += torch.stack([(gy1 * xh1 + k1 * xd1).sum(0), gy1.sum(0), (gy2 * xh2 + k2 * xd2).sum(0), gy2.sum(0)]).reshape(-1).to(g_ln.dtype)
+    return torch.cat([branch(gy1, k1, ln[0], xh1, r1, xd1, pdc), branch(gy2, k2, ln[2], xh2, r2, xd2, pdg)], dim=1)
+
+
+def _rbf_d_dfreq(d, freq, rc, p):
+    """d/dfreq_k of (d basis_k / dd)  [M,R]  (mixed second derivative)."""
+    d = d[:, None]
+    x = d / rc
+    nrm = math.sqrt(2.0 / rc)
+    sn, cs = torch.sin(freq * x), torch.cos(freq * x)
+    if p != 0:
+        a, b, cc = -(p + 1) * (p + 2) / 2, p * (p + 2), -p * (p + 1) / 2
+        env = 1 + a * x**p + b * x ** (p + 1) + cc * x ** (p + 2)
+        denv = (a * p * x ** (p - 1) + b * (p + 1) * x**p + cc * (p + 2) * x ** (p + 1)) / rc
+        inside = x < 1
+        env = torch.where(inside, env, torch.zeros_like(env))
+        denv = torch.where(inside, denv, torch.zeros_like(denv))
+    else:
+        env, denv = torch.ones_like(x), torch.zeros_like(x)
+    # raw = nrm sin(w x)/d ; draw = nrm [ (w/rc) cos(w x)/d - sin(w x)/d^2 ]
+    draw_dw = nrm * ((1 / rc) * cs / d - (freq / rc) * x * sn / d - x * cs / d**2)
+    raw_dw = nrm * x * cs / d
+    return draw_dw * env + raw_dw * denv
+
+
 class SpecKernels:
     """Drop-in for ``chgnet_b200._lib.CudaKernels`` in CPU tests."""
 
@@ -269,13 +351,163 @@ class SpecKernels:
             g_ang_in = torch.zeros_like(save_p[:, :64])
         g_pre.copy_(_gate_bwd(g_ang_in, saved, ln, g_ln))
 
+
+    # ---- second-order kernels: tangent pass along rdot, and the reverse of (primal + tangent) --------
+    def edge_tangent(self, rvec, dist, rhat, center, nbr, owner, u_atom, w_graph, ddist, drhat):
+        """rdot_e = u[c] - u[n] + r_e . W[graph(c)];  ddist = rhat . rdot;  drhat = (rdot - rhat ddist)/d"""
+        c, n = center.long(), nbr.long()
+        rdot = u_atom[c] - u_atom[n] + torch.einsum("ei,eij->ej", rvec, w_graph.view(-1, 3, 3)[owner.long()[c]])
+        dd = (rhat * rdot).sum(dim=1)
+        ddist.copy_(dd)
+        drhat.copy_((rdot - rhat * dd[:, None]) / dist[:, None])
+
+    def bond_basis_tangent(self, dist, ddist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0d, wagd, wbgd, tbasis):
+        du, ddu = dist[u2d.long()], ddist[u2d.long()]
+        _, dag = _rbf(du, freq_ag, rc_ag, p)
+        _, dbg = _rbf(du, freq_bg, rc_bg, p)
+        tag, tbg = dag * ddu[:, None], dbg * ddu[:, None]
+        e0d.copy_(tag @ w3t[0]), wagd.copy_(tag @ w3t[1]), wbgd.copy_(tbg @ w3t[2])
+        R = freq_ag.shape[0]
+        tbasis.zero_()
+        tbasis[:, :R] = tag
+        tbasis[:, 32 : 32 + R] = tbg
+
+    def bond_basis_bwd2(self, dist, ddist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, lam_e0, lam_wag, lam_wbg, g_freq):
+        """g_freq += d/dfreq < lam, (dB/dd ddist) W >  (lam held fixed)"""
+        du, ddu = dist[u2d.long()], ddist[u2d.long()]
+        gb_ag = lam_e0 @ w3[0] + lam_wag @ w3[1]
+        gb_bg = lam_wbg @ w3[2]
+        g_freq[0] += (gb_ag * _rbf_d_dfreq(du, freq_ag, rc_ag, p) * ddu[:, None]).sum(dim=0).to(g_freq.dtype)
+        g_freq[1] += (gb_bg * _rbf_d_dfreq(du, freq_bg, rc_bg, p) * ddu[:, None]).sum(dim=0).to(g_freq.dtype)
+
+    def _theta_dot(self, rhat, drhat, ang_di, ang_dj):
+        i, j = ang_di.long(), ang_dj.long()
+        u = (rhat[i] * rhat[j]).sum(dim=1) * (1 - 1e-6)
+        ud = ((drhat[i] * rhat[j]).sum(dim=1) + (rhat[i] * drhat[j]).sum(dim=1)) * (1 - 1e-6)
+        return torch.acos(u), -ud / torch.sqrt(1 - u * u)
+
+    def angle_basis_tangent(self, rhat, drhat, ang_di, ang_dj, freq, wt, a0d, tbasis):
+        th, thd = self._theta_dot(rhat, drhat, ang_di, ang_dj)
+        arg = th[:, None] * freq[None, :]
+        fd = torch.cat([torch.zeros_like(th[:, None]), torch.cos(arg) * freq, -torch.sin(arg) * freq], dim=1)
+        fd = fd * thd[:, None] / math.sqrt(math.pi)
+        a0d.copy_(fd @ wt)
+        tbasis.zero_()
+        tbasis[:, : fd.shape[1]] = fd
+
+    def angle_basis_bwd2(self, rhat, drhat, ang_di, ang_dj, freq, w, lam_a0, g_freq):
+        th, thd = self._theta_dot(rhat, drhat, ang_di, ang_dj)
+        arg = th[:, None] * freq[None, :]
+        nf = freq.shape[0]
+        gf = (lam_a0 @ w) / math.sqrt(math.pi)
+        sn, cs = torch.sin(arg), torch.cos(arg)
+        # d/dw [ w cos(w th) ] = cos - w th sin ;  d/dw [ -w sin(w th) ] = -(sin + w th cos)
+        term = gf[:, 1 : 1 + nf] * (cs - arg * sn) - gf[:, 1 + nf :] * (sn + arg * cs)
+        g_freq += (term * thd[:, None]).sum(dim=0).to(g_freq.dtype)
+
+    @staticmethod
+    def _w2(h, w2t):
+        return torch.cat([h[:, :64] @ w2t[:, :64], h[:, 64:] @ w2t[:, 64:]], dim=1)
+
+    @staticmethod
+    def _w2_bwd(g, w2):
+        return torch.cat([g[:, :64] @ w2[:64], g[:, 64:] @ w2[64:]], dim=1)
+
+    def atom_conv_tan(self, pcn_d, pe_d, wag, wag_d, center, nbr, d2u, save_pre, save_p, w2t, ln, msg_d, pre_d, p_d):
+        pre_d.copy_(self._atom_pre(pcn_d, pe_d, center, nbr, d2u))
+        p_d.copy_(self._w2(_dsilu(save_pre) * pre_d, w2t))
+        o, od, _ = _gate_tan(save_p, p_d, ln)
+        u = d2u.long()
+        msg_d.copy_(od * wag[u] + o * wag_d[u])
+
+    def atom_conv_bwd2(self, save_pre, save_p, pre_d, p_d, g_p_lam, wag, wag_d, center, d2u, lam_agg, bar_agg, w2, ln,
+                       bar_pre, bar_w, u_out, g_ln):
+        c, u = center.long(), d2u.long()
+        lam, bar, w, wd = lam_agg[c], bar_agg[c], wag[u], wag_d[u]
+        o, od, cache = _gate_tan(save_p, p_d, ln)
+        bar_w.copy_(bar * o + lam * od)
+        uu = _gate_bwd2(bar * w + lam * wd, lam * w, cache, ln, g_ln)
+        u_out.copy_(uu)
+        bar_pre.copy_(_dsilu(save_pre) * self._w2_bwd(uu, w2) + _d2silu(save_pre) * pre_d * self._w2_bwd(g_p_lam, w2))
+
+    def bond_conv_tan(self, pij_d, px_d, pa_d, wbg, wbg_d, ang_atom, ang_i, ang_j, save_pre, save_p, w2t, ln, upd_d,
+                      pre_d, p_d):
+        pre_d.copy_(self._bond_pre(pij_d, px_d, pa_d, ang_atom, ang_i, ang_j))
+        p_d.copy_(self._w2(_dsilu(save_pre) * pre_d, w2t))
+        o, od, _ = _gate_tan(save_p, p_d, ln)
+        i, j = ang_i.long(), ang_j.long()
+        upd_d.copy_(od * wbg[i] * wbg[j] + o * (wbg_d[i] * wbg[j] + wbg[i] * wbg_d[j]))
+
+    def bond_conv_bwd2(self, save_pre, save_p, pre_d, p_d, g_p_lam, wbg, wbg_d, ang_i, ang_j, lam_agg, bar_agg, w2, ln,
+                       bar_pre, bar_wi, bar_wj, u_out, g_ln):
+        i, j = ang_i.long(), ang_j.long()
+        lam, bar = lam_agg[i], bar_agg[i]
+        wi, wj, wdi, wdj = wbg[i], wbg[j], wbg_d[i], wbg_d[j]
+        o, od, cache = _gate_tan(save_p, p_d, ln)
+        bar_wi.copy_(bar * o * wj + lam * (od * wj + o * wdj))
+        bar_wj.copy_(bar * o * wi + lam * (od * wi + o * wdi))
+        uu = _gate_bwd2(bar * wi * wj + lam * (wdi * wj + wi * wdj), lam * wi * wj, cache, ln, g_ln)
+        u_out.copy_(uu)
+        bar_pre.copy_(_dsilu(save_pre) * self._w2_bwd(uu, w2) + _d2silu(save_pre) * pre_d * self._w2_bwd(g_p_lam, w2))
+
+    def angle_update_tan(self, pij_d, px_d, pa_d, ang_d, ang_atom, ang_i, ang_j, save_p, ln, ang_new_d, p_d):
+        p_d.copy_(self._bond_pre(pij_d, px_d, pa_d, ang_atom, ang_i, ang_j))
+        _, od, _ = _gate_tan(save_p, p_d, ln)
+        ang_new_d.copy_(od + ang_d)
+
+    def angle_update_bwd2(self, save_p, p_d, lam_ang, bar_ang, ln, bar_pre, g_ln):
+        """lam_ang / bar_ang: lambda / R2 adjoint of ang_new (None = zero)."""
+        _, _, cache = _gate_tan(save_p, p_d, ln)
+        z = torch.zeros_like(save_p[:, :64])
+        bar_pre.copy_(_gate_bwd2(z if bar_ang is None else bar_ang, z if lam_ang is None else lam_ang, cache, ln, g_ln))
+
+    def readout_bwd2(self, x, xd, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, bar_x, h_all, hd_all, gz_all, zbar_all,
+                     g_h0, hbar0, xhat, xhatd):
+        """Reverse of (readout, its tangent along xd) for the scalar  sum_i seed_i site_e_i + T_i,
+        T_i = <d site_e_i/dx_i, xd_i>.  gz_all = lambda of the pre-activations (seed 1) = adjoint of the
+        tangent pre-activations; zbar_all = adjoint of the primal pre-activations."""
+        L = mlp_wt.shape[0]
+        if ln is not None:
+            h0, xh, rstd = _ln_fwd(x, ln[0], ln[1])
+            xd_hat = _ln_tan(xd, xh, rstd)
+            hd = ln[0] * xd_hat
+            xhat.copy_(xh), xhatd.copy_(xd_hat)
+        else:
+            h0, hd = x, xd
+        h, zs, zds = h0, [], []
+        for l in range(L):
+            h_all[l].copy_(h), hd_all[l].copy_(hd)
+            z = h @ mlp_wt[l] + mlp_b[l]
+            zd = hd @ mlp_wt[l]
+            zs.append(z), zds.append(zd)
+            h, hd = _silu(z), _dsilu(z) * zd
+        h_all[L].copy_(h), hd_all[L].copy_(hd)
+        hdbar = w_last[None, :].expand_as(h)  # adjoint of hd_L (T = hd_L . w_last)
+        hbar = w_last[None, :] * seed[:, None]  # adjoint of h_L (energy-loss seed)
+        for l in reversed(range(L)):
+            zdbar = hdbar * _dsilu(zs[l])
+            zbar = hdbar * _d2silu(zs[l]) * zds[l] + hbar * _dsilu(zs[l])
+            gz_all[l].copy_(zdbar), zbar_all[l].copy_(zbar)
+            hdbar, hbar = zdbar @ mlp_w[l], zbar @ mlp_w[l]
+        g_h0.copy_(hdbar), hbar0.copy_(hbar)
+        if ln is None:
+            bar_x.copy_(hbar)
+            return
+        kk = hdbar * ln[0]
+        v = hbar * ln[0] + rstd * (-kk * (xh * xd).mean(dim=1, keepdim=True) - (kk * xh).sum(dim=1, keepdim=True) * xd / 64)
+        q = rstd * (v - v.mean(dim=1, keepdim=True) - xh * (v * xh).mean(dim=1, keepdim=True))
+        bar_x.copy_(q - rstd * xh * (kk * xd_hat).sum(dim=1, keepdim=True) / 64)
+
     # ---- training-only kernels (reference trainer.py:398-411: loss.backward() + optimizer.step())
-    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False):
+    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False, x2=None):
         """out[64][n] = act(x[x_rows])^T @ g[g_rows]; colsum[n] = sum_rows g[g_rows].  x, g, out may be
-        column-slice views (unit column stride)."""
+        column-slice views (unit column stride).  act: identity; x_silu -> silu(x); x2 given ->
+        silu'(x) * x2 (the tangent of the hidden activations)."""
         xs = x if x_rows is None else x[x_rows.long()]
         gs = g if g_rows is None else g[g_rows.long()]
-        if x_silu:
+        if x2 is not None:
+            xs = _dsilu(xs) * x2
+        elif x_silu:
             xs = _silu(xs)
         out.copy_(xs.T @ gs)
         if colsum is not None:

@@ -156,3 +156,46 @@ def test_two_rank_gradient_allreduce_equals_global_batch(weights030):
         assert loss == pytest.approx(want_loss, rel=1e-6)  # global-batch means on every rank
         assert flat.shape == flat_want.shape
         assert np.abs(flat - flat_want).max() <= 1e-6 * max(np.abs(flat_want).max(), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# force / stress losses: the second-order pass against autograd's double backward (fp64)
+# ---------------------------------------------------------------------------------------------
+def _oracle_efsm_grads(weights, graphs, ce, cm, cf, cs, args=None):
+    P = {k: torch.as_tensor(np.asarray(v)).double().requires_grad_(k != "composition_model.fc.weight")
+         for k, v in weights.items()}
+    out = orc.forward(P, graphs, "efsm", dtype=torch.float64, train=True, args=args)
+    n = out["atoms_per_graph"].double()
+    loss = ((out["e"] * n * ce).sum() + (torch.cat(out["m"]) * cm).sum() + (torch.cat(out["f"]) * cf).sum()
+            + (torch.stack(out["s"]) * cs).sum())
+    names = [k for k, v in P.items() if v.requires_grad]
+    gr = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    return {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(names, gr)}
+
+
+@pytest.mark.parametrize("compact", [True, False])
+def test_force_and_stress_loss_gradients_match_double_backward(weights030, compact):
+    graphs = graphgen.random_graphs(3, 6, 10, 8600)
+    n_atoms = sum(g.atomic_number.shape[0] for g in graphs)
+    gen = torch.Generator().manual_seed(7)
+    ce = torch.randn(len(graphs), generator=gen, dtype=torch.float64)
+    cm = torch.randn(n_atoms, generator=gen, dtype=torch.float64)
+    cf = torch.randn(n_atoms, 3, generator=gen, dtype=torch.float64)
+    cs = torch.randn(len(graphs), 3, 3, generator=gen, dtype=torch.float64)
+    want = _oracle_efsm_grads(weights030, graphs, ce, cm, cf, cs)
+
+    sd = {k: torch.as_tensor(np.asarray(v)).double() for k, v in weights030.items()}
+    eng = Engine(pack_weights(sd, None, device="cpu", dtype=torch.float64), SpecKernels())
+    b = build_batch(graphs, "cpu", compact_bonds=compact)
+    b.frac, b.lattice, b.image = b.frac.double(), b.lattice.double(), b.image.double()
+    out = eng.run(b, need_grad=True, need_magmom=True, train=True)
+    eng.input_grads(out, record=True)
+    got = unpack_grads(eng.param_grads(out, ce, cm, cf, cs), sd)
+    worst = 0.0
+    for k, w in want.items():
+        scale = max(float(w.abs().max()), 1.0)
+        err = float((got[k] - w).abs().max())
+        worst = max(worst, err / scale)
+        # second derivatives near collinear angles amplify rounding (acos' ~ 1/sqrt(1-u^2) up to 700)
+        assert err <= 1e-6 * scale, (k, err, scale)
+    print("worst relative error", worst)
