@@ -57,16 +57,20 @@ def make_workload(name: str, rank: int):
         z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000 + rank)
         return [graphgen.make_crystal_graph(z, frac, lat, graph_id="LiMnO2-10x5x25")], "LiMnO2 10x5x25 supercell, 10,000 atoms, sigma=0.02 A"
     if name == "c5":
-        return graphgen.random_graphs(128, 20, 40, 5000 + 1000 * rank), "fine-tune batch=128 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A; targets 'em' (MSE), Adam lr 1e-3"
+        return graphgen.random_graphs(128, 20, 40, 5000 + 1000 * rank), "fine-tune batch=128 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A; targets 'efsm' (MSE, ratios 1/1/0.1/0.1), Adam lr 1e-3"
     raise SystemExit(f"unknown workload {name}")
 
 
 def train_labels(preds, seed: int):
-    """labels = prediction + uniform noise (+-0.1 eV/atom, +-0.03 muB)"""
+    """labels = prediction + uniform noise (+-0.1 eV/atom, +-0.01 eV/A, +-0.05 GPa, +-0.03 muB)"""
     gen = torch.Generator().manual_seed(seed)
-    e = torch.tensor([float(p["e"]) for p in preds]) + (torch.rand(len(preds), generator=gen) - 0.5) * 0.2
-    m = [torch.as_tensor(p["m"]) + (torch.rand(len(p["m"]), generator=gen) - 0.5) * 0.06 for p in preds]
-    return e, m
+
+    def noisy(v, amp):
+        v = torch.as_tensor(np.asarray(v), dtype=torch.float32)
+        return v + (torch.rand(v.shape, generator=gen) - 0.5) * 2 * amp
+
+    return {"e": noisy([float(p["e"]) for p in preds], 0.1), "f": [noisy(p["f"], 0.01) for p in preds],
+            "s": [noisy(p["s"], 0.05) for p in preds], "m": [noisy(p["m"], 0.03) for p in preds]}
 
 
 def run_reference_train(args) -> None:
@@ -77,16 +81,17 @@ def run_reference_train(args) -> None:
     graphs, desc = make_workload("c5", 0)
     sample = graphs[: max(1, min(len(graphs), args.cpu_sample))]
     w = orc.load_weights_npz(WEIGHTS)
-    base = orc.predict_graph(w, sample, "em", batch_size=len(sample))
-    e_t, m_t = train_labels(base, 5)
+    base = orc.predict_graph(w, sample, "efsm", batch_size=len(sample))
+    lab = train_labels(base, 5)
     P = {k: torch.as_tensor(np.asarray(v)).float().requires_grad_(k != "composition_model.fc.weight") for k, v in w.items()}
     opt = torch.optim.Adam([v for v in P.values() if v.requires_grad], lr=1e-3)
     crit = torch.nn.MSELoss()
 
     def step():
         opt.zero_grad()
-        out = orc.forward(P, sample, "em", train=True)
-        loss = crit(e_t, out["e"]) + 0.1 * crit(torch.cat(m_t), torch.cat(out["m"]))
+        out = orc.forward(P, sample, "efsm", train=True)
+        loss = (crit(lab["e"], out["e"]) + crit(torch.cat(lab["f"]), torch.cat(out["f"]))
+                + 0.1 * crit(torch.stack(lab["s"]), torch.stack(out["s"])) + 0.1 * crit(torch.cat(lab["m"]), torch.cat(out["m"])))
         loss.backward()
         opt.step()
 
@@ -100,10 +105,10 @@ def run_reference_train(args) -> None:
     value = len(sample) / dt
     sdesc = f"first {len(sample)} graphs of the batch per step; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep)"
     print(json.dumps({
-        "impl": "reference", "metric": "train_structures_per_sec_EM", "value": value, "unit": "structures/s",
+        "impl": "reference", "metric": "train_structures_per_sec_EFSM", "value": value, "unit": "structures/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c5: {desc}", "task": "train em"},
+        "config": {"workload": f"c5: {desc}", "task": "train efsm"},
         "cpu_baseline": {"value": value, "unit": "structures/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sdesc},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -128,9 +133,9 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
         model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev)
     graphs, desc = make_workload("c5", rank)
     c = counts(graphs)
-    base = model.predict_graph(graphs, task="em", batch_size=len(graphs))
-    e_t, m_t = train_labels(base, 5 + rank)
-    trainer = Trainer(model, targets="em", criterion="MSE", learning_rate=1e-3)
+    base = model.predict_graph(graphs, task="efsm", batch_size=len(graphs))
+    lab = train_labels(base, 5 + rank)
+    trainer = Trainer(model, targets="efsm", criterion="MSE", learning_rate=1e-3)
     flush = L2Flush(dev)
     K = model._get_engine().K
 
@@ -140,12 +145,11 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.synchronize()
 
     batch = build_batch(graphs, dev, with_reverse=True)
-    e_dev = e_t.to(dev)
-    m_dev = torch.cat(m_t).to(dev)
+    tg_dev = trainer._targets(lab, batch.atoms_per_graph, dev)
 
     def step_resident():
         engine = model._get_engine()  # re-packs the weights the previous Adam step changed
-        report_, G = loss_and_grads(engine, batch, trainer.cfg, e_dev, m_dev, model.is_intensive, None)
+        report_, G = loss_and_grads(engine, batch, trainer.cfg, tg_dev, model.is_intensive, None)
         fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
         if world > 1:
             dist.all_reduce(fg)
@@ -179,10 +183,10 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
     ms_per_step = float(t.item()) / args.steps
 
     # end to end: Trainer.train_step from host graphs + host labels, report read back every step
-    targets = {"e": e_t, "m": m_t}
+    targets = lab
     for _ in range(2):
         trainer.train_step(graphs, targets)
-    h2d = int(build_batch(graphs, dev, with_reverse=True).h2d_bytes) + 4 * (len(e_t) + int(m_dev.numel()))
+    h2d = int(build_batch(graphs, dev, with_reverse=True).h2d_bytes) + 4 * sum(int(v.numel()) for v in tg_dev.values())
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -209,17 +213,19 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
 
     eng2 = Engine(model._get_engine().pw, ek)
     out2 = eng2.run(batch, need_grad=True, need_magmom=True, train=True)
-    eng2.param_grads(out2, torch.ones(c["graphs"], device=dev), torch.ones(c["atoms"], device=dev))
+    eng2.input_grads(out2, record=True)
+    eng2.param_grads(out2, torch.ones(c["graphs"], device=dev), torch.ones(c["atoms"], device=dev),
+                     torch.ones(c["atoms"], 3, device=dev), torch.ones(c["graphs"], 3, 3, device=dev))
     shares = ek.table()
     total = c["graphs"] * world
     print(json.dumps({
-        "metric": "train_structures_per_sec_EM", "value": total / (ms_per_step * 1e-3), "unit": "structures/s",
+        "metric": "train_structures_per_sec_EFSM", "value": total / (ms_per_step * 1e-3), "unit": "structures/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c5: {desc}", "task": "train em", "per_gpu": c, "weights": "CHGNet 0.3.0",
+        "config": {"workload": f"c5: {desc}", "task": "train efsm", "per_gpu": c, "weights": "CHGNet 0.3.0",
                    "l2": "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations",
                    "parallelism": f"graph-sharded x{world}, one all-reduce of the flat gradient buffer per step",
-                   "note": "force / stress loss terms are not built yet: this is the 'em' training step, not the C5 'efsm' one"},
+                   "second_order": "tangent pass + reverse over (primal, tangent) for the force / stress loss terms"},
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "structures/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48, "api": "Trainer.train_step(list[CrystalGraph] on host, labels on host)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,

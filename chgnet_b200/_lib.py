@@ -40,12 +40,25 @@ SIGNATURES: dict[str, list] = {
     "chg_magmom": [P, I, P, F, P, P],
     "chg_force_virial": [P, P, P, P, P, P, P, P, P, P, I, P, P, P],
     # training
-    "chg_wgrad": [P, I, P, I, P, I, P, I, I, P, I, P, P, P],
+    "chg_wgrad": [P, P, I, P, I, P, I, P, I, I, P, I, P, P, P],
     "chg_colsum": [P, I, P, I, P, I, I, P, P],
     "chg_readout_bwd": [P, I, P, P, P, P, I, P, P, P, P, P, P, P, P],
     "chg_magmom_bwd": [P, I, P, F, P, P, P, P],
     "chg_loss_terms": [P, P, I, I, F, P, P, P],
     "chg_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P],
+    # second order (force / stress losses)
+    "chg_edge_tangent": [P, P, P, P, P, P, P, P, I, P, P, P],
+    "chg_bond_basis_tangent": [P, P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
+    "chg_bond_basis_bwd2": [P, P, P, I, P, P, I, F, F, I, P, P, P, P, P, P],
+    "chg_angle_basis_tangent": [P, P, P, P, I, P, I, P, P, P, P],
+    "chg_angle_basis_bwd2": [P, P, P, P, I, P, I, P, P, P, P],
+    "chg_atom_conv_tan": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P],
+    "chg_atom_conv_bwd2": [P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
+    "chg_bond_conv_tan": [P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P],
+    "chg_bond_conv_bwd2": [P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, P],
+    "chg_angle_update_tan": [P, P, P, P, P, P, P, I, P, P, P, P, P],
+    "chg_angle_update_bwd2": [P, P, P, P, I, P, P, P, P],
+    "chg_readout_bwd2": [P, P, I, P, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P],
 }
 
 _lib = None
@@ -227,11 +240,13 @@ class CudaKernels:
             self._ws = ws
         return ws
 
-    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False):
-        self._chk_rows(x, g, out)
+    def wgrad(self, x, g, out, colsum=None, x_rows=None, g_rows=None, x_silu=False, x2=None):
+        self._chk_rows(x, g, out, x2)
         self._chk(colsum, x_rows, g_rows)
+        if x2 is not None and x2.stride(0) != x.stride(0):
+            raise ChgnetB200Error("wgrad: x2 must have the row stride of x")
         m = x_rows.shape[0] if x_rows is not None else (g_rows.shape[0] if g_rows is not None else x.shape[0])
-        self._call("chg_wgrad", _p(x), x.stride(0), _p(x_rows), int(bool(x_silu)), _p(g), g.stride(0), _p(g_rows), m,
+        self._call("chg_wgrad", _p(x), _p(x2), x.stride(0), _p(x_rows), int(bool(x_silu)), _p(g), g.stride(0), _p(g_rows), m,
                    out.shape[1], _p(out), out.stride(0), _p(colsum), _p(self._workspace(out.shape[1], x.device)))
 
     def colsum(self, a, out, b=None, rowscale=None):
@@ -252,6 +267,78 @@ class CudaKernels:
     def loss_terms(self, pred, target, kind, delta, g_pred, sums):
         self._chk(pred, target, g_pred, sums)
         self._call("chg_loss_terms", _p(pred), _p(target), pred.numel(), int(kind), float(delta), _p(g_pred), _p(sums))
+
+    # ------------------------------------------------------------------ second order
+    def edge_tangent(self, rvec, dist, rhat, center, nbr, owner, u_atom, w_graph, ddist, drhat):
+        self._chk(rvec, dist, rhat, center, nbr, owner, u_atom, w_graph, ddist, drhat)
+        self._call("chg_edge_tangent", _p(rvec), _p(dist), _p(rhat), _p(center), _p(nbr), _p(owner), _p(u_atom),
+                   _p(w_graph), center.shape[0], _p(ddist), _p(drhat))
+
+    def bond_basis_tangent(self, dist, ddist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3t, e0d, wagd, wbgd, tbasis):
+        self._chk(dist, ddist, u2d, freq_ag, freq_bg, w3t, e0d, wagd, wbgd, tbasis)
+        self._call("chg_bond_basis_tangent", _p(dist), _p(ddist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
+                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3t), _p(e0d), _p(wagd), _p(wbgd), _p(tbasis))
+
+    def bond_basis_bwd2(self, dist, ddist, u2d, freq_ag, freq_bg, rc_ag, rc_bg, p, w3, lam_e0, lam_wag, lam_wbg, g_freq):
+        self._chk(dist, ddist, u2d, freq_ag, freq_bg, w3, lam_e0, lam_wag, lam_wbg, g_freq)
+        self._call("chg_bond_basis_bwd2", _p(dist), _p(ddist), _p(u2d), u2d.shape[0], _p(freq_ag), _p(freq_bg),
+                   freq_ag.shape[0], float(rc_ag), float(rc_bg), int(p), _p(w3), _p(lam_e0), _p(lam_wag), _p(lam_wbg),
+                   _p(g_freq))
+
+    def angle_basis_tangent(self, rhat, drhat, ang_di, ang_dj, freq, wt, a0d, tbasis):
+        self._chk(rhat, drhat, ang_di, ang_dj, freq, wt, a0d, tbasis)
+        self._call("chg_angle_basis_tangent", _p(rhat), _p(drhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
+                   freq.shape[0], _p(wt), _p(a0d), _p(tbasis))
+
+    def angle_basis_bwd2(self, rhat, drhat, ang_di, ang_dj, freq, w, lam_a0, g_freq):
+        self._chk(rhat, drhat, ang_di, ang_dj, freq, w, lam_a0, g_freq)
+        self._call("chg_angle_basis_bwd2", _p(rhat), _p(drhat), _p(ang_di), _p(ang_dj), ang_di.shape[0], _p(freq),
+                   freq.shape[0], _p(w), _p(lam_a0), _p(g_freq))
+
+    def atom_conv_tan(self, pcn_d, pe_d, wag, wag_d, center, nbr, d2u, save_pre, save_p, w2t, ln, msg_d, pre_d, p_d):
+        self._chk(pcn_d, pe_d, wag, wag_d, center, nbr, d2u, save_pre, save_p, w2t, ln, msg_d, pre_d, p_d)
+        self._call("chg_atom_conv_tan", _p(pcn_d), _p(pe_d), _p(wag), _p(wag_d), _p(center), _p(nbr), _p(d2u),
+                   center.shape[0], _p(save_pre), _p(save_p), _p(w2t), _p(ln), _p(msg_d), _p(pre_d), _p(p_d))
+
+    def atom_conv_bwd2(self, save_pre, save_p, pre_d, p_d, g_p_lam, wag, wag_d, center, d2u, lam_agg, bar_agg, w2, ln,
+                       bar_pre, bar_w, u_out, g_ln):
+        self._chk(save_pre, save_p, pre_d, p_d, g_p_lam, wag, wag_d, center, d2u, lam_agg, bar_agg, w2, ln, bar_pre,
+                  bar_w, u_out, g_ln)
+        self._call("chg_atom_conv_bwd2", _p(save_pre), _p(save_p), _p(pre_d), _p(p_d), _p(g_p_lam), _p(wag), _p(wag_d),
+                   _p(center), _p(d2u), center.shape[0], _p(lam_agg), _p(bar_agg), _p(w2), _p(ln), _p(bar_pre), _p(bar_w),
+                   _p(u_out), _p(g_ln))
+
+    def bond_conv_tan(self, pij_d, px_d, pa_d, wbg, wbg_d, ang_atom, ang_i, ang_j, save_pre, save_p, w2t, ln, upd_d,
+                      pre_d, p_d):
+        self._chk(pij_d, px_d, pa_d, wbg, wbg_d, ang_atom, ang_i, ang_j, save_pre, save_p, w2t, ln, upd_d, pre_d, p_d)
+        self._call("chg_bond_conv_tan", _p(pij_d), _p(px_d), _p(pa_d), _p(wbg), _p(wbg_d), _p(ang_atom), _p(ang_i),
+                   _p(ang_j), ang_i.shape[0], _p(save_pre), _p(save_p), _p(w2t), _p(ln), _p(upd_d), _p(pre_d), _p(p_d))
+
+    def bond_conv_bwd2(self, save_pre, save_p, pre_d, p_d, g_p_lam, wbg, wbg_d, ang_i, ang_j, lam_agg, bar_agg, w2, ln,
+                       bar_pre, bar_wi, bar_wj, u_out, g_ln):
+        self._chk(save_pre, save_p, pre_d, p_d, g_p_lam, wbg, wbg_d, ang_i, ang_j, lam_agg, bar_agg, w2, ln, bar_pre,
+                  bar_wi, bar_wj, u_out, g_ln)
+        self._call("chg_bond_conv_bwd2", _p(save_pre), _p(save_p), _p(pre_d), _p(p_d), _p(g_p_lam), _p(wbg), _p(wbg_d),
+                   _p(ang_i), _p(ang_j), ang_i.shape[0], _p(lam_agg), _p(bar_agg), _p(w2), _p(ln), _p(bar_pre),
+                   _p(bar_wi), _p(bar_wj), _p(u_out), _p(g_ln))
+
+    def angle_update_tan(self, pij_d, px_d, pa_d, ang_d, ang_atom, ang_i, ang_j, save_p, ln, ang_new_d, p_d):
+        self._chk(pij_d, px_d, pa_d, ang_d, ang_atom, ang_i, ang_j, save_p, ln, ang_new_d, p_d)
+        self._call("chg_angle_update_tan", _p(pij_d), _p(px_d), _p(pa_d), _p(ang_d), _p(ang_atom), _p(ang_i), _p(ang_j),
+                   ang_i.shape[0], _p(save_p), _p(ln), _p(ang_new_d), _p(p_d))
+
+    def angle_update_bwd2(self, save_p, p_d, lam_ang, bar_ang, ln, bar_pre, g_ln):
+        self._chk(save_p, p_d, lam_ang, bar_ang, ln, bar_pre, g_ln)
+        self._call("chg_angle_update_bwd2", _p(save_p), _p(p_d), _p(lam_ang), _p(bar_ang), save_p.shape[0], _p(ln),
+                   _p(bar_pre), _p(g_ln))
+
+    def readout_bwd2(self, x, xd, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, bar_x, h_all, hd_all, gz_all, zbar_all,
+                     g_h0, hbar0, xhat, xhatd):
+        self._chk(x, xd, ln, mlp_wt, mlp_w, mlp_b, w_last, seed, bar_x, h_all, hd_all, gz_all, zbar_all, g_h0, hbar0,
+                  xhat, xhatd)
+        self._call("chg_readout_bwd2", _p(x), _p(xd), x.shape[0], _p(ln), _p(mlp_wt), _p(mlp_w), _p(mlp_b),
+                   mlp_wt.shape[0], _p(w_last), _p(seed), _p(bar_x), _p(h_all), _p(hd_all), _p(gz_all), _p(zbar_all),
+                   _p(g_h0), _p(hbar0), _p(xhat), _p(xhatd))
 
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
         self._chk(p, g, m, v)

@@ -88,6 +88,62 @@ __device__ __forceinline__ void gather_pre(float (&acc)[4][8], const float* __re
 }
 
 
+// ---- shared by gated.cu (first order) and gated_2nd.cu (second order) ---------------------------
+#ifdef __CUDACC__
+constexpr int TM = 64;     // rows (edges / angles) per tile
+constexpr int NTHR = 256;  // threads per CTA
+
+__device__ __forceinline__ void copy_to_smem(float* dst, const float* src, int n_floats, int tid) {
+  for (int i = tid * 4; i < n_floats; i += NTHR * 4) sts4(dst + i, ldg4(src + i));
+}
+
+// Block-diagonal pair of 64x64 products on a [64][HS] tile:
+// acc[i][0..3] += sum_k T[r0+i][k]    * Bc[k][c0..]
+// acc[i][4..7] += sum_k T[r0+i][64+k] * Bg[k][c0..]
+// Bc row k at sBc + k*ldb, Bg row k at sBg + k*ldb.
+__device__ __forceinline__ void gemm_blockdiag(float (&acc)[4][8], const float* __restrict__ sT,
+                                               const float* __restrict__ sBc, const float* __restrict__ sBg,
+                                               int ldb, int r0, int c0) {
+#pragma unroll 2
+  for (int k4 = 0; k4 < 16; ++k4) {
+    float4 hc[4], hg[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hc[i] = lds4(sT + (r0 + i) * HS + k4 * 4);
+      hg[i] = lds4(sT + (r0 + i) * HS + 64 + k4 * 4);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 wc = lds4(sBc + (k4 * 4 + kk) * ldb + c0);
+      const float4 wg = lds4(sBg + (k4 * 4 + kk) * ldb + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = f4at(hc[i], kk);
+        const float g = f4at(hg[i], kk);
+        acc[i][0] = fmaf(a, wc.x, acc[i][0]);
+        acc[i][1] = fmaf(a, wc.y, acc[i][1]);
+        acc[i][2] = fmaf(a, wc.z, acc[i][2]);
+        acc[i][3] = fmaf(a, wc.w, acc[i][3]);
+        acc[i][4] = fmaf(g, wg.x, acc[i][4]);
+        acc[i][5] = fmaf(g, wg.y, acc[i][5]);
+        acc[i][6] = fmaf(g, wg.z, acc[i][6]);
+        acc[i][7] = fmaf(g, wg.w, acc[i][7]);
+      }
+    }
+  }
+}
+
+
+template <typename KernelT>
+inline int resident_ctas(KernelT kernel, int smem_bytes) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NTHR, smem_bytes) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return per_sm * sm_count();
+}
+
+#endif
+
 // entry points of the tcgen05 implementation (gated_tc.cu)
 int atom_conv_fwd_tc(const FwdArgs& a, cudaStream_t stream);
 int bond_conv_fwd_tc(const FwdArgs& a, cudaStream_t stream);

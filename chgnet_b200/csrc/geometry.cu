@@ -390,6 +390,239 @@ angle_basis_bwd_kernel(const float* __restrict__ rhat, const int32_t* __restrict
   }
 }
 
+// =====================================================================================
+// Second-order pass of a force / stress loss (reference model.py:518-535 create_graph=True):
+// tangents along a fixed direction rdot of the edge vectors, and the mixed derivatives of the
+// basis functions with respect to their learnable frequencies.
+// =====================================================================================
+__global__ void edge_tangent_kernel(const float* __restrict__ rvec, const float* __restrict__ dist,
+                                    const float* __restrict__ rhat, const int32_t* __restrict__ center,
+                                    const int32_t* __restrict__ nbr, const int32_t* __restrict__ owner,
+                                    const float* __restrict__ u_atom, const float* __restrict__ w_graph, int n_edges,
+                                    float* __restrict__ ddist, float* __restrict__ drhat) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int c = center[e], n = nbr[e];
+  const float* W = w_graph + (size_t)owner[c] * 9;
+  float r[3], rh[3], rd[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    r[j] = rvec[(size_t)e * 3 + j];
+    rh[j] = rhat[(size_t)e * 3 + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)  // rdot = u[c] - u[n] + r . W
+    rd[j] = u_atom[(size_t)c * 3 + j] - u_atom[(size_t)n * 3 + j] +
+            fmaf(r[2], __ldg(W + 6 + j), fmaf(r[1], __ldg(W + 3 + j), r[0] * __ldg(W + j)));
+  const float dd = fmaf(rh[2], rd[2], fmaf(rh[1], rd[1], rh[0] * rd[0]));
+  const float inv_d = 1.f / dist[e];
+  ddist[e] = dd;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) drhat[(size_t)e * 3 + j] = (rd[j] - rh[j] * dd) * inv_d;
+}
+
+// d basis_k / dd for lane k (0 outside the basis), both cutoffs
+__device__ __forceinline__ void rbf_ddist(float d, float f_ag, float f_bg, float rc_ag, float rc_bg, int p, bool live,
+                                          float& dag, float& dbg) {
+  dag = dbg = 0.f;
+  if (!live) return;
+  const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
+  const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
+  float sn, cs;
+  sincosf(f_ag * (d / rc_ag), &sn, &cs);
+  dag = fmaf(nrm_ag * ((f_ag / rc_ag) * cs / d - sn / (d * d)), ea.env, (nrm_ag * sn / d) * ea.denv);
+  if (eb.env != 0.f || eb.denv != 0.f || !(d == d)) {
+    sincosf(f_bg * (d / rc_bg), &sn, &cs);
+    dbg = fmaf(nrm_bg * ((f_bg / rc_bg) * cs / d - sn / (d * d)), eb.env, (nrm_bg * sn / d) * eb.denv);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bond_basis_tangent_kernel(const float* __restrict__ dist, const float* __restrict__ ddist,
+                          const int32_t* __restrict__ u2d, int n_bonds, const float* __restrict__ freq_ag,
+                          const float* __restrict__ freq_bg, int R, float rc_ag, float rc_bg, int p,
+                          const float* __restrict__ w3t, float* __restrict__ e0d, float* __restrict__ wagd,
+                          float* __restrict__ wbgd, float* __restrict__ tbasis) {
+  extern __shared__ __align__(16) float s_w[];  // [3][R][64]
+  for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3t[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float f_ag = lane < R ? freq_ag[lane] : 0.f, f_bg = lane < R ? freq_bg[lane] : 0.f;
+  for (int u = warp; u < n_bonds; u += n_warps) {
+    const int e = u2d[u];
+    const float d = dist[e], dd = ddist[e];
+    float tag, tbg;
+    rbf_ddist(d, f_ag, f_bg, rc_ag, rc_bg, p, lane < R, tag, tbg);
+    tag *= dd;
+    tbg *= dd;
+    tbasis[(size_t)u * 64 + lane] = tag;
+    tbasis[(size_t)u * 64 + 32 + lane] = tbg;
+    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < R; ++k) {
+      const float* w = s_w + k * 64;
+      const float ba = __shfl_sync(0xffffffffu, tag, k), bb = __shfl_sync(0xffffffffu, tbg, k);
+      o[0] = fmaf(ba, w[lane], o[0]);
+      o[1] = fmaf(ba, w[lane + 32], o[1]);
+      o[2] = fmaf(ba, w[R * 64 + lane], o[2]);
+      o[3] = fmaf(ba, w[R * 64 + lane + 32], o[3]);
+      o[4] = fmaf(bb, w[2 * R * 64 + lane], o[4]);
+      o[5] = fmaf(bb, w[2 * R * 64 + lane + 32], o[5]);
+    }
+    e0d[(size_t)u * 64 + lane] = o[0];
+    e0d[(size_t)u * 64 + lane + 32] = o[1];
+    wagd[(size_t)u * 64 + lane] = o[2];
+    wagd[(size_t)u * 64 + lane + 32] = o[3];
+    wbgd[(size_t)u * 64 + lane] = o[4];
+    wbgd[(size_t)u * 64 + lane + 32] = o[5];
+  }
+}
+
+// g_freq += d/dfreq < lam, (dB/dd ddist) W >
+__global__ void __launch_bounds__(256)
+bond_basis_bwd2_kernel(const float* __restrict__ dist, const float* __restrict__ ddist,
+                       const int32_t* __restrict__ u2d, int n_bonds, const float* __restrict__ freq_ag,
+                       const float* __restrict__ freq_bg, int R, float rc_ag, float rc_bg, int p,
+                       const float* __restrict__ w3, const float* __restrict__ lam_e0,
+                       const float* __restrict__ lam_wag, const float* __restrict__ lam_wbg,
+                       double* __restrict__ g_freq) {
+  extern __shared__ __align__(16) float s_w[];  // [3][64][R]
+  for (int i = threadIdx.x; i < 3 * R * 64; i += blockDim.x) s_w[i] = w3[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int kl = lane < R ? lane : 0;
+  const float f_ag = freq_ag[kl], f_bg = freq_bg[kl];
+  const float nrm_ag = sqrtf(2.f / rc_ag), nrm_bg = sqrtf(2.f / rc_bg);
+  double gf_ag = 0.0, gf_bg = 0.0;
+  for (int u = warp; u < n_bonds; u += n_warps) {
+    const int e = u2d[u];
+    const float d = dist[e], dd = ddist[e];
+    const float a0 = lam_e0[(size_t)u * 64 + lane], a1 = lam_e0[(size_t)u * 64 + lane + 32];
+    const float b0 = lam_wag[(size_t)u * 64 + lane], b1 = lam_wag[(size_t)u * 64 + lane + 32];
+    const float c0 = lam_wbg[(size_t)u * 64 + lane], c1 = lam_wbg[(size_t)u * 64 + lane + 32];
+    float gb_ag = 0.f, gb_bg = 0.f;
+    for (int n = 0; n < 32; ++n) {
+      gb_ag = fmaf(__shfl_sync(0xffffffffu, a0, n), s_w[n * R + kl], gb_ag);
+      gb_ag = fmaf(__shfl_sync(0xffffffffu, a1, n), s_w[(n + 32) * R + kl], gb_ag);
+      gb_ag = fmaf(__shfl_sync(0xffffffffu, b0, n), s_w[(64 + n) * R + kl], gb_ag);
+      gb_ag = fmaf(__shfl_sync(0xffffffffu, b1, n), s_w[(64 + n + 32) * R + kl], gb_ag);
+      gb_bg = fmaf(__shfl_sync(0xffffffffu, c0, n), s_w[(128 + n) * R + kl], gb_bg);
+      gb_bg = fmaf(__shfl_sync(0xffffffffu, c1, n), s_w[(128 + n + 32) * R + kl], gb_bg);
+    }
+    if (lane < R) {
+      // d/dw of  nrm [ (w/rc) cos(w x)/d - sin(w x)/d^2 ] env + nrm sin(w x)/d env' ,  x = d/rc
+      const Envelope ea = envelope(d, rc_ag, p), eb = envelope(d, rc_bg, p);
+      float sn, cs;
+      float x = d / rc_ag;
+      sincosf(f_ag * x, &sn, &cs);
+      float mixed = nrm_ag * (cs / (rc_ag * d) - (f_ag / rc_ag) * x * sn / d - x * cs / (d * d)) * ea.env +
+                    nrm_ag * x * cs / d * ea.denv;
+      gf_ag += (double)(gb_ag * mixed * dd);
+      if (eb.env != 0.f || eb.denv != 0.f || !(d == d)) {
+        x = d / rc_bg;
+        sincosf(f_bg * x, &sn, &cs);
+        mixed = nrm_bg * (cs / (rc_bg * d) - (f_bg / rc_bg) * x * sn / d - x * cs / (d * d)) * eb.env +
+                nrm_bg * x * cs / d * eb.denv;
+        gf_bg += (double)(gb_bg * mixed * dd);
+      }
+    }
+  }
+  if (lane < R) {
+    atomicAdd(g_freq + lane, gf_ag);
+    atomicAdd(g_freq + R + lane, gf_bg);
+  }
+}
+
+// theta and its tangent for angle (di, dj)
+__device__ __forceinline__ void theta_dot(const float* __restrict__ rhat, const float* __restrict__ drhat, int di,
+                                          int dj, float& th, float& thd) {
+  float ri[3], rj[3];
+  const float u = angle_cos(rhat, di, dj, ri, rj);
+  float ud = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    ud = fmaf(drhat[(size_t)di * 3 + j], rj[j], fmaf(ri[j], drhat[(size_t)dj * 3 + j], ud));
+  ud *= (1.f - 1e-6f);
+  th = acosf(u);
+  thd = -ud / sqrtf(1.f - u * u);
+}
+
+__global__ void __launch_bounds__(256)
+angle_basis_tangent_kernel(const float* __restrict__ rhat, const float* __restrict__ drhat,
+                           const int32_t* __restrict__ ang_di, const int32_t* __restrict__ ang_dj, int n_angles,
+                           const float* __restrict__ freq, int nf, const float* __restrict__ wt,
+                           float* __restrict__ a0d, float* __restrict__ tbasis) {
+  extern __shared__ __align__(16) float s_w[];  // [2nf+1][64]
+  const int nb = 2 * nf + 1;
+  for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool is_sin = lane >= 1 && lane <= nf, is_cos = lane > nf && lane < nb;
+  const float w = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
+  const float inv_sqrt_pi = 0.5641895835477563f;
+  for (int a = warp; a < n_angles; a += n_warps) {
+    float th, thd;
+    theta_dot(rhat, drhat, ang_di[a], ang_dj[a], th, thd);
+    float fd = 0.f;
+    if (is_sin) fd = w * cosf(w * th);
+    else if (is_cos) fd = -w * sinf(w * th);
+    fd *= thd * inv_sqrt_pi;
+    tbasis[(size_t)a * 64 + lane] = fd;
+    tbasis[(size_t)a * 64 + 32 + lane] = 0.f;
+    float oa = 0.f, ob = 0.f;
+    for (int m = 0; m < nb; ++m) {
+      const float fm = __shfl_sync(0xffffffffu, fd, m);
+      oa = fmaf(fm, s_w[m * 64 + lane], oa);
+      ob = fmaf(fm, s_w[m * 64 + lane + 32], ob);
+    }
+    a0d[(size_t)a * 64 + lane] = oa;
+    a0d[(size_t)a * 64 + lane + 32] = ob;
+  }
+}
+
+// g_freq += d/dfreq < lam_a0, (dF/dtheta thetadot) W >
+__global__ void __launch_bounds__(256)
+angle_basis_bwd2_kernel(const float* __restrict__ rhat, const float* __restrict__ drhat,
+                        const int32_t* __restrict__ ang_di, const int32_t* __restrict__ ang_dj, int n_angles,
+                        const float* __restrict__ freq, int nf, const float* __restrict__ w,
+                        const float* __restrict__ lam_a0, double* __restrict__ g_freq) {
+  extern __shared__ __align__(16) float s_w[];  // [64][2nf+1]
+  const int nb = 2 * nf + 1;
+  for (int i = threadIdx.x; i < nb * 64; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const bool is_sin = lane >= 1 && lane <= nf, is_cos = lane > nf && lane < nb;
+  const float wf = is_sin ? freq[lane - 1] : (is_cos ? freq[lane - 1 - nf] : 0.f);
+  const int ml = lane < nb ? lane : 0;
+  const float inv_sqrt_pi = 0.5641895835477563f;
+  double gfr = 0.0;
+  for (int a = warp; a < n_angles; a += n_warps) {
+    float th, thd;
+    theta_dot(rhat, drhat, ang_di[a], ang_dj[a], th, thd);
+    const float ga = lam_a0[(size_t)a * 64 + lane], gb = lam_a0[(size_t)a * 64 + lane + 32];
+    float gf = 0.f;
+    for (int n = 0; n < 32; ++n) {
+      gf = fmaf(__shfl_sync(0xffffffffu, ga, n), s_w[n * nb + ml], gf);
+      gf = fmaf(__shfl_sync(0xffffffffu, gb, n), s_w[(n + 32) * nb + ml], gf);
+    }
+    float sn, cs;
+    const float arg = wf * th;
+    sincosf(arg, &sn, &cs);
+    // d/dw [ w cos(w th) ] = cos - w th sin ;  d/dw [ -w sin(w th) ] = -(sin + w th cos)
+    if (is_sin) gfr += (double)(gf * (cs - arg * sn) * thd * inv_sqrt_pi);
+    else if (is_cos) gfr -= (double)(gf * (sn + arg * cs) * thd * inv_sqrt_pi);
+  }
+  if (is_sin) atomicAdd(g_freq + lane - 1, gfr);
+  else if (is_cos) atomicAdd(g_freq + lane - 1 - nf, gfr);
+}
+
 // ---- magmom head -------------------------------------------------------------------
 __global__ void magmom_kernel(const float* __restrict__ x, int n_atoms, const float* __restrict__ w, float b,
                               float* __restrict__ m) {
@@ -570,5 +803,70 @@ extern "C" int chg_force_virial(const float* rvec, const float* dist, const floa
                 "null pointer");
   force_virial_kernel<<<(n_edges + 255) / 256, 256, 0, as_stream(stream)>>>(
       rvec, dist, rhat, g_rhat, g_dist, d2u, u2d, center, nbr, atom_owner, n_edges, force, virial);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_edge_tangent(const float* rvec, const float* dist, const float* rhat, const int32_t* center,
+                                const int32_t* nbr, const int32_t* atom_owner, const float* u_atom,
+                                const float* w_graph, int32_t n_edges, float* ddist, float* drhat, void* stream) {
+  CHG_CHECK_ARG(n_edges >= 0, "negative size");
+  if (n_edges == 0) return CHG_OK;
+  CHG_CHECK_ARG(rvec && dist && rhat && center && nbr && atom_owner && u_atom && w_graph && ddist && drhat, "null pointer");
+  edge_tangent_kernel<<<(n_edges + 255) / 256, 256, 0, as_stream(stream)>>>(rvec, dist, rhat, center, nbr, atom_owner,
+                                                                            u_atom, w_graph, n_edges, ddist, drhat);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_bond_basis_tangent(const float* dist, const float* ddist, const int32_t* u2d, int32_t n_bonds,
+                                      const float* freq_ag, const float* freq_bg, int32_t n_radial, float rc_ag,
+                                      float rc_bg, int32_t p, const float* w3t, float* e0d, float* wagd, float* wbgd,
+                                      float* tbasis, void* stream) {
+  CHG_CHECK_ARG(n_bonds >= 0, "negative size");
+  CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
+  if (n_bonds == 0) return CHG_OK;
+  CHG_CHECK_ARG(dist && ddist && u2d && freq_ag && freq_bg && w3t && e0d && wagd && wbgd && tbasis, "null pointer");
+  const int smem = 3 * n_radial * 64 * 4;
+  bond_basis_tangent_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+      dist, ddist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3t, e0d, wagd, wbgd, tbasis);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_bond_basis_bwd2(const float* dist, const float* ddist, const int32_t* u2d, int32_t n_bonds,
+                                   const float* freq_ag, const float* freq_bg, int32_t n_radial, float rc_ag,
+                                   float rc_bg, int32_t p, const float* w3, const float* lam_e0, const float* lam_wag,
+                                   const float* lam_wbg, double* g_freq, void* stream) {
+  CHG_CHECK_ARG(n_bonds >= 0, "negative size");
+  CHG_CHECK_ARG(n_radial >= 1 && n_radial <= MAX_BASIS, "num_radial must be in [1, 32]");
+  if (n_bonds == 0) return CHG_OK;
+  CHG_CHECK_ARG(dist && ddist && u2d && freq_ag && freq_bg && w3 && lam_e0 && lam_wag && lam_wbg && g_freq, "null pointer");
+  const int smem = 3 * n_radial * 64 * 4;
+  bond_basis_bwd2_kernel<<<warp_grid(n_bonds), 256, smem, as_stream(stream)>>>(
+      dist, ddist, u2d, n_bonds, freq_ag, freq_bg, n_radial, rc_ag, rc_bg, p, w3, lam_e0, lam_wag, lam_wbg, g_freq);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_angle_basis_tangent(const float* rhat, const float* drhat, const int32_t* ang_di,
+                                       const int32_t* ang_dj, int32_t n_angles, const float* freq, int32_t n_freq,
+                                       const float* wt, float* a0d, float* tbasis, void* stream) {
+  CHG_CHECK_ARG(n_angles >= 0, "negative size");
+  CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
+  if (n_angles == 0) return CHG_OK;
+  CHG_CHECK_ARG(rhat && drhat && ang_di && ang_dj && freq && wt && a0d && tbasis, "null pointer");
+  const int smem = (2 * n_freq + 1) * 64 * 4;
+  angle_basis_tangent_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, drhat, ang_di, ang_dj, n_angles,
+                                                                                   freq, n_freq, wt, a0d, tbasis);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_angle_basis_bwd2(const float* rhat, const float* drhat, const int32_t* ang_di, const int32_t* ang_dj,
+                                    int32_t n_angles, const float* freq, int32_t n_freq, const float* w,
+                                    const float* lam_a0, double* g_freq, void* stream) {
+  CHG_CHECK_ARG(n_angles >= 0, "negative size");
+  CHG_CHECK_ARG(n_freq >= 0 && 2 * n_freq + 1 <= MAX_BASIS, "num_angular must be odd and <= 31");
+  if (n_angles == 0) return CHG_OK;
+  CHG_CHECK_ARG(rhat && drhat && ang_di && ang_dj && freq && w && lam_a0 && g_freq, "null pointer");
+  const int smem = (2 * n_freq + 1) * 64 * 4;
+  angle_basis_bwd2_kernel<<<warp_grid(n_angles), 256, smem, as_stream(stream)>>>(rhat, drhat, ang_di, ang_dj, n_angles,
+                                                                                freq, n_freq, w, lam_a0, g_freq);
   CHG_LAUNCH_END();
 }

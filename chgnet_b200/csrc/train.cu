@@ -20,9 +20,11 @@ namespace {
 constexpr int WG_ROWS = 32;  // rows staged per step
 constexpr int WG_MAX_CHUNKS = 1024;
 
-template <bool SILU>
+// ACT: 0 x, 1 silu(x), 2 silu'(x) * x2 (tangent of the hidden activations; x2 shares x's rows / stride)
+template <int ACT>
 __global__ void __launch_bounds__(256)
-wgrad_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ x_rows, const float* __restrict__ g,
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ x2, int ldx, const int32_t* __restrict__ x_rows,
+             const float* __restrict__ g,
              int ldg, const int32_t* __restrict__ g_rows, int m, int n, float* __restrict__ partial,
              float* __restrict__ cs_partial) {
   __shared__ __align__(16) float s_x[WG_ROWS][64];
@@ -43,7 +45,7 @@ wgrad_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ x
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   // register-staged software pipeline: the global loads of step s+1 are in flight while step s
   // is multiplied out of shared memory
-  float4 xr[2], gr[2];
+  float4 xr[2], gr[2], x2r[2];
   auto fetch = [&](int step) {
     const int base = step * WG_ROWS;
 #pragma unroll
@@ -53,10 +55,12 @@ wgrad_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ x
       const int row = base + r;
       xr[h] = make_float4(0.f, 0.f, 0.f, 0.f);
       gr[h] = xr[h];
+      x2r[h] = xr[h];
       if (row < m) {
         const int xi = x_rows != nullptr ? x_rows[row] : row;
         const int gi = g_rows != nullptr ? g_rows[row] : row;
         xr[h] = ldg4(x + (size_t)xi * ldx + c);
+        if (ACT == 2) x2r[h] = ldg4(x2 + (size_t)xi * ldx + c);
         gr[h] = ldg4(g + (size_t)gi * ldg + col_base + c);
       }
     }
@@ -69,7 +73,10 @@ wgrad_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ x
       const int f4 = tid + h * 256;
       const int r = f4 >> 4, c = (f4 & 15) * 4;
       float4 xv = xr[h];
-      if (SILU) xv = make_float4(silu_f(xv.x), silu_f(xv.y), silu_f(xv.z), silu_f(xv.w));
+      if (ACT == 1) xv = make_float4(silu_f(xv.x), silu_f(xv.y), silu_f(xv.z), silu_f(xv.w));
+      if (ACT == 2)
+        xv = make_float4(dsilu_f(xv.x) * x2r[h].x, dsilu_f(xv.y) * x2r[h].y, dsilu_f(xv.z) * x2r[h].z,
+                         dsilu_f(xv.w) * x2r[h].w);
       sts4(&s_x[r][c], xv);
       sts4(&s_g[r][c], gr[h]);
     }
@@ -238,6 +245,139 @@ readout_bwd_kernel(const float* __restrict__ x, int n_atoms, const float* __rest
   }
 }
 
+// ---- readout, second order: reverse of (readout, its tangent along xd) ---------------------------------
+// scalar per atom:  seed * site_e + <d site_e / dx, xd>.  gz_all = adjoint of the TANGENT pre-activations
+// (= dE/dz with seed 1), zbar_all = adjoint of the PRIMAL pre-activations.  (oracle/kernel_specs.py
+// readout_bwd2 states the same maths.)
+__device__ __forceinline__ float d2silu_r(float x) {
+  const float s = sigmoid_f(x);
+  return s * (1.f - s) * fmaf(x, 1.f - 2.f * s, 2.f);
+}
+
+__global__ void __launch_bounds__(256)
+readout_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ xd, int n_atoms,
+                    const float* __restrict__ ln, const float* __restrict__ mlp_wt, const float* __restrict__ mlp_w,
+                    const float* __restrict__ mlp_b, int n_hidden, const float* __restrict__ w_last,
+                    const float* __restrict__ seed, float* __restrict__ bar_x, float* __restrict__ h_all,
+                    float* __restrict__ hd_all, float* __restrict__ gz_all, float* __restrict__ zbar_all,
+                    float* __restrict__ g_h0, float* __restrict__ hbar0, float* __restrict__ xhat,
+                    float* __restrict__ xhatd) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_wt = smem;
+  float* s_w = s_wt + n_hidden * 4096;
+  for (int i = threadIdx.x; i < n_hidden * 4096; i += blockDim.x) {
+    s_wt[i] = mlp_wt[i];
+    s_w[i] = mlp_w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float wl0 = w_last[lane], wl1 = w_last[lane + 32];
+  const size_t plane = (size_t)n_atoms * 64;
+  for (int atom = warp; atom < n_atoms; atom += n_warps) {
+    const size_t off = (size_t)atom * 64;
+    float h0 = x[off + lane], h1 = x[off + lane + 32];
+    float d0 = xd[off + lane], d1 = xd[off + lane + 32];
+    const float xd0 = d0, xd1 = d1;
+    float xh0 = 0.f, xh1 = 0.f, xt0 = 0.f, xt1 = 0.f, rstd = 1.f;
+    if (ln != nullptr) {
+      const float mean = sum32(h0 + h1) * (1.f / 64.f);
+      const float c0 = h0 - mean, c1 = h1 - mean;
+      const float var = sum32(fmaf(c0, c0, c1 * c1)) * (1.f / 64.f);
+      rstd = 1.f / sqrtf(var + 1e-5f);
+      xh0 = c0 * rstd;
+      xh1 = c1 * rstd;
+      const float m1 = sum32(d0 + d1) * (1.f / 64.f);
+      const float m2 = sum32(fmaf(xh0, d0, xh1 * d1)) * (1.f / 64.f);
+      xt0 = rstd * (d0 - m1 - xh0 * m2);
+      xt1 = rstd * (d1 - m1 - xh1 * m2);
+      h0 = fmaf(xh0, ln[lane], ln[64 + lane]);
+      h1 = fmaf(xh1, ln[lane + 32], ln[64 + lane + 32]);
+      d0 = ln[lane] * xt0;
+      d1 = ln[lane + 32] * xt1;
+      xhat[off + lane] = xh0;
+      xhat[off + lane + 32] = xh1;
+      xhatd[off + lane] = xt0;
+      xhatd[off + lane + 32] = xt1;
+    }
+    float za[MAX_HIDDEN], zb[MAX_HIDDEN], zda[MAX_HIDDEN], zdb[MAX_HIDDEN];
+#pragma unroll
+    for (int l = 0; l < MAX_HIDDEN; ++l) {
+      if (l < n_hidden) {
+        h_all[l * plane + off + lane] = h0;
+        h_all[l * plane + off + lane + 32] = h1;
+        hd_all[l * plane + off + lane] = d0;
+        hd_all[l * plane + off + lane + 32] = d1;
+        const float* wt = s_wt + l * 4096;
+        float a = mlp_b[l * 64 + lane], b = mlp_b[l * 64 + lane + 32], ad = 0.f, bd = 0.f;
+        for (int k = 0; k < 32; ++k) {
+          const float v0 = __shfl_sync(0xffffffffu, h0, k), v1 = __shfl_sync(0xffffffffu, h1, k);
+          const float u0 = __shfl_sync(0xffffffffu, d0, k), u1 = __shfl_sync(0xffffffffu, d1, k);
+          const float w00 = wt[k * 64 + lane], w01 = wt[k * 64 + lane + 32];
+          const float w10 = wt[(k + 32) * 64 + lane], w11 = wt[(k + 32) * 64 + lane + 32];
+          a = fmaf(v0, w00, a); b = fmaf(v0, w01, b); a = fmaf(v1, w10, a); b = fmaf(v1, w11, b);
+          ad = fmaf(u0, w00, ad); bd = fmaf(u0, w01, bd); ad = fmaf(u1, w10, ad); bd = fmaf(u1, w11, bd);
+        }
+        za[l] = a; zb[l] = b; zda[l] = ad; zdb[l] = bd;
+        h0 = silu_f(a);
+        h1 = silu_f(b);
+        d0 = dsilu_f(a) * ad;
+        d1 = dsilu_f(b) * bd;
+      }
+    }
+    h_all[n_hidden * plane + off + lane] = h0;
+    h_all[n_hidden * plane + off + lane + 32] = h1;
+    hd_all[n_hidden * plane + off + lane] = d0;
+    hd_all[n_hidden * plane + off + lane + 32] = d1;
+    const float sd = seed[atom];
+    float hdb0 = wl0, hdb1 = wl1;            // adjoint of hd (tangent stream)
+    float hb0 = wl0 * sd, hb1 = wl1 * sd;    // adjoint of h (primal stream)
+#pragma unroll
+    for (int l = MAX_HIDDEN - 1; l >= 0; --l) {
+      if (l < n_hidden) {
+        const float* w = s_w + l * 4096;
+        const float ds0 = dsilu_f(za[l]), ds1 = dsilu_f(zb[l]);
+        const float zdbar0 = hdb0 * ds0, zdbar1 = hdb1 * ds1;
+        const float zbar0 = fmaf(hdb0 * d2silu_r(za[l]), zda[l], hb0 * ds0);
+        const float zbar1 = fmaf(hdb1 * d2silu_r(zb[l]), zdb[l], hb1 * ds1);
+        gz_all[l * plane + off + lane] = zdbar0;
+        gz_all[l * plane + off + lane + 32] = zdbar1;
+        zbar_all[l * plane + off + lane] = zbar0;
+        zbar_all[l * plane + off + lane + 32] = zbar1;
+        float a = 0.f, b = 0.f, ab = 0.f, bb = 0.f;
+        for (int n = 0; n < 32; ++n) {
+          const float v0 = __shfl_sync(0xffffffffu, zdbar0, n), v1 = __shfl_sync(0xffffffffu, zdbar1, n);
+          const float u0 = __shfl_sync(0xffffffffu, zbar0, n), u1 = __shfl_sync(0xffffffffu, zbar1, n);
+          const float w00 = w[n * 64 + lane], w01 = w[n * 64 + lane + 32];
+          const float w10 = w[(n + 32) * 64 + lane], w11 = w[(n + 32) * 64 + lane + 32];
+          a = fmaf(v0, w00, a); b = fmaf(v0, w01, b); a = fmaf(v1, w10, a); b = fmaf(v1, w11, b);
+          ab = fmaf(u0, w00, ab); bb = fmaf(u0, w01, bb); ab = fmaf(u1, w10, ab); bb = fmaf(u1, w11, bb);
+        }
+        hdb0 = a; hdb1 = b; hb0 = ab; hb1 = bb;
+      }
+    }
+    g_h0[off + lane] = hdb0;
+    g_h0[off + lane + 32] = hdb1;
+    hbar0[off + lane] = hb0;
+    hbar0[off + lane + 32] = hb1;
+    if (ln != nullptr) {
+      const float k0 = hdb0 * ln[lane], k1 = hdb1 * ln[lane + 32];
+      const float m2 = sum32(fmaf(xh0, xd0, xh1 * xd1)) * (1.f / 64.f);
+      const float skx = sum32(fmaf(k0, xh0, k1 * xh1));
+      const float skt = sum32(fmaf(k0, xt0, k1 * xt1));
+      const float v0 = fmaf(hb0, ln[lane], rstd * (-k0 * m2 - skx * xd0 * (1.f / 64.f)));
+      const float v1 = fmaf(hb1, ln[lane + 32], rstd * (-k1 * m2 - skx * xd1 * (1.f / 64.f)));
+      const float mv = sum32(v0 + v1) * (1.f / 64.f);
+      const float mvx = sum32(fmaf(v0, xh0, v1 * xh1)) * (1.f / 64.f);
+      hb0 = rstd * (v0 - mv - xh0 * mvx) - rstd * xh0 * skt * (1.f / 64.f);
+      hb1 = rstd * (v1 - mv - xh1 * mvx) - rstd * xh1 * skt * (1.f / 64.f);
+    }
+    bar_x[off + lane] = hb0;
+    bar_x[off + lane + 32] = hb1;
+  }
+}
+
 // ---- magmom head reverse: m = |x.w + b| --------------------------------------------------------
 __global__ void magmom_bwd_kernel(const float* __restrict__ x, int n_atoms, const float* __restrict__ w, float b,
                                   const float* __restrict__ g_m, float* __restrict__ g_x,
@@ -327,24 +467,27 @@ extern "C" int64_t chg_wgrad_workspace_floats(int32_t n_out) {
   return chunks * (64 * (int64_t)n_out + n_out);
 }
 
-extern "C" int chg_wgrad(const float* x, int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
+extern "C" int chg_wgrad(const float* x, const float* x2, int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
                          int32_t ldg, const int32_t* g_rows, int32_t m, int32_t n_out, float* out, int32_t ldo,
                          float* colsum, float* workspace, void* stream) {
   CHG_CHECK_ARG(m >= 0, "negative size");
   CHG_CHECK_ARG(n_out > 0 && n_out % 64 == 0, "n_out must be a positive multiple of 64");
   CHG_CHECK_ARG(x && g && out && workspace, "null pointer");
   CHG_CHECK_ARG(ldx >= 64 && ldx % 4 == 0 && ldg >= n_out && ldg % 4 == 0 && ldo >= n_out, "bad leading dimension");
-  CHG_CHECK_ARG((((uintptr_t)x | (uintptr_t)g | (uintptr_t)workspace) & 15) == 0, "x, g, workspace must be 16-byte aligned");
+  CHG_CHECK_ARG((((uintptr_t)x | (uintptr_t)x2 | (uintptr_t)g | (uintptr_t)workspace) & 15) == 0,
+                "x, x2, g, workspace must be 16-byte aligned");
   const int steps = (m + WG_ROWS - 1) / WG_ROWS;
   // narrow outputs get more row chunks (more CTAs per SM in flight: the kernel is latency bound)
   const int n_chunks = max(1, min(min(steps, sm_count() * 2 * max(1, 256 / n_out)), WG_MAX_CHUNKS));
   float* partial = workspace;
   float* cs_partial = colsum != nullptr ? workspace + (size_t)n_chunks * 64 * n_out : nullptr;
   dim3 grid(n_chunks, n_out / 64);
-  if (x_silu)
-    wgrad_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, x_rows, g, ldg, g_rows, m, n_out, partial, cs_partial);
+  if (x2 != nullptr)
+    wgrad_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(x, x2, ldx, x_rows, g, ldg, g_rows, m, n_out, partial, cs_partial);
+  else if (x_silu)
+    wgrad_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(x, x2, ldx, x_rows, g, ldg, g_rows, m, n_out, partial, cs_partial);
   else
-    wgrad_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, x_rows, g, ldg, g_rows, m, n_out, partial, cs_partial);
+    wgrad_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(x, x2, ldx, x_rows, g, ldg, g_rows, m, n_out, partial, cs_partial);
   {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -420,5 +563,28 @@ extern "C" int chg_adam_step(float* p, const float* g, float* m, float* v, int64
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   const int blocks = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)sm_count() * 4));
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2);
+  CHG_LAUNCH_END();
+}
+
+extern "C" int chg_readout_bwd2(const float* x, const float* xd, int32_t n_atoms, const float* ln, const float* mlp_wt,
+                                const float* mlp_w, const float* mlp_b, int32_t n_hidden, const float* w_last,
+                                const float* seed, float* bar_x, float* h_all, float* hd_all, float* gz_all,
+                                float* zbar_all, float* g_h0, float* hbar0, float* xhat, float* xhatd, void* stream) {
+  CHG_CHECK_ARG(n_atoms >= 0, "negative size");
+  CHG_CHECK_ARG(n_hidden >= 1 && n_hidden <= MAX_HIDDEN, "n_hidden must be in [1, 4]");
+  if (n_atoms == 0) return CHG_OK;
+  CHG_CHECK_ARG(x && xd && mlp_wt && mlp_w && mlp_b && w_last && seed && bar_x && h_all && hd_all && gz_all && zbar_all &&
+                    g_h0 && hbar0, "null pointer");
+  CHG_CHECK_ARG(ln == nullptr || (xhat != nullptr && xhatd != nullptr), "xhat / xhatd are required with LayerNorm");
+  const int smem = 2 * n_hidden * 4096 * 4;
+  static int max_smem_set = 0;
+  if (smem > max_smem_set) {
+    CHG_CUDA(cudaFuncSetAttribute(readout_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    max_smem_set = smem;
+  }
+  const int blocks = max(1, min((n_atoms + 7) / 8, sm_count() * 2));
+  readout_bwd2_kernel<<<blocks, 256, smem, as_stream(stream)>>>(x, xd, n_atoms, ln, mlp_wt, mlp_w, mlp_b, n_hidden, w_last,
+                                                                seed, bar_x, h_all, hd_all, gz_all, zbar_all, g_h0, hbar0,
+                                                                xhat, xhatd);
   CHG_LAUNCH_END();
 }

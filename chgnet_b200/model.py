@@ -162,20 +162,20 @@ class _ParamGradBridge(torch.autograd.Function):
     """Joins the kernel engine to autograd: backward = the engine's training reverse pass."""
 
     @staticmethod
-    def forward(ctx, model, eng_out, names, e, m, *params):
-        ctx.model, ctx.eng_out, ctx.names = model, eng_out, names
-        ctx.has_m = m is not None
-        return e.clone(), (m.clone() if m is not None else e.new_zeros(0))
+    def forward(ctx, model, eng_out, names, keys, *tensors):
+        ctx.model, ctx.eng_out, ctx.names, ctx.keys = model, eng_out, names, keys
+        return tuple(t.clone() for t in tensors[: len(keys)])
 
     @staticmethod
-    def backward(ctx, g_e, g_m):
+    def backward(ctx, *g_outs):
         model, out = ctx.model, ctx.eng_out
         engine = model._get_engine()
-        n = torch.tensor(model.last_batch.atoms_per_graph, device=g_e.device, dtype=g_e.dtype)
-        seed_e = g_e / n if model.is_intensive else g_e  # d/d(extensive model energy)
-        G = engine.param_grads(out, seed_e.contiguous(), g_m.contiguous() if ctx.has_m else None)
+        g = {k: v.contiguous() for k, v in zip(ctx.keys, g_outs)}
+        n = torch.tensor(model.last_batch.atoms_per_graph, device=g["e"].device, dtype=g["e"].dtype)
+        seed_e = g["e"] / n if model.is_intensive else g["e"]  # d/d(extensive model energy)
+        G = engine.param_grads(out, seed_e.contiguous(), g.get("m"), g.get("f"), g.get("s"))
         grads = unpack_grads(G, model.state_dict())
-        return (None, None, None, None, None, *[grads[k] for k in ctx.names])
+        return (None, None, None, None, *[None] * len(ctx.keys), *[grads[k] for k in ctx.names])
 
 
 class _Node(nn.Module):
@@ -350,8 +350,8 @@ class CHGNet(nn.Module):
         self.last_batch = batch
         out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
                          need_crystal_fea=return_crystal_feas, train=train)
-        if train and need_grad:  # forces / stresses of a training step: values only (see forward)
-            engine.input_grads(out)
+        if train and need_grad:  # force pass; keeps the adjoints the second-order pass needs
+            engine.input_grads(out, record=True)
         self._last_out = out
         n_dev = torch.tensor(batch.atoms_per_graph, device=self.device)
         raw: dict[str, Any] = {"atoms_per_graph": n_dev}
@@ -391,20 +391,15 @@ class CHGNet(nn.Module):
         train = self.training and torch.is_grad_enabled()
         raw = self._run(graphs, task, return_site_energies, return_atom_feas, return_crystal_feas, train=train)
         if train:
-            # ``e`` and ``m`` carry autograd history to the parameters (the reference's training mode,
-            # model.py:518 / trainer.py:398-410); ``f`` and ``s`` are values only: a loss on them needs
-            # the second-order pass, which is not built yet
-            if ("f" in task or "s" in task) and not getattr(self, "_warned_train", False):
-                warnings.warn("chgnet_b200: forces / stresses returned in training mode carry no autograd "
-                              "history; only losses on e and m reach the parameters", stacklevel=2)
-                self._warned_train = True
+            # every output carries autograd history to the parameters (the reference's training mode,
+            # model.py:518-535 create_graph=True / trainer.py:398-410): backward() runs the engine's
+            # training reverse pass, with the second-order pass when f / s received a gradient
             names = [n for n, p in self.named_parameters() if p.requires_grad]
             params = [p for _, p in self.named_parameters() if p.requires_grad]
-            m_in = raw.get("m")
-            e, m = _ParamGradBridge.apply(self, self._last_out, names, raw["e"], m_in, *params)
-            raw["e"] = e
-            if m_in is not None:
-                raw["m"] = m
+            keys = [k for k in ("e", "m", "f", "s") if raw.get(k) is not None]
+            outs = _ParamGradBridge.apply(self, self._last_out, names, keys, *[raw[k] for k in keys], *params)
+            for k, v in zip(keys, outs):
+                raw[k] = v
         n_list = self.last_batch.atoms_per_graph
         pred: dict[str, Any] = {}
         for key, val in raw.items():

@@ -6,12 +6,12 @@ Mirrors the pieces of the reference ``Trainer`` that sit on the hot path of a fi
 ``energy_loss_ratio`` ..., ``optimizer="Adam"``, ``learning_rate``, ``delta``,
 ``allow_missing_labels``).
 
-What is covered: losses on energies and magnetic moments (``targets`` "e" / "em"),
-MSE / MAE / Huber with NaN-masked missing labels, Adam as one fused kernel over a flat parameter
-buffer, data-parallel training with ONE all-reduce of the flat gradient buffer per step
-(SURVEY.md §8e).  Losses on forces / stresses need the second-order reverse pass, which is not
-built yet: ``targets`` containing "f" or "s" raise ``NotImplementedError`` instead of training on
-a silently incomplete gradient.
+What is covered: every ``targets`` string of the reference ("e", "ef", "em", "efs",
+"efsm"), MSE / MAE / Huber with NaN-masked missing labels, Adam as one fused kernel over a flat
+parameter buffer, data-parallel training with ONE all-reduce of the flat gradient buffer per step
+(SURVEY.md §8e).  Losses on forces / stresses go through the second-order pass of the engine
+(``Engine._second_order``: tangent pass + reverse over (primal, tangent)), which replaces autograd's
+double backward (model.py:518-535 ``create_graph=True``).
 
 The loss normalisation follows the reference exactly for one process (``nn.MSELoss`` means over
 the batch); across ranks the means are over the GLOBAL batch: the per-term numerators and counts
@@ -43,10 +43,8 @@ class LossConfig:
     def __post_init__(self) -> None:
         if self.criterion not in _KIND:
             raise NotImplementedError(self.criterion)  # same as trainer.py:763
-        if "f" in self.target_str or "s" in self.target_str:
-            raise NotImplementedError(
-                "chgnet_b200 trains on energy / magmom losses (targets 'e' or 'em'); force and stress losses "
-                "need the second-order reverse pass, which is not built yet (DESIGN.md §9)")
+        if not set(self.target_str) <= set("efsm") or "e" not in self.target_str:
+            raise ValueError(f"Invalid targets={self.target_str!r}")
 
 
 def _all_reduce(t: Tensor, group) -> None:
@@ -56,55 +54,63 @@ def _all_reduce(t: Tensor, group) -> None:
         dist.all_reduce(t, group=group)
 
 
-def loss_and_seeds(K, cfg: LossConfig, e_pred: Tensor, e_target: Tensor, m_pred: Tensor | None,
-                   m_target: Tensor | None, group=None) -> tuple[dict, Tensor, Tensor | None]:
+def loss_and_seeds(K, cfg: LossConfig, preds: dict[str, Tensor], targets: dict[str, Tensor], group=None) -> tuple[dict, dict]:
     """CombinedLoss (trainer.py:779-869) on the device.
 
-    Returns (report, dL/de [B], dL/dm [N] | None); ``report`` holds python floats: loss, e_MAE,
-    e_MAE_size, (m_MAE, m_MAE_size).  NaN targets are missing labels.  With an initialised process
-    group the means are over the global batch.
+    ``preds`` / ``targets``: flat-able tensors per key of ``cfg.target_str`` (e [B], f [N,3], s [B,3,3],
+    m [N]); NaN targets are missing labels.  Returns (report, seeds): ``report`` holds python floats
+    (loss, X_MAE, X_MAE_size per term), ``seeds[key]`` = d loss / d preds[key].  With an initialised
+    process group the means are over the global batch.
     """
     kind = _KIND[cfg.criterion]
-    dev = e_pred.device
-    sums = torch.zeros(2, 3, dtype=torch.float64, device=dev)
-    g_e = torch.empty_like(e_pred)
-    K.loss_terms(e_pred.contiguous(), e_target.contiguous(), kind, cfg.delta, g_e, sums[0])
-    use_m = "m" in cfg.target_str and m_pred is not None and m_target is not None
-    g_m = None
-    if use_m:
-        g_m = torch.empty_like(m_pred)
-        K.loss_terms(m_pred.contiguous(), m_target.contiguous(), kind, cfg.delta, g_m, sums[1])
+    keys = [k for k in "efsm" if k in cfg.target_str and preds.get(k) is not None and targets.get(k) is not None]
+    ratio = {"e": cfg.energy_loss_ratio, "f": cfg.force_loss_ratio, "s": cfg.stress_loss_ratio, "m": cfg.mag_loss_ratio}
+    dev = preds["e"].device
+    sums = torch.zeros(len(keys), 3, dtype=torch.float64, device=dev)
+    raw = {}
+    for i, k in enumerate(keys):
+        p = preds[k].contiguous()
+        raw[k] = torch.empty_like(p)
+        K.loss_terms(p.view(-1), targets[k].to(p.dtype).contiguous().view(-1), kind, cfg.delta, raw[k].view(-1), sums[i])
     _all_reduce(sums, group)
     cnt = sums[:, 2].clamp_min(1.0)
-    g_e = g_e * (cfg.energy_loss_ratio / cnt[0]).to(g_e.dtype)
-    if use_m:
-        g_m = g_m * (cfg.mag_loss_ratio / cnt[1]).to(g_m.dtype)
+    seeds = {k: raw[k] * (ratio[k] / cnt[i]).to(raw[k].dtype) for i, k in enumerate(keys)}
     host = sums.cpu()
-    n_e, n_m = max(float(host[0, 2]), 1.0), max(float(host[1, 2]), 1.0)
-    report = {"loss": cfg.energy_loss_ratio * float(host[0, 0]) / n_e, "e_MAE": float(host[0, 1]) / n_e,
-              "e_MAE_size": int(host[0, 2])}
-    if "m" in cfg.target_str:
-        report["m_MAE"], report["m_MAE_size"] = float(host[1, 1]) / n_m, int(host[1, 2])
-        report["loss"] += cfg.mag_loss_ratio * float(host[1, 0]) / n_m
-    return report, g_e, g_m
+    report = {"loss": 0.0}
+    for i, k in enumerate(keys):
+        n = max(float(host[i, 2]), 1.0)
+        report["loss"] += ratio[k] * float(host[i, 0]) / n
+        report[f"{k}_MAE"], report[f"{k}_MAE_size"] = float(host[i, 1]) / n, int(host[i, 2])
+    return report, seeds
 
 
-def loss_and_grads(engine, batch, cfg: LossConfig, e_target: Tensor, m_target: Tensor | None,
-                   is_intensive: bool = True, group=None) -> tuple[dict, dict]:
-    """One forward + loss + training reverse pass on an already built batch.
+def loss_and_grads(engine, batch, cfg: LossConfig, targets: dict[str, Tensor], is_intensive: bool = True,
+                   group=None) -> tuple[dict, dict]:
+    """One forward (+ force pass) + loss + training reverse pass on an already built batch.
 
-    Returns (report, packed-layout gradients of THIS rank's graphs under the global-batch loss);
-    sum the gradients over ranks to get the global gradient.
+    ``targets``: e [B] (per atom if ``is_intensive``), f [N,3], s [B,3,3] (GPa), m [N], as far as
+    ``cfg.target_str`` asks.  Returns (report, packed-layout gradients of THIS rank's graphs under the
+    global-batch loss); sum the gradients over ranks to get the global gradient.
     """
+    from chgnet_b200.engine import EV_A3_TO_GPA
+
     K = engine.K
+    second = "f" in cfg.target_str or "s" in cfg.target_str
     out = engine.run(batch, need_grad=True, need_magmom="m" in cfg.target_str, train=True)
+    if second:
+        engine.input_grads(out, record=True)
     n = torch.tensor(batch.atoms_per_graph, device=out.energy.device, dtype=out.energy.dtype)
     total = out.energy + out.e_ref
-    e_pred = (total / n if is_intensive else total).to(out.site_e.dtype)
-    report, g_e, g_m = loss_and_seeds(K, cfg, e_pred, e_target.to(e_pred.dtype), out.magmom,
-                                      None if m_target is None else m_target.to(e_pred.dtype), group)
-    seed_e = g_e / n.to(g_e.dtype) if is_intensive else g_e
-    return report, engine.param_grads(out, seed_e.contiguous(), g_m)
+    dt = out.site_e.dtype
+    preds = {"e": (total / n if is_intensive else total).to(dt), "m": out.magmom}
+    if "f" in cfg.target_str:
+        preds["f"] = out.force.to(dt)
+    if "s" in cfg.target_str:
+        scale = EV_A3_TO_GPA / batch.volume.to(torch.float64)
+        preds["s"] = (out.virial.view(-1, 3, 3) * scale[:, None, None]).to(dt)
+    report, seeds = loss_and_seeds(K, cfg, preds, targets, group)
+    seed_e = seeds["e"] / n.to(dt) if is_intensive else seeds["e"]
+    return report, engine.param_grads(out, seed_e.contiguous(), seeds.get("m"), seeds.get("f"), seeds.get("s"))
 
 
 class Trainer:
@@ -150,15 +156,22 @@ class Trainer:
         model.mark_params_updated()
 
     # ------------------------------------------------------------------
-    def _targets(self, targets: dict, n_list: Sequence[int], device) -> tuple[Tensor, Tensor | None]:
-        e_t = torch.as_tensor(targets["e"], dtype=torch.float32).reshape(-1).to(device)
-        m_t = None
+    def _targets(self, targets: dict, n_list: Sequence[int], device) -> dict[str, Tensor]:
+        """reference label layout (dataset.py:763-788: e [B], f / m lists per graph, s list of [3,3]) ->
+        flat device tensors; None / NaN = missing labels (trainer.py:846-851)"""
+        def per_graph(vals, shape_of):
+            parts = [torch.full(shape_of(n), float("nan")) if v is None else torch.as_tensor(v, dtype=torch.float32).reshape(shape_of(n))
+                     for n, v in zip(n_list, vals)]
+            return torch.cat(parts).to(device)
+
+        out = {"e": torch.as_tensor(targets["e"], dtype=torch.float32).reshape(-1).to(device)}
+        if "f" in self.cfg.target_str:
+            out["f"] = per_graph(targets["f"], lambda n: (n, 3))
+        if "s" in self.cfg.target_str:
+            out["s"] = per_graph(targets["s"], lambda n: (1, 3, 3))
         if "m" in self.cfg.target_str:
-            parts = []
-            for n, m in zip(n_list, targets["m"]):  # None / NaN = missing labels (trainer.py:846-851)
-                parts.append(torch.full((n,), float("nan")) if m is None else torch.as_tensor(m, dtype=torch.float32).reshape(-1))
-            m_t = torch.cat(parts).to(device)
-        return e_t, m_t
+            out["m"] = per_graph(targets["m"], lambda n: (n,))
+        return out
 
     def flatten_grads(self, grads: dict[str, Tensor]) -> Tensor:
         for name, o, sz in zip(self.names, self.offsets, self.sizes):
@@ -177,8 +190,8 @@ class Trainer:
         engine = model._get_engine()
         compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
         batch = build_batch(graphs, model.device, with_reverse=True, compact_bonds=compact)
-        e_t, m_t = self._targets(targets, batch.atoms_per_graph, model.device)
-        report, G = loss_and_grads(engine, batch, self.cfg, e_t, m_t, model.is_intensive, self.group)
+        tg = self._targets(targets, batch.atoms_per_graph, model.device)
+        report, G = loss_and_grads(engine, batch, self.cfg, tg, model.is_intensive, self.group)
         flat_grad = self.flatten_grads(unpack_grads(G, model.state_dict()))
         _all_reduce(flat_grad, self.group)  # the one collective of the step
         self.step_count += 1

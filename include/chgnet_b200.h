@@ -194,7 +194,8 @@ int chg_force_virial(const float* rvec, const float* dist, const float* rhat,
  * ldx / ldg / ldo are row strides in floats (column-slice views are allowed).  Deterministic:
  * per-CTA partials in `workspace` (>= chg_wgrad_workspace_floats(n_out) floats), summed in fp64. */
 int64_t chg_wgrad_workspace_floats(int32_t n_out);
-int chg_wgrad(const float* x, int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
+int chg_wgrad(const float* x, const float* x2 /* non-NULL: act = silu'(x) * x2 (tangent of the hidden layer) */,
+              int32_t ldx, const int32_t* x_rows, int32_t x_silu, const float* g,
               int32_t ldg, const int32_t* g_rows, int32_t m, int32_t n_out, float* out, int32_t ldo,
               float* colsum, float* workspace, void* stream);
 /* out[c] += sum_r a[r][c] * (bmul ? bmul[r][c] : 1) * (rowscale ? rowscale[r] : 1), n in {64,128,256} */
@@ -218,6 +219,72 @@ int chg_loss_terms(const float* pred, const float* target, int32_t n, int32_t ki
 /* torch.optim.Adam (trainer.py:178-189) on one flat fp32 buffer; step counts from 1               */
 int chg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
+/* ======================= second order: losses on forces and stresses =======================
+ * F = -dE/dcart and sigma = (c/V) dE/d(strain) come from the reverse pass, so their parameter
+ * gradient is d/dtheta of  T = sum_e <dE/dr_e, rdot_e>  with the loss-weighted direction
+ * rdot_e = -(gF[c] - gF[n]) + r_e . (gS c/V) held fixed (reference model.py:518-535 create_graph=True,
+ * trainer.py:409).  T is evaluated by a TANGENT pass along rdot (the *_tan / *_tangent kernels mirror
+ * the forward kernels), then one more reverse pass over (primal, tangent) (the *_bwd2 kernels) gives
+ * dT/dtheta together with the energy / magmom part of the loss.  "lam" arguments are adjoints
+ * dE/d(.) recorded by the force pass; "bar" arguments are the adjoints of the primal intermediates in
+ * this second reverse pass.                                                                        */
+int chg_edge_tangent(const float* rvec, const float* dist, const float* rhat, const int32_t* center,
+                     const int32_t* nbr, const int32_t* atom_owner, const float* u_atom /* [N][3] */,
+                     const float* w_graph /* [B][9] */, int32_t n_edges, float* ddist, float* drhat,
+                     void* stream);
+/* tangent of K1b along ddist; tbasis [Eu][64] = (dB/dd ddist) for the ag | bg bases              */
+int chg_bond_basis_tangent(const float* dist, const float* ddist, const int32_t* u2d, int32_t n_bonds,
+                           const float* freq_ag, const float* freq_bg, int32_t n_radial, float rc_ag,
+                           float rc_bg, int32_t p, const float* w3t, float* e0d, float* wagd, float* wbgd,
+                           float* tbasis, void* stream);
+/* g_freq [2][n_radial] += d/dfreq < lam, (dB/dd ddist) W >                                          */
+int chg_bond_basis_bwd2(const float* dist, const float* ddist, const int32_t* u2d, int32_t n_bonds,
+                        const float* freq_ag, const float* freq_bg, int32_t n_radial, float rc_ag,
+                        float rc_bg, int32_t p, const float* w3, const float* lam_e0, const float* lam_wag,
+                        const float* lam_wbg, double* g_freq, void* stream);
+int chg_angle_basis_tangent(const float* rhat, const float* drhat, const int32_t* ang_di,
+                            const int32_t* ang_dj, int32_t n_angles, const float* freq, int32_t n_freq,
+                            const float* wt, float* a0d, float* tbasis, void* stream);
+int chg_angle_basis_bwd2(const float* rhat, const float* drhat, const int32_t* ang_di, const int32_t* ang_dj,
+                         int32_t n_angles, const float* freq, int32_t n_freq, const float* w,
+                         const float* lam_a0, double* g_freq, void* stream);
+/* tangent of K4: msg' = o' wag[u] + o wag'[u]; also returns pre' and p' [Ed][128] for the reverse    */
+int chg_atom_conv_tan(const float* pcn_d, const float* pe_d, const float* wag, const float* wag_d,
+                      const int32_t* center, const int32_t* nbr, const int32_t* d2u, int32_t n_edges,
+                      const float* save_pre, const float* save_p, const float* w2t, const float* ln,
+                      float* msg_d, float* pre_d, float* p_d, void* stream);
+/* reverse of (K4, its tangent): bar_pre = adjoint of pre, bar_w [Ed][64] = adjoint of the wag rows,
+ * u_out [Ed][128] = adjoint of p (for the second-layer weight gradient), g_ln accumulated        */
+int chg_atom_conv_bwd2(const float* save_pre, const float* save_p, const float* pre_d, const float* p_d,
+                       const float* g_p_lam, const float* wag, const float* wag_d, const int32_t* center,
+                       const int32_t* d2u, int32_t n_edges, const float* lam_agg, const float* bar_agg,
+                       const float* w2, const float* ln, float* bar_pre, float* bar_w, float* u_out,
+                       double* g_ln, void* stream);
+int chg_bond_conv_tan(const float* pij_d, const float* px_d, const float* pa_d, const float* wbg,
+                      const float* wbg_d, const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                      int32_t n_angles, const float* save_pre, const float* save_p, const float* w2t,
+                      const float* ln, float* upd_d, float* pre_d, float* p_d, void* stream);
+int chg_bond_conv_bwd2(const float* save_pre, const float* save_p, const float* pre_d, const float* p_d,
+                       const float* g_p_lam, const float* wbg, const float* wbg_d, const int32_t* ang_i,
+                       const int32_t* ang_j, int32_t n_angles, const float* lam_agg, const float* bar_agg,
+                       const float* w2, const float* ln, float* bar_pre, float* bar_wi, float* bar_wj,
+                       float* u_out, double* g_ln, void* stream);
+int chg_angle_update_tan(const float* pij_d, const float* px_d, const float* pa_d, const float* ang_d,
+                         const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                         int32_t n_angles, const float* save_p, const float* ln, float* ang_new_d, float* p_d,
+                         void* stream);
+/* lam_ang / bar_ang: adjoints of ang_new (NULL = zero)                                              */
+int chg_angle_update_bwd2(const float* save_p, const float* p_d, const float* lam_ang, const float* bar_ang,
+                          int32_t n_angles, const float* ln, float* bar_pre, double* g_ln, void* stream);
+/* reverse of (readout, its tangent along xd) for  sum_i seed_i site_e_i + <d site_e_i/dx_i, xd_i>:
+ * bar_x = adjoint of x; h_all / hd_all [n_hidden+1][N][64] inputs of every linear and their tangents;
+ * gz_all / zbar_all [n_hidden][N][64] adjoints of the tangent / primal pre-activations; g_h0 / hbar0
+ * adjoints of the tangent / primal LayerNorm output; xhat, xhatd                                      */
+int chg_readout_bwd2(const float* x, const float* xd, int32_t n_atoms, const float* ln, const float* mlp_wt,
+                     const float* mlp_w, const float* mlp_b, int32_t n_hidden, const float* w_last,
+                     const float* seed, float* bar_x, float* h_all, float* hd_all, float* gz_all,
+                     float* zbar_all, float* g_h0, float* hbar0, float* xhat, float* xhatd, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,8 +33,24 @@ OUT_ARGS = {
     "colsum": [1],
     "readout_bwd": [7, 8, 9, 10, 11],
     "magmom_bwd": [4, 5],
+    # second order
+    "edge_tangent": [8, 9],
+    "bond_basis_tangent": [9, 10, 11, 12],
+    "bond_basis_bwd2": [12],
+    "angle_basis_tangent": [6, 7],
+    "angle_basis_bwd2": [7],
+    "atom_conv_tan": [11, 12, 13],
+    "atom_conv_bwd2": [13, 14, 15, 16],
+    "bond_conv_tan": [12, 13, 14],
+    "bond_conv_bwd2": [13, 14, 15, 16, 17],
+    "angle_update_tan": [9, 10],
+    "angle_update_bwd2": [5, 6],
+    "readout_bwd2": [8, 9, 10, 11, 12, 13, 14, 15, 16],
 }
-TRAIN_KERNELS = {"wgrad", "colsum", "readout_bwd", "magmom_bwd"}
+SECOND_ORDER_KERNELS = {"edge_tangent", "bond_basis_tangent", "bond_basis_bwd2", "angle_basis_tangent", "angle_basis_bwd2",
+                        "atom_conv_tan", "atom_conv_bwd2", "bond_conv_tan", "bond_conv_bwd2", "angle_update_tan",
+                        "angle_update_bwd2", "readout_bwd2"}
+TRAIN_KERNELS = {"wgrad", "colsum", "readout_bwd", "magmom_bwd"} | SECOND_ORDER_KERNELS
 INFER_KERNELS = set(OUT_ARGS) - TRAIN_KERNELS
 
 

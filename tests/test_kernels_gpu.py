@@ -79,6 +79,11 @@ def test_every_training_kernel_matches_its_spec(weights030):
     gen = torch.Generator().manual_seed(11)
     n_atoms = sum(g.atomic_number.shape[0] for g in graphs)
     eng.param_grads(out, torch.randn(len(graphs), generator=gen), torch.randn(n_atoms, generator=gen))
+    # and a step with force / stress seeds: the second-order kernels
+    out = eng.run(build_batch(graphs, "cpu"), need_grad=True, need_magmom=True, train=True)
+    eng.input_grads(out, record=True)
+    eng.param_grads(out, torch.randn(len(graphs), generator=gen), torch.randn(n_atoms, generator=gen),
+                    torch.randn(n_atoms, 3, generator=gen), torch.randn(len(graphs), 3, 3, generator=gen))
     K = CudaKernels()
     seen = {}
     for name, snap, outs in rec.calls:

@@ -115,8 +115,8 @@ def test_trainer_step_matches_reference_loss_and_torch_adam(weights030):
     slow = Trainer(_new_model(), targets="em", criterion="Huber", learning_rate=1e-5)
     losses = [slow.train_step(graphs, {"e": e_t, "m": m_t})["loss"] for _ in range(8)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
-    with pytest.raises(NotImplementedError):
-        Trainer(model, targets="ef")
+    with pytest.raises(ValueError):
+        Trainer(model, targets="fx")
 
 
 def test_v020_shaped_architecture_parameter_gradients():
@@ -140,3 +140,68 @@ def test_v020_shaped_architecture_parameter_gradients():
     _, want = _oracle_grads(w, graphs, loss_fn, args=args)
     got = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
     print("worst relative gradient error:", _check(got, want, rtol=5e-3))
+
+
+def _oracle_grads_efsm(weights, graphs, loss_fn, args=None):
+    from oracle import chgnet_oracle as orc
+
+    P = {k: torch.as_tensor(np.asarray(v)).double().requires_grad_(k != "composition_model.fc.weight")
+         for k, v in weights.items()}
+    out = orc.forward(P, graphs, "efsm", dtype=torch.float64, train=True, args=args)
+    loss = loss_fn(out["e"], torch.cat(out["m"]), torch.cat(out["f"]), torch.stack(out["s"]))
+    names = [k for k, v in P.items() if v.requires_grad]
+    gr = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+    return float(loss.detach()), {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(names, gr)}
+
+
+def test_force_and_stress_losses_backpropagate_through_the_second_order_pass(weights030):
+    """loss on e, f, s, m through CHGNet.forward in training mode == autograd's double backward (fp64)."""
+    model = _new_model()
+    model.train()
+    graphs = graphgen.random_graphs(4, 10, 18, 8700)
+    gen = torch.Generator().manual_seed(4)
+    n_atoms = sum(g.atomic_number.shape[0] for g in graphs)
+    cf = torch.randn(n_atoms, 3, generator=gen, dtype=torch.float64)
+    cs = torch.randn(len(graphs), 3, 3, generator=gen, dtype=torch.float64)
+
+    def loss_fn(e, m, f, s):
+        d = dict(device=e.device, dtype=e.dtype)
+        return (e**2).sum() + 0.1 * (m**2).sum() + ((f - 0.05 * cf.to(**d)) ** 2).mean() + 0.1 * ((s - 0.1 * cs.to(**d)) ** 2).mean()
+
+    pred = model(graphs, task="efsm")
+    assert pred["f"][0].requires_grad and pred["s"][0].requires_grad
+    loss = loss_fn(pred["e"], torch.cat(pred["m"]), torch.cat(pred["f"]), torch.stack(pred["s"]))
+    loss.backward()
+    want_loss, want = _oracle_grads_efsm(weights030, graphs, loss_fn)
+    assert float(loss) == pytest.approx(want_loss, rel=1e-3)
+    got = {n: p.grad for n, p in model.named_parameters() if p.requires_grad}
+    print("worst relative gradient error:", _check(got, want, rtol=1e-2))
+
+
+def test_trainer_efsm_step_matches_reference_combined_loss(weights030):
+    from chgnet_b200.trainer import Trainer
+
+    model = _new_model()
+    graphs = graphgen.random_graphs(5, 10, 18, 8800)
+    gen = torch.Generator().manual_seed(6)
+    base = model.predict_graph(graphs, task="efsm", batch_size=5)
+    noisy = lambda v, a: torch.as_tensor(np.asarray(v), dtype=torch.float32) + a * torch.randn(np.asarray(v).shape, generator=gen)  # noqa: E731
+    lab = {"e": noisy([float(p["e"]) for p in base], 0.05), "f": [noisy(p["f"], 0.02) for p in base],
+           "s": [noisy(p["s"], 0.05) for p in base], "m": [noisy(p["m"], 0.05) for p in base]}
+    lab["m"][3] = None
+    crit = torch.nn.MSELoss()
+
+    def loss_fn(e, m, f, s):
+        keep = torch.cat([torch.full((len(b["m"]),), t is not None) for b, t in zip(base, lab["m"])])
+        mt = torch.cat([t if t is not None else torch.zeros(len(b["m"])) for b, t in zip(base, lab["m"])]).double()
+        return (crit(lab["e"].double(), e) + crit(torch.cat(lab["f"]).double(), f)
+                + 0.1 * crit(torch.stack(lab["s"]).double(), s) + 0.1 * crit(mt[keep], m[keep]))
+
+    want_loss, want = _oracle_grads_efsm(weights030, graphs, loss_fn)
+    trainer = Trainer(model, targets="efsm", criterion="MSE", learning_rate=1e-5)
+    report = trainer.train_step(graphs, lab)
+    assert report["loss"] == pytest.approx(want_loss, rel=5e-3, abs=1e-7)
+    assert report["f_MAE_size"] == 3 * sum(len(b["m"]) for b in base) and report["s_MAE_size"] == 45
+    _check({n: g.clone() for n, g in trainer.grads_by_name().items()}, want, rtol=1e-2)
+    losses = [report["loss"]] + [trainer.train_step(graphs, lab)["loss"] for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses

@@ -94,7 +94,7 @@ def _rank_grads(weights, graphs, e_t, m_t, criterion, group=None):
     b.frac, b.lattice, b.image = b.frac.double(), b.lattice.double(), b.image.double()
     m_flat = torch.cat([torch.full((g.atomic_number.shape[0],), float("nan"), dtype=torch.float64) if m is None else m
                         for g, m in zip(graphs, m_t)])
-    report, G = loss_and_grads(eng, b, LossConfig("em", criterion), e_t, m_flat, True, group)
+    report, G = loss_and_grads(eng, b, LossConfig("em", criterion), {"e": e_t, "m": m_flat}, True, group)
     return report, unpack_grads(G, sd)
 
 
