@@ -201,6 +201,33 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
         if world > 1:
             dist.barrier()
         return
+    # breakdown of one resident step (synchronised, outside the timed loops)
+    from chgnet_b200.engine import EV_A3_TO_GPA
+    from chgnet_b200.trainer import loss_and_seeds
+
+    def tick():
+        torch.cuda.synchronize()
+        return time.perf_counter()
+
+    t0 = tick()
+    engine = model._get_engine()
+    t1 = tick()
+    o = engine.run(batch, need_grad=True, need_magmom=True, train=True)
+    t2 = tick()
+    engine.input_grads(o, record=True)
+    t3 = tick()
+    n_dev = torch.tensor(batch.atoms_per_graph, device=dev, dtype=torch.float64)
+    preds = {"e": ((o.energy + o.e_ref) / n_dev).float(), "m": o.magmom, "f": o.force.float(),
+             "s": (o.virial.view(-1, 3, 3) * (EV_A3_TO_GPA / batch.volume.double())[:, None, None]).float()}
+    rep_, seeds = loss_and_seeds(K, trainer.cfg, preds, tg_dev, None)
+    t4 = tick()
+    G = engine.param_grads(o, (seeds["e"] / n_dev.float()).contiguous(), seeds["m"], seeds["f"], seeds["s"])
+    t5 = tick()
+    fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
+    t6 = tick()
+    breakdown = {"repack_weights_ms": (t1 - t0) * 1e3, "forward_ms": (t2 - t1) * 1e3, "force_pass_ms": (t3 - t2) * 1e3,
+                 "loss_ms": (t4 - t3) * 1e3, "second_order_and_wgrads_ms": (t5 - t4) * 1e3,
+                 "unpack_flatten_grads_ms": (t6 - t5) * 1e3}
     peaks, peak_kind = measured_peaks()
     sc_ms, sc_bytes = time_scatter_kernel(K, batch)
     achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
@@ -229,7 +256,7 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "structures/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48, "api": "Trainer.train_step(list[CrystalGraph] on host, labels on host)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
-        "last_report": rep_last, "kernel_shares": shares}), flush=True)
+        "last_report": rep_last, "breakdown": breakdown, "kernel_shares": shares}), flush=True)
     if world > 1:
         dist.barrier()
 

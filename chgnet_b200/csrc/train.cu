@@ -107,21 +107,36 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ x2, int ldx,
     stg4(cs_partial + (size_t)blockIdx.x * n + col_base + n0, make_float4(cs[0], cs[1], cs[2], cs[3]));
 }
 
-// second pass: sum the per-chunk partials in fp64 (fixed order -> deterministic)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ cs_partial,
-                                    int n_chunks, int n, float* __restrict__ out, int ldo,
-                                    float* __restrict__ colsum) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// second pass: sum the per-chunk partials in fp64 (fixed order -> deterministic).
+// A block owns 32 consecutive outputs; its 8 chunk-lanes each sum every 8th chunk with independent
+// loads in flight, then combine through shared memory.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ cs_partial, int n_chunks, int n,
+                    float* __restrict__ out, int ldo, float* __restrict__ colsum) {
+  __shared__ double s_red[8][32];
+  const int o = threadIdx.x & 31, cl = threadIdx.x >> 5;
   const int n_w = 64 * n;
-  if (idx < n_w) {
-    double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c) s += (double)partial[(size_t)c * n_w + idx];
-    out[(size_t)(idx / n) * ldo + (idx % n)] = (float)s;
-  } else if (colsum != nullptr && idx < n_w + n) {
-    const int j = idx - n_w;
-    double s = 0.0;
-    for (int c = 0; c < n_chunks; ++c) s += (double)cs_partial[(size_t)c * n + j];
-    colsum[j] = (float)s;
+  const int idx = blockIdx.x * 32 + o;  // [0, n_w) weights, [n_w, n_w + n) column sums
+  const bool is_w = idx < n_w, is_c = !is_w && colsum != nullptr && idx < n_w + n;
+  const float* src = is_w ? partial + idx : (is_c ? cs_partial + (idx - n_w) : nullptr);
+  const size_t stride = is_w ? (size_t)n_w : (size_t)n;
+  double s = 0.0;
+  if (src != nullptr) {
+    int c = cl;
+    for (; c + 24 < n_chunks; c += 32) {
+      const float v0 = src[(size_t)c * stride], v1 = src[(size_t)(c + 8) * stride];
+      const float v2 = src[(size_t)(c + 16) * stride], v3 = src[(size_t)(c + 24) * stride];
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; c < n_chunks; c += 8) s += (double)src[(size_t)c * stride];
+  }
+  s_red[cl][o] = s;
+  __syncthreads();
+  if (cl == 0 && src != nullptr) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += s_red[q][o];
+    if (is_w) out[(size_t)(idx / n) * ldo + (idx % n)] = (float)s;
+    else colsum[idx - n_w] = (float)s;
   }
 }
 
@@ -134,13 +149,19 @@ colsum_kernel(const float* __restrict__ a, int lda, const float* __restrict__ bm
   const int c = tid % n, rl = tid / n, lanes = 256 / n;
   const int rows_per_cta = (m + gridDim.x - 1) / gridDim.x;
   const int r_beg = blockIdx.x * rows_per_cta, r_end = min(r_beg + rows_per_cta, m);
-  double s = 0.0;
-  for (int r = r_beg + rl; r < r_end; r += lanes) {
+  auto term = [&](int r) {
     float v = a[(size_t)r * lda + c];
     if (bmul != nullptr) v *= bmul[(size_t)r * ldb + c];
     if (rowscale != nullptr) v *= rowscale[r];
-    s += (double)v;
+    return v;
+  };
+  double s = 0.0;
+  int r = r_beg + rl;
+  for (; r + 3 * lanes < r_end; r += 4 * lanes) {  // four independent loads in flight
+    const float v0 = term(r), v1 = term(r + lanes), v2 = term(r + 2 * lanes), v3 = term(r + 3 * lanes);
+    s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
   }
+  for (; r < r_end; r += lanes) s += (double)term(r);
   s_red[tid] = s;
   __syncthreads();
   if (rl == 0) {
@@ -497,8 +518,8 @@ extern "C" int chg_wgrad(const float* x, const float* x2, int32_t ldx, const int
     count_launch();
   }
   const int total = 64 * n_out + n_out;
-  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(partial, cs_partial, n_chunks, n_out, out, ldo,
-                                                                        colsum);
+  wgrad_reduce_kernel<<<(total + 31) / 32, 256, 0, as_stream(stream)>>>(partial, cs_partial, n_chunks, n_out, out, ldo,
+                                                                      colsum);
   CHG_LAUNCH_END();
 }
 
@@ -508,7 +529,7 @@ extern "C" int chg_colsum(const float* a, int32_t lda, const float* bmul, int32_
   CHG_CHECK_ARG(n == 64 || n == 128 || n == 256, "n must be 64, 128 or 256");
   if (m == 0) return CHG_OK;
   CHG_CHECK_ARG(a && out, "null pointer");
-  const int blocks = max(1, min((m + 63) / 64, sm_count() * 2));
+  const int blocks = max(1, min((m + 63) / 64, sm_count() * 8));
   colsum_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, lda, bmul, ldb, rowscale, m, n, out);
   CHG_LAUNCH_END();
 }

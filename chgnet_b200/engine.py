@@ -396,8 +396,8 @@ class Engine:
             K.segment_sum(bar_pre, b.perm_n, b.ptr_n, 0, sp[:, 128:])
             spe = self._seg(b, bar_pre, b.perm_u, b.ptr_u, Eu)
             G[f"atom.{t}.wcn_t"] = wsum(sv["x"], sp, 256, tt["x_d"], la["sp"])
-            G[f"atom.{t}.we_t"] = wsum(sv["e"], spe, 128, tt["e_d"], la["spe"])
-            G[f"atom.{t}.b1"] = self._colsum(b, spe)
+            we_bar, G[f"atom.{t}.b1"] = self._wgrad(b, sv["e"], spe, 128, colsum=True)
+            G[f"atom.{t}.we_t"] = we_bar + self._wgrad(b, tt["e_d"], la["spe"], 128)
             K.segment_sum(bar_w, b.perm_u, b.ptr_u, 1, bar_wag)
             return acc(bar_xout, sp, gp.extra["wcn_b"]), acc(bar_e, spe, gp.extra["we_b"])
 
@@ -411,8 +411,8 @@ class Engine:
             spx = self._seg(b, bar_pre, b.perm_x, b.ptr_x, N)
             G[f"{key}.wij_t"] = wsum(sv["e"], sp, 256, tt["e_d"], la["sp"], x_rows=sid)
             G[f"{key}.wx_t"] = wsum(sv["x"], spx, 128, tt["x_d"], la["spx"])
-            G[f"{key}.w1a_t"] = wsum(sv["ang"], bar_pre, 128, tt["ang_d"], la["g_pre"])
-            G[f"{key}.b1"] = self._colsum(b, bar_pre)
+            w1a_bar, G[f"{key}.b1"] = self._wgrad(b, sv["ang"], bar_pre, 128, colsum=True)
+            G[f"{key}.w1a_t"] = w1a_bar + self._wgrad(b, tt["ang_d"], la["g_pre"], 128)
             return acc(bar_x, spx, ex["wx_b"]), bar_e
 
         bar_x, bar_e = atom_bwd2(n_conv - 1, bar_x, None)

@@ -9,7 +9,7 @@ for wl in c2 c4 c5; do
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_${wl}_${TAG}.json").read().strip().splitlines()[-1])
-print("${wl}", d["metric"], round(d["value"],1), "struct/s", round(d["ms_per_step"],3), "ms | e2e", round(d["e2e"]["value"],1), round(d["e2e"]["ms_per_step"],2), "ms | launches", d["gpu_launches"], "| roofline", d["roofline"]["frac"], d.get("last_report"))
+print("${wl}", d["metric"], round(d["value"],1), "struct/s", round(d["ms_per_step"],3), "ms | e2e", round(d["e2e"]["value"],1), round(d["e2e"]["ms_per_step"],2), "ms | launches", d["gpu_launches"], "| roofline", d["roofline"]["frac"], d.get("last_report"), d.get("breakdown"))
 for k,v in list(d["kernel_shares"].items())[:10]: print("   ",k,v)
 PY
 done
