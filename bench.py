@@ -219,7 +219,7 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
     n_dev = torch.tensor(batch.atoms_per_graph, device=dev, dtype=torch.float64)
     preds = {"e": ((o.energy + o.e_ref) / n_dev).float(), "m": o.magmom, "f": o.force.float(),
              "s": (o.virial.view(-1, 3, 3) * (EV_A3_TO_GPA / batch.volume.double())[:, None, None]).float()}
-    rep_, seeds = loss_and_seeds(K, trainer.cfg, preds, tg_dev, None)
+    rep_, seeds = loss_and_seeds(K, trainer.cfg, preds, tg_dev, False)  # rank 0 only: no collective here
     t4 = tick()
     G = engine.param_grads(o, (seeds["e"] / n_dev.float()).contiguous(), seeds["m"], seeds["f"], seeds["s"])
     t5 = tick()

@@ -48,8 +48,11 @@ class LossConfig:
 
 
 def _all_reduce(t: Tensor, group) -> None:
+    """SUM over the ranks of ``group`` (None = default group; False = this rank only)."""
     import torch.distributed as dist
 
+    if group is False:
+        return
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, group=group)
 
