@@ -279,7 +279,7 @@ struct Bwd2Smem {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(NTHR, 1) gated_bwd2_kernel(const Bwd2Args a) {
+__global__ void __launch_bounds__(NTHR, 2) gated_bwd2_kernel(const Bwd2Args a) {
   using L = Bwd2Smem<MODE>;
   extern __shared__ __align__(16) float smem[];
   float* s_w2 = smem + L::W2_OFF;   // [128][64]

@@ -111,8 +111,8 @@ def random_weights(seed: int = 0, args: dict | None = None) -> dict[str, np.ndar
     return w
 
 
-def _t(w: dict, dtype) -> dict[str, Tensor]:
-    return {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in w.items()}
+def _t(w: dict, dtype, device=None) -> dict[str, Tensor]:
+    return {k: torch.as_tensor(np.asarray(v)).to(device=device, dtype=dtype) for k, v in w.items()}
 
 
 # --------------------------------------------------------------------------
@@ -136,7 +136,7 @@ def radial_bessel(d: Tensor, freq: Tensor, cutoff: float, p: int) -> Tensor:
 def fourier(theta: Tensor, freq: Tensor) -> Tensor:
     """[1/sqrt2, sin(w th), cos(w th)]/sqrt(pi)  (reference basis.py:33-40)."""
     arg = theta[:, None] * freq[None, :]
-    const = torch.full((theta.shape[0], 1), 1.0 / math.sqrt(2.0), dtype=theta.dtype)
+    const = torch.full((theta.shape[0], 1), 1.0 / math.sqrt(2.0), dtype=theta.dtype, device=theta.device)
     return torch.cat([const, torch.sin(arg), torch.cos(arg)], dim=1) / math.sqrt(math.pi)
 
 
@@ -193,6 +193,7 @@ def forward(
     return_crystal_feas: bool = False,
     return_intermediates: bool = False,
     train: bool = False,
+    device=None,
 ) -> dict:
     """CHGNet.forward restated (reference model.py:330-542, 792-913).
 
@@ -204,7 +205,9 @@ def forward(
     s list[3,3] GPa, m list[n_i], atoms_per_graph, plus optional extras.
     """
     a = {**DEFAULT_ARGS, **(args or {})}
-    w = dict(weights) if train else _t(weights, dtype)
+    w = dict(weights) if train else _t(weights, dtype, device)
+    if device is not None:  # stock PyTorch on an accelerator: same ops, graph tensors moved like CrystalGraph.to()
+        graphs = [g.to(device) for g in graphs]
     R = a["num_radial"]
     p = int(a["cutoff_coeff"])
     n_conv = a["n_conv"]
@@ -218,8 +221,8 @@ def forward(
         n = g.atomic_number.shape[0]
         lat0 = g.lattice.detach().to(dtype)
         if want_s:  # model.py:826-830
-            strain = torch.zeros(3, 3, dtype=dtype, requires_grad=True)
-            lat = lat0 @ (torch.eye(3, dtype=dtype) + strain)
+            strain = torch.zeros(3, 3, dtype=dtype, device=lat0.device, requires_grad=True)
+            lat = lat0 @ (torch.eye(3, dtype=dtype, device=lat0.device) + strain)
         else:
             strain, lat = None, lat0
         vols.append(torch.dot(lat[0], torch.linalg.cross(lat[1], lat[2])))  # 834-836
@@ -247,7 +250,7 @@ def forward(
             bases_ang.append(fourier(torch.acos(cosij), w["angle_basis_expansion.fourier_expansion.frequencies"]))
             bg_list.append(torch.stack([bg[:, 0] + atom_off, bg[:, 1] + und_off, bg[:, 3] + und_off], dim=1))
         z_all.append(g.atomic_number.long())
-        owners.append(torch.full((n,), gi, dtype=torch.long))
+        owners.append(torch.full((n,), gi, dtype=torch.long, device=lat0.device))
         atom_off += n
         und_off += len(du)
 
@@ -314,7 +317,7 @@ def forward(
         idx += 2
     last = max(int(k.split(".")[2]) for k in w if k.startswith("mlp.layers.") and k.endswith(".weight"))
     site_e = linear(h, w, f"mlp.layers.{last}").view(-1)
-    energy = torch.zeros(B, dtype=dtype).index_add_(0, owners, site_e)
+    energy = torch.zeros(B, dtype=dtype, device=site_e.device).index_add_(0, owners, site_e)
     if return_crystal_feas:
         out["crystal_fea"] = scatter_sum(x, owners, B)
     if return_intermediates:

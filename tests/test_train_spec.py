@@ -199,3 +199,43 @@ def test_force_and_stress_loss_gradients_match_double_backward(weights030, compa
         # second derivatives near collinear angles amplify rounding (acos' ~ 1/sqrt(1-u^2) up to 700)
         assert err <= 1e-6 * scale, (k, err, scale)
     print("worst relative error", worst)
+
+
+def test_training_gradients_without_angles_and_with_isolated_atom(weights030):
+    """Empty bond graph (model.py:438, 460) + an atom without edges in the batch, targets "ef" (no magmom):
+    both the first-order and the second-order pass against autograd."""
+    g_noang = graphgen.make_crystal_graph([3, 8], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 5.5)
+    g_iso = graphgen.make_crystal_graph([3], np.zeros((1, 3)), np.eye(3) * 20.0)
+    graphs = [g_iso, g_noang]
+    assert len(g_noang.bond_graph) == 0 and len(g_iso.atom_graph) == 0
+    gen = torch.Generator().manual_seed(9)
+    ce = torch.randn(2, generator=gen, dtype=torch.float64)
+    cf = torch.randn(3, 3, generator=gen, dtype=torch.float64)
+    cs = torch.randn(2, 3, 3, generator=gen, dtype=torch.float64)
+    P = {k: torch.as_tensor(np.asarray(v)).double().requires_grad_(k != "composition_model.fc.weight")
+         for k, v in weights030.items()}
+    out = orc.forward(P, graphs, "efs", dtype=torch.float64, train=True)
+    n = out["atoms_per_graph"].double()
+    names = [k for k, v in P.items() if v.requires_grad]
+    loss1 = (out["e"] * n * ce).sum()
+    loss2 = loss1 + (torch.cat(out["f"]) * cf).sum() + (torch.stack(out["s"]) * cs).sum()
+    want1 = dict(zip(names, torch.autograd.grad(loss1, [P[k] for k in names], allow_unused=True, retain_graph=True)))
+    want2 = dict(zip(names, torch.autograd.grad(loss2, [P[k] for k in names], allow_unused=True)))
+
+    sd = {k: torch.as_tensor(np.asarray(v)).double() for k, v in weights030.items()}
+    eng = Engine(pack_weights(sd, None, device="cpu", dtype=torch.float64), SpecKernels())
+
+    def batch():
+        b = build_batch(graphs, "cpu")
+        b.frac, b.lattice, b.image = b.frac.double(), b.lattice.double(), b.image.double()
+        return b
+
+    o = eng.run(batch(), need_grad=True, train=True)
+    got1 = unpack_grads(eng.param_grads(o, ce), sd)
+    o = eng.run(batch(), need_grad=True, train=True)
+    eng.input_grads(o, record=True)
+    got2 = unpack_grads(eng.param_grads(o, ce, None, cf, cs), sd)
+    for want, got in ((want1, got1), (want2, got2)):
+        for k in names:
+            w = want[k] if want[k] is not None else torch.zeros_like(P[k])
+            assert float((got[k] - w).abs().max()) <= 1e-7 * max(float(w.abs().max()), 1.0), k
