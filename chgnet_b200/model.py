@@ -280,6 +280,8 @@ class CHGNet(nn.Module):
                            as_buffer=(not learnable_rbf and name.endswith("frequencies")))
         self._engine: Engine | None = None
         self._engine_key: tuple | None = None
+        self._native = None  # native.NativeForward (inference)
+        self._native_key: tuple | None = None
         self.last_batch: DeviceBatch | None = None
         version_str = f" v{version}" if version else ""
         print(f"CHGNet{version_str} initialized with {self.n_params:,} parameters")
@@ -309,6 +311,16 @@ class CHGNet(nn.Module):
     def device(self) -> torch.device:
         return next(self.parameters()).device
 
+    def _get_engine_checks(self) -> None:
+        a = self._arch
+        for name in ("atom_conv_hidden_dim", "bond_conv_hidden_dim"):
+            if a[name] != 64 and list(np.atleast_1d(a[name])) != [64]:
+                raise NotImplementedError(f"{name} must be 64 for the CUDA kernels")
+        if a["angle_layer_hidden_dim"] not in (0, None):
+            raise NotImplementedError("angle_layer_hidden_dim must be 0 for the CUDA kernels")
+        if a["conv_norm"] is not None:
+            raise NotImplementedError("conv_norm is not supported by the CUDA kernels")
+
     def _get_engine(self) -> Engine:
         dev = self.device
         if dev.type != "cuda":
@@ -320,38 +332,64 @@ class CHGNet(nn.Module):
         if self._engine is None or key != self._engine_key:
             from chgnet_b200._lib import CudaKernels
 
-            a = self._arch
-            for name in ("atom_conv_hidden_dim", "bond_conv_hidden_dim"):
-                if a[name] != 64 and list(np.atleast_1d(a[name])) != [64]:
-                    raise NotImplementedError(f"{name} must be 64 for the CUDA kernels")
-            if a["angle_layer_hidden_dim"] not in (0, None):
-                raise NotImplementedError("angle_layer_hidden_dim must be 0 for the CUDA kernels")
-            if a["conv_norm"] is not None:
-                raise NotImplementedError("conv_norm is not supported by the CUDA kernels")
+            self._get_engine_checks()
             pw = pack_weights(sd, self.model_args, device=dev)
             self._engine = Engine(pw, CudaKernels())
             self._engine_key = key
         return self._engine
 
+    def _get_native(self):
+        """Inference path: packed weights on the device + ONE ``chg_forward`` call per batch (native.py)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "chgnet_b200.CHGNet has no CPU path: move the model to a CUDA device (B200) first "
+                f"(parameters are on {dev})")
+        sd = self.state_dict()
+        key = (str(dev), tuple(int(v._version) for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
+        if self._native is None or key != self._native_key:
+            from chgnet_b200.native import NativeForward
+
+            self._get_engine_checks()
+            self._native = NativeForward(sd, self.model_args, dev)
+            self._native_key = key
+        return self._native
+
     def mark_params_updated(self) -> None:
         """Call after changing parameter storage in place from outside autograd (e.g. the fused Adam
         kernel): the packed kernel weights are rebuilt on the next forward."""
         self._engine_key = None
+        self._native_key = None
 
     # ------------------------------------------------------------------ forward
     def _run(self, graphs, task, return_site_energies, return_atom_feas, return_crystal_feas,
              train: bool = False) -> dict[str, Any]:
-        """One batch through the kernel engine; returns BATCHED device tensors."""
-        engine = self._get_engine()
+        """One batch through the kernels; returns BATCHED device tensors.
+
+        Inference = one native ``chg_forward`` call (native.py; ``CHGNET_B200_ENGINE=python`` selects the
+        call-by-call Python schedule of engine.py instead, same kernels); training = engine.py."""
         need_grad = "f" in task or "s" in task
         # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
-        compact = not any(gp.extra["bo"] is not None for gp in engine.pw.bond)
+        compact = not self._arch.get("mlp_out_bias", False)
         batch = build_batch(graphs, self.device, with_reverse=need_grad or train, compact_bonds=compact)
         self.last_batch = batch
-        out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
-                         need_crystal_fea=return_crystal_feas, train=train)
-        if train and need_grad:  # force pass; keeps the adjoints the second-order pass needs
-            engine.input_grads(out, record=True)
+        if not train and os.environ.get("CHGNET_B200_ENGINE", "native") != "python":
+            nat = self._get_native()
+            res = nat(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
+                      need_crystal_fea=return_crystal_feas)
+            from chgnet_b200.engine import EngineOutput
+
+            out = EngineOutput(energy=res["energy"], e_ref=res["e_ref"], site_e=res["site_e"], magmom=res.get("magmom"),
+                               atom_fea=res.get("atom_fea"), crystal_fea=res.get("crystal_fea"), force=res.get("force"),
+                               virial=res.get("virial"))
+            atom_ref = nat.atom_ref
+        else:
+            engine = self._get_engine()
+            out = engine.run(batch, need_grad=need_grad, need_magmom="m" in task, need_atom_fea=return_atom_feas,
+                             need_crystal_fea=return_crystal_feas, train=train)
+            if train and need_grad:  # force pass; keeps the adjoints the second-order pass needs
+                engine.input_grads(out, record=True)
+            atom_ref = engine.pw.atom_ref
         self._last_out = out
         n_dev = torch.tensor(batch.atoms_per_graph, device=self.device)
         raw: dict[str, Any] = {"atoms_per_graph": n_dev}
@@ -360,7 +398,7 @@ class CHGNet(nn.Module):
         if "m" in task:
             raw["m"] = out.magmom
         if return_site_energies:
-            raw["site_energies"] = out.site_e + engine.pw.atom_ref[batch.z.long() - 1]
+            raw["site_energies"] = out.site_e + atom_ref[batch.z.long() - 1]
         if return_crystal_feas:
             raw["crystal_fea"] = out.crystal_fea
         if "f" in task:

@@ -34,6 +34,7 @@ extern "C" {
 #endif
 
 #define CHG_FEA 64
+#define CHG_MAX_CONV 8
 #define CHG_OK 0
 #define CHG_ERR_ARG (-1)
 #define CHG_ERR_CUDA (-2)
@@ -181,6 +182,82 @@ int chg_force_virial(const float* rvec, const float* dist, const float* rhat,
                      const int32_t* u2d, const int32_t* center, const int32_t* nbr,
                      const int32_t* atom_owner, int32_t n_edges, double* force,
                      double* virial, void* stream);
+
+/* ======================= whole-path entry points =======================
+ * One call for CHGNet._compute + the two autograd.grad calls (reference model.py:389-542): the kernel
+ * schedule of chgnet_b200/engine.py run natively on a caller-provided workspace.  This is what a
+ * non-Python host, or model.py through a single ctypes call, binds; the per-kernel entry points above
+ * stay available for unit parity tests and ncu isolation.                                           */
+typedef struct {
+  int32_t num_radial;        /* 31 (0.3.0) / 9 (0.2.0), <= 32                                       */
+  int32_t num_angular;       /* 2*n_freq+1: 31 / 9, odd, <= 31                                      */
+  int32_t n_conv;            /* AtomConv layers (4); BondConv = n_conv-1, live AngleUpdate = n_conv-2 */
+  int32_t cutoff_coeff;      /* envelope exponent p (8 / 5), 0 = no envelope                        */
+  int32_t n_readout_hidden;  /* hidden 64x64 layers of the readout MLP (3 / 2)                      */
+  int32_t use_ln;            /* LayerNorm inside the GatedMLPs (gMLP_norm="layer")                  */
+  int32_t readout_ln;        /* readout_norm="layer"                                                */
+  int32_t has_mlp_out_bias;  /* 0.2.0 checkpoints                                                   */
+  float atom_graph_cutoff;   /* 6 A */
+  float bond_graph_cutoff;   /* 3 A */
+  float b_last;              /* bias of the last readout layer  (set by chg_pack_weights_host)      */
+  float b_mag;               /* bias of the site_wise head      (set by chg_pack_weights_host)      */
+} chg_hparams;
+
+/* one GatedMLP (+ mlp_out) of the reference state_dict, PyTorch layout [out][in], HOST pointers      */
+typedef struct {
+  const float* core_w1; const float* core_b1; const float* gate_w1; const float* gate_b1; /* [64][192|256], [64] */
+  const float* core_w2; const float* core_b2; const float* gate_w2; const float* gate_b2; /* [64][64]; NULL for angle layers */
+  const float* ln1_w; const float* ln1_b; const float* ln2_w; const float* ln2_b;         /* bn1 / bn2, NULL without LayerNorm */
+  const float* out_w; const float* out_b;   /* mlp_out.layers.1 [64][64] (+ bias or NULL); NULL for angle layers */
+} chg_gated_sd;
+typedef struct {
+  const float* atom_embedding;                                  /* [94][64] */
+  const float* freq_ag; const float* freq_bg; const float* freq_ang;
+  const float* bond_embedding; const float* bond_weights_ag; const float* bond_weights_bg; /* [64][num_radial] */
+  const float* angle_embedding;                                 /* [64][num_angular] */
+  chg_gated_sd atom[CHG_MAX_CONV];   /* atom_conv_layers.{t}.twoBody_atom + mlp_out */
+  chg_gated_sd bond[CHG_MAX_CONV];   /* bond_conv_layers.{t}.twoBody_bond + mlp_out */
+  chg_gated_sd angle[CHG_MAX_CONV];  /* angle_layers.{t}.twoBody_bond               */
+  const float* readout_ln_w; const float* readout_ln_b;
+  const float* mlp_w[4]; const float* mlp_b[4];                 /* hidden readout layers */
+  const float* mlp_last_w; float mlp_last_b;                    /* [64], scalar */
+  const float* site_wise_w; float site_wise_b;
+  const float* atom_ref;                                        /* composition_model.fc.weight [94] or NULL */
+} chg_state_dict;
+/* number of floats of the packed weight blob; pack on the HOST (weights.py::pack_weights restated),
+ * then copy the blob to the device (64-byte aligned) and hand it to chg_forward                      */
+int64_t chg_packed_floats(const chg_hparams* hp);
+int chg_pack_weights_host(chg_hparams* hp, const chg_state_dict* sd, float* packed_host);
+
+/* the SoA batch descriptor (chgnet_b200/batch.py::DeviceBatch): device pointers, int32 indices.
+ * Directed edges are sorted by centre atom, angles by bond i; ptr_* are CSR row pointers and perm_* the
+ * grouping permutations (by neighbour atom, by undirected bond, by bond j, by centre atom of the
+ * angle); short_ids / ang_is / ang_js address the compact slots of the bond-graph bonds.              */
+typedef struct {
+  int32_t n_atoms, n_edges, n_bonds, n_angles, n_graphs, n_short;
+  const int32_t* z; const float* frac; const int32_t* owner; const float* lattice;   /* [N], [N][3], [N], [B][9] */
+  const int32_t* center; const int32_t* nbr; const float* image;                     /* [Ed], [Ed], [Ed][3] */
+  const int32_t* d2u; const int32_t* u2d;                                            /* [Ed], [Eu] */
+  const int32_t* ptr_c; const int32_t* perm_n; const int32_t* ptr_n; const int32_t* perm_u; const int32_t* ptr_u;
+  const int32_t* ang_atom; const int32_t* ang_di; const int32_t* ang_dj; const int32_t* ang_is; const int32_t* ang_js;
+  const int32_t* ptr_is; const int32_t* perm_js; const int32_t* ptr_js; const int32_t* perm_x; const int32_t* ptr_x;
+  const int32_t* short_ids;   /* [Es] */
+  const int32_t* graph_ptr;   /* [B+1] atoms of each graph (only for crystal_fea) */
+} chg_batch;
+/* caller-allocated outputs; NULL = not wanted (energy, e_ref, site_e are required).  force / virial
+ * non-NULL runs the reverse pass.  energy / e_ref are EXTENSIVE (eV): e = (energy + e_ref) / n_atoms. */
+typedef struct {
+  double* energy; double* e_ref; float* site_e;      /* [B], [B], [N] */
+  float* magmom; float* atom_fea; float* crystal_fea;  /* [N], [N][64], [B][64] */
+  double* force; double* virial;                     /* [N][3], [B][9] = sum_e r (x) dE/dr (stress = 160.21766208 / V * virial) */
+} chg_outputs;
+/* workspace size for these sizes / wanted outputs (pointers of `sizes` may be NULL; of `wanted` only
+ * NULL-ness matters); `trace` (optional) receives the newline-separated list of kernel calls         */
+int chg_forward_plan(const chg_hparams* hp, const chg_batch* sizes, const chg_outputs* wanted,
+                     size_t* workspace_bytes, char* trace, size_t trace_cap);
+int chg_forward(const chg_hparams* hp, const float* packed_weights, const chg_batch* batch,
+                const chg_outputs* out, void* workspace /* 256-byte aligned */, size_t workspace_bytes,
+                void* stream);
 
 /* ======================= training (reference trainer.py:398-411, 779-869) =======================
  * The reverse pass over activations is the one above (seeded with the loss instead of 1); these

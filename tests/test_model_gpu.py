@@ -191,3 +191,44 @@ def test_v020_shaped_architecture_end_to_end(weights030):
     for p, r in zip(preds, ref):
         for k, tol in TOL.items():
             assert _maxabs(p[k], r[k]) < tol * 5, (k, _maxabs(p[k], r[k]))  # untrained weights: larger magnitudes
+
+
+def test_native_forward_equals_python_schedule(model, monkeypatch):
+    """chg_forward (one C call, native schedule + workspace) == engine.py calling the same kernels one by one."""
+    from chgnet_b200.batch import build_batch
+
+    graphs = graphgen.random_graphs(5, 10, 24, 7700)
+    kw = dict(task="efsm", return_site_energies=True, return_atom_feas=True, return_crystal_feas=True, batch_size=5)
+    nat = model.predict_graph(graphs, **kw)
+    calls = model._get_native().calls
+    assert calls >= 1
+    monkeypatch.setenv("CHGNET_B200_ENGINE", "python")
+    py = model.predict_graph(graphs, **kw)
+    assert model._get_native().calls == calls  # the Python schedule really ran
+    monkeypatch.delenv("CHGNET_B200_ENGINE")
+    for a, b in zip(nat, py):
+        assert set(a) == set(b)
+        for k in a:
+            # same kernels, same order: identical up to the order of the fp64 atomics in force / virial
+            assert _maxabs(a[k], b[k]) <= 1e-6 * max(1.0, float(np.abs(b[k]).max())), k
+    # energy-only call, then a larger batch: the workspace grows and is reused
+    e_only = model.predict_graph(graphs[:2], task="e", batch_size=2)
+    assert _maxabs(e_only[0]["e"], nat[0]["e"]) < 1e-6
+    big = model.predict_graph(graphgen.random_graphs(12, 20, 30, 7800), task="efs", batch_size=12)
+    assert len(big) == 12 and np.isfinite(big[3]["f"]).all()
+    # a workspace that is too small is an error, not a crash
+    import ctypes
+
+    from chgnet_b200 import native
+
+    n = model._get_native()
+    b = build_batch(graphs, model.device)
+    res = {"energy": torch.empty(5, dtype=torch.float64, device="cuda"), "e_ref": torch.empty(5, dtype=torch.float64, device="cuda"),
+           "site_e": torch.empty(b.n_atoms, device="cuda")}
+    outs = native.Outputs(**{k: v.data_ptr() for k, v in res.items()})
+    bs = native.batch_struct(b)
+    small = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    base = (small.data_ptr() + 255) // 256 * 256
+    rc = n.lib.chg_forward(ctypes.byref(n.hps), n.weights.data_ptr(), ctypes.byref(bs), ctypes.byref(outs), base, 1 << 15,
+                           torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"workspace too small" in n.lib.chg_last_error()
