@@ -1,0 +1,283 @@
+// Host-native CrystalGraph builder: periodic neighbour list, undirected-bond pairing, bond (line) graph.
+//
+// This is the counterpart of the reference's only native component on this path — `create_graph.c` /
+// `cygraph.pyx` (chgnet/graph/cygraph.pyx:69-175, create_graph.c:100-107) — plus the neighbour list the
+// reference takes from pymatgen (converter.py:132), with the semantics of converter.py:102-190 and
+// graph.py:132-328 as restated (and pinned against the reference's `Graph` class) by
+// chgnet_b200/graphgen.py:
+//   * directed edges: every (center, neighbour, image) with 1e-8 < d <= r_atom, sorted by
+//     (center, neighbour, image);
+//   * undirected bonds: (c, n, img) and (n, c, -img) share one index, numbered by first appearance;
+//     undirected2directed points at the first of the two;
+//   * bond graph: for every directed edge i with d < r_bond and every OTHER directed edge j with
+//     d < r_bond leaving the same centre, one row (centre, u(i), i, u(j), j); rows sorted by
+//     (u(i), whether i is the second edge of its bond), stable.
+// Pure host code (no device work): a uniform grid over the replicated images makes the search
+// O(N * neighbours); centres are processed in parallel with OpenMP.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+struct chg_graph {
+  std::vector<int32_t> atom_graph;  // [Ed][2]
+  std::vector<float> image;         // [Ed][3]
+  std::vector<int32_t> d2u, u2d;    // [Ed], [Eu]
+  std::vector<int32_t> bond_graph;  // [A][5]
+};
+
+namespace chg {
+namespace {
+
+struct Hit {
+  int32_t nbr;
+  int32_t img[3];
+  double d;
+};
+
+void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+}  // namespace
+}  // namespace chg
+
+using namespace chg;
+
+extern "C" int chg_graph_build(const double* frac, const double* lattice, int32_t n_atoms, double r_atom, double r_bond,
+                               chg_graph** out) {
+  CHG_CHECK_ARG(n_atoms >= 0 && r_atom > 0 && r_bond >= 0, "bad size or cutoff");
+  CHG_CHECK_ARG(lattice != nullptr && out != nullptr && (frac != nullptr || n_atoms == 0), "null pointer");
+  const double tol = 1e-8;
+  const double* L = lattice;  // rows = lattice vectors
+  const int n = n_atoms;
+  chg_graph* G = new chg_graph();
+  *out = G;
+  if (n == 0) return CHG_OK;
+
+  // ---- image range: distance between lattice planes -> repetitions (graphgen.neighbor_list) ----
+  double c12[3], c20[3], c01[3];
+  cross3(L + 3, L + 6, c12);
+  cross3(L + 6, L + 0, c20);
+  cross3(L + 0, L + 3, c01);
+  const double vol = std::fabs(L[0] * c12[0] + L[1] * c12[1] + L[2] * c12[2]);
+  CHG_CHECK_ARG(vol > 0, "singular lattice");
+  const double* crosses[3] = {c12, c20, c01};
+  int lo_i[3], hi_i[3];
+  for (int k = 0; k < 3; ++k) {
+    const double* c = crosses[k];
+    const double height = vol / std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    double fmin = frac[k], fmax = frac[k];
+    for (int i = 1; i < n; ++i) {
+      fmin = std::min(fmin, frac[3 * i + k]);
+      fmax = std::max(fmax, frac[3 * i + k]);
+    }
+    const int reps = (int)std::ceil(r_atom / height);
+    const int span = (int)(std::ceil(fmax) - std::floor(fmin));
+    lo_i[k] = -reps - span;
+    hi_i[k] = reps + span;
+  }
+  std::vector<double> cart((size_t)n * 3);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 3; ++j)
+      cart[3 * i + j] = frac[3 * i] * L[j] + frac[3 * i + 1] * L[3 + j] + frac[3 * i + 2] * L[6 + j];
+
+  // ---- uniform grid (cell edge r_atom) over the centres' bounding box grown by r_atom; only image
+  //      points inside it can be neighbours ----
+  double bmin[3], bmax[3];
+  for (int j = 0; j < 3; ++j) bmin[j] = bmax[j] = cart[j];
+  for (int i = 1; i < n; ++i)
+    for (int j = 0; j < 3; ++j) {
+      bmin[j] = std::min(bmin[j], cart[3 * i + j]);
+      bmax[j] = std::max(bmax[j], cart[3 * i + j]);
+    }
+  int64_t dims[3];
+  for (int j = 0; j < 3; ++j) {
+    bmin[j] -= r_atom * (1 + 1e-9);
+    bmax[j] += r_atom * (1 + 1e-9);
+    dims[j] = std::max<int64_t>(1, (int64_t)std::floor((bmax[j] - bmin[j]) / r_atom));
+  }
+  const double inv_cell[3] = {dims[0] / (bmax[0] - bmin[0]), dims[1] / (bmax[1] - bmin[1]), dims[2] / (bmax[2] - bmin[2])};
+  auto bin_of = [&](const double* p, int64_t* ijk) {
+    for (int j = 0; j < 3; ++j) ijk[j] = std::min<int64_t>(dims[j] - 1, std::max<int64_t>(0, (int64_t)((p[j] - bmin[j]) * inv_cell[j])));
+  };
+  struct Pt {
+    double x, y, z;
+    int32_t atom, i0, i1, i2;
+  };
+  std::vector<Pt> pts;
+  std::vector<int64_t> pt_bin;
+  for (int i0 = lo_i[0]; i0 <= hi_i[0]; ++i0)
+    for (int i1 = lo_i[1]; i1 <= hi_i[1]; ++i1)
+      for (int i2 = lo_i[2]; i2 <= hi_i[2]; ++i2) {
+        const double sh[3] = {i0 * L[0] + i1 * L[3] + i2 * L[6], i0 * L[1] + i1 * L[4] + i2 * L[7],
+                              i0 * L[2] + i1 * L[5] + i2 * L[8]};
+        for (int a = 0; a < n; ++a) {
+          const double p[3] = {cart[3 * a] + sh[0], cart[3 * a + 1] + sh[1], cart[3 * a + 2] + sh[2]};
+          if (p[0] < bmin[0] || p[0] > bmax[0] || p[1] < bmin[1] || p[1] > bmax[1] || p[2] < bmin[2] || p[2] > bmax[2]) continue;
+          int64_t ijk[3];
+          bin_of(p, ijk);
+          pts.push_back(Pt{p[0], p[1], p[2], a, i0, i1, i2});
+          pt_bin.push_back((ijk[0] * dims[1] + ijk[1]) * dims[2] + ijk[2]);
+        }
+      }
+  const int64_t n_bins = dims[0] * dims[1] * dims[2];
+  std::vector<int64_t> bin_start((size_t)n_bins + 1, 0);
+  for (int64_t b : pt_bin) ++bin_start[b + 1];
+  for (int64_t b = 0; b < n_bins; ++b) bin_start[b + 1] += bin_start[b];
+  std::vector<int32_t> order(pts.size());
+  {
+    std::vector<int64_t> fill(bin_start.begin(), bin_start.end() - 1);
+    for (size_t p = 0; p < pts.size(); ++p) order[fill[pt_bin[p]]++] = (int32_t)p;
+  }
+
+  // ---- neighbour search, one centre at a time (parallel), hits sorted by (neighbour, image) ----
+  std::vector<std::vector<Hit>> hits((size_t)n);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int c = 0; c < n; ++c) {
+    const double* pc = &cart[3 * c];
+    int64_t ijk[3];
+    bin_of(pc, ijk);
+    std::vector<Hit>& h = hits[c];
+    for (int64_t bx = std::max<int64_t>(0, ijk[0] - 1); bx <= std::min(dims[0] - 1, ijk[0] + 1); ++bx)
+      for (int64_t by = std::max<int64_t>(0, ijk[1] - 1); by <= std::min(dims[1] - 1, ijk[1] + 1); ++by)
+        for (int64_t bz = std::max<int64_t>(0, ijk[2] - 1); bz <= std::min(dims[2] - 1, ijk[2] + 1); ++bz) {
+          const int64_t b = (bx * dims[1] + by) * dims[2] + bz;
+          for (int64_t q = bin_start[b]; q < bin_start[b + 1]; ++q) {
+            const Pt& p = pts[order[q]];
+            const double dx = p.x - pc[0], dy = p.y - pc[1], dz = p.z - pc[2];
+            const double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+            if (d > tol && d <= r_atom) h.push_back(Hit{p.atom, {p.i0, p.i1, p.i2}, d});
+          }
+        }
+    std::sort(h.begin(), h.end(), [](const Hit& x, const Hit& y) {
+      if (x.nbr != y.nbr) return x.nbr < y.nbr;
+      if (x.img[0] != y.img[0]) return x.img[0] < y.img[0];
+      if (x.img[1] != y.img[1]) return x.img[1] < y.img[1];
+      return x.img[2] < y.img[2];
+    });
+  }
+  size_t n_dir = 0;
+  for (int c = 0; c < n; ++c) n_dir += hits[c].size();
+  CHG_CHECK_ARG(n_dir < (size_t)INT32_MAX, "too many edges for int32 indices");
+  G->atom_graph.resize(n_dir * 2);
+  G->image.resize(n_dir * 3);
+  G->d2u.resize(n_dir);
+  std::vector<double> dist(n_dir);
+  std::vector<int32_t> ctr(n_dir);
+  {
+    size_t e = 0;
+    for (int c = 0; c < n; ++c)
+      for (const Hit& h : hits[c]) {
+        G->atom_graph[2 * e] = c;
+        G->atom_graph[2 * e + 1] = h.nbr;
+        for (int j = 0; j < 3; ++j) G->image[3 * e + j] = (float)h.img[j];
+        dist[e] = h.d;
+        ctr[e] = c;
+        ++e;
+      }
+  }
+
+  // ---- undirected bonds, numbered by first appearance ----
+  // the reverse of edge (c, n, img) is (n, c, -img): found by binary search among the (sorted) hits of n
+  std::vector<int64_t> first_edge((size_t)n + 1, 0);
+  for (int c = 0; c < n; ++c) first_edge[c + 1] = first_edge[c] + (int64_t)hits[c].size();
+  std::vector<int32_t> rev(n_dir);
+  bool complete = true;
+#pragma omp parallel for schedule(dynamic, 16) reduction(&& : complete)
+  for (int c = 0; c < n; ++c) {
+    for (size_t k = 0; k < hits[c].size(); ++k) {
+      const Hit& h = hits[c][k];
+      const Hit want{c, {-h.img[0], -h.img[1], -h.img[2]}, 0.0};
+      const std::vector<Hit>& hn = hits[h.nbr];
+      auto it = std::lower_bound(hn.begin(), hn.end(), want, [](const Hit& x, const Hit& y) {
+        if (x.nbr != y.nbr) return x.nbr < y.nbr;
+        if (x.img[0] != y.img[0]) return x.img[0] < y.img[0];
+        if (x.img[1] != y.img[1]) return x.img[1] < y.img[1];
+        return x.img[2] < y.img[2];
+      });
+      const bool found = it != hn.end() && it->nbr == c && it->img[0] == want.img[0] && it->img[1] == want.img[1] &&
+                         it->img[2] == want.img[2];
+      complete = complete && found;
+      rev[first_edge[c] + (int64_t)k] = found ? (int32_t)(first_edge[h.nbr] + (it - hn.begin())) : -1;
+    }
+  }
+  if (!complete) {
+    set_error("chg_graph_build: directed edges are not complete: some undirected bond does not have exactly 2 directed edges");
+    return CHG_ERR_ARG;
+  }
+  G->u2d.reserve(n_dir / 2);
+  for (size_t e = 0; e < n_dir; ++e) {
+    if ((size_t)rev[e] > e) {  // first appearance of this bond
+      G->d2u[e] = (int32_t)G->u2d.size();
+      G->u2d.push_back((int32_t)e);
+    } else {
+      G->d2u[e] = G->d2u[rev[e]];
+    }
+  }
+
+  // ---- bond graph: rows are generated centre by centre; the final order (undirected bond of i, then
+  //      first / second edge of that bond, stable) is a counting sort over 2 * Eu keys ----
+  std::vector<int32_t> short_e;
+  for (size_t e = 0; e < n_dir; ++e)
+    if (dist[e] < r_bond) short_e.push_back((int32_t)e);
+  const size_t n_keys = G->u2d.size() * 2;
+  std::vector<int64_t> key_start(n_keys + 1, 0);
+  auto key_of = [&](int32_t ei) { return (size_t)G->d2u[ei] * 2 + (G->u2d[G->d2u[ei]] != ei ? 1 : 0); };
+  for (size_t s0 = 0; s0 < short_e.size();) {
+    size_t t = s0;
+    while (t < short_e.size() && ctr[short_e[t]] == ctr[short_e[s0]]) ++t;
+    for (size_t i = s0; i < t; ++i) key_start[key_of(short_e[i]) + 1] += (int64_t)(t - s0 - 1);
+    s0 = t;
+  }
+  for (size_t k = 0; k < n_keys; ++k) key_start[k + 1] += key_start[k];
+  G->bond_graph.resize((size_t)key_start[n_keys] * 5);
+  {
+    std::vector<int64_t> fill(key_start.begin(), key_start.end() - 1);
+    for (size_t s0 = 0; s0 < short_e.size();) {
+      size_t t = s0;
+      while (t < short_e.size() && ctr[short_e[t]] == ctr[short_e[s0]]) ++t;
+      for (size_t i = s0; i < t; ++i) {
+        const int32_t ei = short_e[i];
+        const int32_t ui = G->d2u[ei];
+        int64_t& at = fill[key_of(ei)];
+        for (size_t j = s0; j < t; ++j) {
+          if (j == i) continue;
+          const int32_t ej = short_e[j];
+          int32_t* row = &G->bond_graph[(size_t)at * 5];
+          row[0] = ctr[ei]; row[1] = ui; row[2] = ei; row[3] = G->d2u[ej]; row[4] = ej;
+          ++at;
+        }
+      }
+      s0 = t;
+    }
+  }
+  return CHG_OK;
+}
+
+extern "C" void chg_graph_sizes(const chg_graph* g, int64_t* n_edges, int64_t* n_bonds, int64_t* n_angles) {
+  if (n_edges) *n_edges = g ? (int64_t)g->d2u.size() : 0;
+  if (n_bonds) *n_bonds = g ? (int64_t)g->u2d.size() : 0;
+  if (n_angles) *n_angles = g ? (int64_t)g->bond_graph.size() / 5 : 0;
+}
+
+extern "C" int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int32_t* d2u, int32_t* u2d,
+                                int32_t* bond_graph) {
+  CHG_CHECK_ARG(g != nullptr, "null graph");
+  auto put = [](void* dst, const void* src, size_t bytes) {
+    if (dst != nullptr && bytes > 0) std::memcpy(dst, src, bytes);
+  };
+  put(atom_graph, g->atom_graph.data(), g->atom_graph.size() * 4);
+  put(image, g->image.data(), g->image.size() * 4);
+  put(d2u, g->d2u.data(), g->d2u.size() * 4);
+  put(u2d, g->u2d.data(), g->u2d.size() * 4);
+  put(bond_graph, g->bond_graph.data(), g->bond_graph.size() * 4);
+  return CHG_OK;
+}
+
+extern "C" void chg_graph_free(chg_graph* g) { delete g; }

@@ -153,6 +153,48 @@ def build_graph_arrays(center, neighbor, image, distance, bond_cutoff: float):
     return atom_graph, d2u, u2d, rows[order]
 
 
+def native_graph_arrays(frac: np.ndarray, lattice: np.ndarray, atom_graph_cutoff: float, bond_graph_cutoff: float):
+    """The same arrays as ``neighbor_list`` + ``build_graph_arrays`` from the C++ builder of the kernel
+    library (``chg_graph_build``, csrc/graph_builder.cu — host code, no GPU needed): atom_graph [Ed,2],
+    image [Ed,3] (fp32), d2u, u2d, bond_graph [A,5] (int32)."""
+    import ctypes
+
+    from chgnet_b200._lib import ChgnetB200Error, load_library
+
+    lib = load_library()
+    if not getattr(lib, "_graph_bound", False):
+        lib.chg_graph_build.restype = ctypes.c_int32
+        lib.chg_graph_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
+                                        ctypes.POINTER(ctypes.c_void_p)]
+        lib.chg_graph_sizes.restype = None
+        lib.chg_graph_sizes.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int64)] * 3
+        lib.chg_graph_export.restype = ctypes.c_int32
+        lib.chg_graph_export.argtypes = [ctypes.c_void_p] * 6
+        lib.chg_graph_free.restype = None
+        lib.chg_graph_free.argtypes = [ctypes.c_void_p]
+        lib._graph_bound = True
+    frac = np.ascontiguousarray(frac, dtype=np.float64).reshape(-1, 3)
+    lattice = np.ascontiguousarray(lattice, dtype=np.float64).reshape(3, 3)
+    handle = ctypes.c_void_p()
+    rc = lib.chg_graph_build(frac.ctypes.data, lattice.ctypes.data, len(frac), float(atom_graph_cutoff),
+                             float(bond_graph_cutoff), ctypes.byref(handle))
+    try:
+        if rc != 0:
+            msg = lib.chg_last_error().decode()
+            raise (ValueError if "not complete" in msg else ChgnetB200Error)(msg)
+        ne, nb, na = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        lib.chg_graph_sizes(handle, ctypes.byref(ne), ctypes.byref(nb), ctypes.byref(na))
+        ag = np.empty((ne.value, 2), np.int32)
+        img = np.empty((ne.value, 3), np.float32)
+        d2u, u2d = np.empty(ne.value, np.int32), np.empty(nb.value, np.int32)
+        bg = np.empty((na.value, 5), np.int32)
+        lib.chg_graph_export(handle, ag.ctypes.data, img.ctypes.data, d2u.ctypes.data, u2d.ctypes.data, bg.ctypes.data)
+    finally:
+        if handle:
+            lib.chg_graph_free(handle)
+    return ag, img, d2u, u2d, bg
+
+
 def make_crystal_graph(
     atomic_numbers,
     frac,
@@ -161,21 +203,31 @@ def make_crystal_graph(
     atom_graph_cutoff: float = 6.0,
     bond_graph_cutoff: float = 3.0,
     graph_id: str | None = None,
+    backend: str = "native",
 ) -> CrystalGraph:
-    """numpy structure -> CrystalGraph with the reference's dtypes."""
+    """numpy structure -> CrystalGraph with the reference's dtypes.
+
+    ``backend="native"`` (default): the C++ builder of the kernel library; ``"numpy"``: the vectorised
+    restatement above (the builder's own oracle, pinned against the reference's ``Graph`` class)."""
     frac = np.asarray(frac, dtype=np.float64)
     lattice = np.asarray(lattice, dtype=np.float64)
-    c, n, img, d = neighbor_list(frac, lattice, atom_graph_cutoff)
-    ag, d2u, u2d, bg = build_graph_arrays(c, n, img, d, bond_graph_cutoff)
+    if backend == "native":
+        ag, img, d2u, u2d, bg = native_graph_arrays(frac, lattice, atom_graph_cutoff, bond_graph_cutoff)
+    elif backend == "numpy":
+        c, n, img, d = neighbor_list(frac, lattice, atom_graph_cutoff)
+        ag, d2u, u2d, bg = build_graph_arrays(c, n, img, d, bond_graph_cutoff)
+    else:
+        raise ValueError(f"unknown {backend=}")
+    as_i32 = (lambda a: torch.from_numpy(a)) if backend == "native" else (lambda a: torch.tensor(a, dtype=torch.int32))
     return CrystalGraph(
         atomic_number=torch.tensor(np.asarray(atomic_numbers), dtype=torch.int32),
         atom_frac_coord=torch.tensor(frac, dtype=TORCH_DTYPE),
-        atom_graph=torch.tensor(ag, dtype=torch.int32).reshape(-1, 2),
+        atom_graph=as_i32(ag).reshape(-1, 2),
         atom_graph_cutoff=atom_graph_cutoff,
-        neighbor_image=torch.tensor(img, dtype=TORCH_DTYPE).reshape(-1, 3),
-        directed2undirected=torch.tensor(d2u, dtype=torch.int32),
-        undirected2directed=torch.tensor(u2d, dtype=torch.int32),
-        bond_graph=torch.tensor(bg, dtype=torch.int32).reshape(-1, 5),
+        neighbor_image=(torch.from_numpy(img) if backend == "native" else torch.tensor(img, dtype=TORCH_DTYPE)).reshape(-1, 3),
+        directed2undirected=as_i32(d2u),
+        undirected2directed=as_i32(u2d),
+        bond_graph=as_i32(bg).reshape(-1, 5),
         bond_graph_cutoff=bond_graph_cutoff,
         lattice=torch.tensor(lattice, dtype=TORCH_DTYPE),
         graph_id=graph_id,

@@ -259,6 +259,25 @@ int chg_forward(const chg_hparams* hp, const float* packed_weights, const chg_ba
                 const chg_outputs* out, void* workspace /* 256-byte aligned */, size_t workspace_bytes,
                 void* stream);
 
+/* ======================= host-native graph construction (row f1, host stage) =======================
+ * The reference's only native component on this path is its C graph builder
+ * (chgnet/graph/cygraph.pyx:69-175 -> create_graph.c:100-107, called from converter.py:257-266 after
+ * pymatgen's neighbour list, converter.py:132).  chg_graph_build does both steps in C++ on the HOST
+ * (no device work): periodic neighbour list (1e-8 < d <= r_atom, sorted by centre, neighbour, image),
+ * undirected-bond pairing (numbered by first appearance) and the bond graph (d < r_bond), with the row
+ * order of chgnet_b200/graphgen.py (pinned against the reference's Graph class).  frac [n][3] and
+ * lattice [3][3] (rows = lattice vectors) are fp64 HOST arrays; the graph object owns host memory
+ * until chg_graph_free.                                                                             */
+typedef struct chg_graph chg_graph;
+int chg_graph_build(const double* frac, const double* lattice, int32_t n_atoms, double r_atom, double r_bond,
+                    chg_graph** out);
+void chg_graph_sizes(const chg_graph* g, int64_t* n_edges, int64_t* n_bonds, int64_t* n_angles);
+/* copies into caller arrays (NULL = skip): atom_graph [Ed][2], image [Ed][3], d2u [Ed], u2d [Eu],
+ * bond_graph [A][5] = (centre atom, undirected i, directed i, undirected j, directed j)               */
+int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int32_t* d2u, int32_t* u2d,
+                     int32_t* bond_graph);
+void chg_graph_free(chg_graph* g);
+
 /* ======================= training (reference trainer.py:398-411, 779-869) =======================
  * The reverse pass over activations is the one above (seeded with the loss instead of 1); these
  * entry points add the parameter gradients, the loss terms and the optimizer step.  Losses on

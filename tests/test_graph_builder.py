@@ -1,0 +1,57 @@
+"""CPU: the host-native C++ graph builder (chg_graph_build, csrc/graph_builder.cu) against the numpy
+restatement of the reference's converter + Graph class (graphgen.py, itself pinned against the live
+reference in tests/test_oracle_golden.py): every index array identical, row for row."""
+import numpy as np
+import pytest
+import torch
+
+from chgnet_b200 import graphgen
+
+FIELDS = ("atom_graph", "neighbor_image", "directed2undirected", "undirected2directed", "bond_graph")
+
+
+def _same(z, frac, lat, **cut):
+    a = graphgen.make_crystal_graph(z, frac, lat, backend="native", **cut)
+    b = graphgen.make_crystal_graph(z, frac, lat, backend="numpy", **cut)
+    for f in FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y), f
+    return a
+
+
+@pytest.mark.parametrize("n,seed", [(1, 11), (2, 12), (9, 13), (33, 14), (120, 15)])
+def test_random_cells(n, seed):
+    z, frac, lat = graphgen.random_structure(n, seed)
+    g = _same(z, frac, lat)
+    assert len(g.directed2undirected) == 2 * len(g.undirected2directed)  # crystalgraph.py:96-100
+
+
+def test_reference_counts_and_cutoffs():
+    z, frac, lat = graphgen.limno2_structure()
+    g = _same(z, frac, lat, atom_graph_cutoff=5.0, bond_graph_cutoff=3.0)
+    assert (len(g.atom_graph), len(g.bond_graph), len(g.undirected2directed)) == (384, 744, 192)  # tests/test_crystal_graph.py:22-42
+    g = _same(z, frac, lat)
+    assert (len(g.atom_graph), len(g.bond_graph), len(g.undirected2directed)) == (672, 744, 336)
+    z, frac, lat = graphgen.limno2_structure((3, 2, 2), 0.03, 7)
+    _same(z, frac, lat, atom_graph_cutoff=4.5, bond_graph_cutoff=2.2)
+
+
+def test_edge_cases():
+    # isolated atom (no edges), no bond graph, fractional coordinates outside [0, 1), triclinic cell that
+    # needs several images per axis, an atom bonded to its own images
+    g = _same([3], np.zeros((1, 3)), np.eye(3) * 20.0)
+    assert len(g.atom_graph) == 0 and len(g.bond_graph) == 0
+    g = _same([3, 8], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 5.5)
+    assert len(g.bond_graph) == 0 and len(g.atom_graph) > 0
+    frac = np.array([[1.3, -0.2, 0.5], [0.1, 0.9, 2.2]])
+    lat = np.array([[2.1, 0.1, 0.0], [0.3, 2.4, 0.2], [0.0, 0.5, 2.9]])
+    g = _same([3, 8], frac, lat)
+    assert (g.atom_graph[:, 0] == g.atom_graph[:, 1]).any()  # self-image bonds exist in a 2 A cell
+    _same([26], np.array([[0.25, 0.25, 0.25]]), np.eye(3) * 2.5)
+
+
+def test_bad_input_is_reported():
+    from chgnet_b200._lib import ChgnetB200Error
+
+    with pytest.raises(ChgnetB200Error):
+        graphgen.native_graph_arrays(np.zeros((1, 3)), np.zeros((3, 3)), 6.0, 3.0)  # singular lattice
