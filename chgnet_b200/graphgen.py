@@ -208,7 +208,7 @@ def make_crystal_graph(
     """numpy structure -> CrystalGraph with the reference's dtypes.
 
     ``backend="native"`` (default): the C++ builder of the kernel library; ``"numpy"``: the vectorised
-    restatement above (the builder's own oracle, pinned against the reference's ``Graph`` class)."""
+    restatement above (the builder's own checker, pinned against the reference's ``Graph`` class)."""
     frac = np.asarray(frac, dtype=np.float64)
     lattice = np.asarray(lattice, dtype=np.float64)
     if backend == "native":
