@@ -13,10 +13,11 @@
 //     d < r_bond leaving the same centre, one row (centre, u(i), i, u(j), j); rows sorted by
 //     (u(i), whether i is the second edge of its bond), stable.
 // Pure host code (no device work): a uniform grid over the replicated images makes the search
-// O(N * neighbours); centres are processed in parallel with OpenMP.
+// O(N * neighbours); the per-centre loops can run on CHG_GRAPH_THREADS OpenMP threads (default 1).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,6 +38,14 @@ struct Hit {
   int32_t img[3];
   double d;
 };
+
+// worker threads for the per-centre loops: CHG_GRAPH_THREADS (default 1 — deterministic timing; the
+// two OpenMP runtimes of a PyTorch process do not always cooperate)
+int graph_threads() {
+  const char* e = std::getenv("CHG_GRAPH_THREADS");
+  const int t = e != nullptr ? std::atoi(e) : 1;
+  return t < 1 ? 1 : (t > 64 ? 64 : t);
+}
 
 void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
@@ -138,12 +147,14 @@ extern "C" int chg_graph_build(const double* frac, const double* lattice, int32_
 
   // ---- neighbour search, one centre at a time (parallel), hits sorted by (neighbour, image) ----
   std::vector<std::vector<Hit>> hits((size_t)n);
-#pragma omp parallel for schedule(dynamic, 16)
+  const int n_threads = graph_threads();
+#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads)
   for (int c = 0; c < n; ++c) {
     const double* pc = &cart[3 * c];
     int64_t ijk[3];
     bin_of(pc, ijk);
     std::vector<Hit>& h = hits[c];
+    h.reserve(128);
     for (int64_t bx = std::max<int64_t>(0, ijk[0] - 1); bx <= std::min(dims[0] - 1, ijk[0] + 1); ++bx)
       for (int64_t by = std::max<int64_t>(0, ijk[1] - 1); by <= std::min(dims[1] - 1, ijk[1] + 1); ++by)
         for (int64_t bz = std::max<int64_t>(0, ijk[2] - 1); bz <= std::min(dims[2] - 1, ijk[2] + 1); ++bz) {
@@ -189,7 +200,7 @@ extern "C" int chg_graph_build(const double* frac, const double* lattice, int32_
   for (int c = 0; c < n; ++c) first_edge[c + 1] = first_edge[c] + (int64_t)hits[c].size();
   std::vector<int32_t> rev(n_dir);
   bool complete = true;
-#pragma omp parallel for schedule(dynamic, 16) reduction(&& : complete)
+#pragma omp parallel for schedule(dynamic, 64) reduction(&& : complete) num_threads(n_threads)
   for (int c = 0; c < n; ++c) {
     for (size_t k = 0; k < hits[c].size(); ++k) {
       const Hit& h = hits[c][k];
