@@ -9,11 +9,12 @@ and messages.  Parameters are registered under the reference's ``state_dict`` na
 be handed back to the reference.
 
 The arithmetic is NOT torch: ``forward`` builds one :class:`DeviceBatch` and runs the
-kernel schedule of :mod:`chgnet_b200.engine` through the C ABI.  No CPU path.
+kernels through the C ABI — inference as ONE native call (``chg_forward``,
+:mod:`chgnet_b200.native`), training through the schedule of :mod:`chgnet_b200.engine`
+(``e / f / s / m`` then carry autograd history to the parameters).  No CPU path.
 
-Round-1 limits (raise, never fall back): feature dims must be 64, GatedMLP hidden
-dims 64 (conv) / 0 (angle), layer- or no normalisation, ``mlp_first=True``;
-outputs carry no autograd history (inference: E, F, sigma, magmom).
+Limits (raise, never fall back): feature dims must be 64, GatedMLP hidden dims 64 (conv) /
+0 (angle), layer- or no normalisation, ``mlp_first=True``.
 """
 from __future__ import annotations
 

@@ -10,9 +10,8 @@ schedule used for training and for the CPU specification tests.
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 
-import numpy as np
 import torch
 from torch import Tensor
 
@@ -254,4 +253,4 @@ def packed_layout(hps: HParams) -> dict[str, tuple[int, int]]:
 
 
 __all__ = ["NativeForward", "pack_weights_native", "plan", "packed_layout", "HParams", "Batch", "Outputs", "batch_struct",
-           "hparams_struct", "np", "c_double"]
+           "hparams_struct"]

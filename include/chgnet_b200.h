@@ -280,9 +280,9 @@ void chg_graph_free(chg_graph* g);
 
 /* ======================= training (reference trainer.py:398-411, 779-869) =======================
  * The reverse pass over activations is the one above (seeded with the loss instead of 1); these
- * entry points add the parameter gradients, the loss terms and the optimizer step.  Losses on
- * energies and magnetic moments are covered; losses on forces / stresses need the second-order
- * pass and are not built yet.                                                       */
+ * entry points add the parameter gradients, the loss terms and the optimizer step for losses on
+ * energies and magnetic moments; losses on forces / stresses additionally use the second-order
+ * entry points further down.                                                    */
 
 /* dL/dW^T: out[k][j] = sum_r act(x[xr(r)][k]) * g[gr(r)][j],  k < 64, j < n_out (multiple of 64);
  * colsum[j] = sum_r g[gr(r)][j] (bias gradient) or NULL.  x_silu != 0 applies SiLU to x (second
