@@ -239,3 +239,79 @@ def test_training_gradients_without_angles_and_with_isolated_atom(weights030):
         for k in names:
             w = want[k] if want[k] is not None else torch.zeros_like(P[k])
             assert float((got[k] - w).abs().max()) <= 1e-7 * max(float(w.abs().max()), 1.0), k
+
+
+# ---------------------------------------------------------------------------------------------
+# Trainer host logic on the CPU (flat parameter buffer, label packing, fused Adam, engine re-pack) with the
+# torch kernel specifications injected in place of the CUDA library
+# ---------------------------------------------------------------------------------------------
+def test_trainer_step_host_logic_with_spec_kernels(monkeypatch):
+    import os
+
+    from chgnet_b200.model import CHGNet
+    from chgnet_b200.trainer import Trainer
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz")
+    model = CHGNet.from_file(path, version="0.3.0")  # CPU parameters: the product refuses to run, the test injects the spec
+    with pytest.raises(RuntimeError):
+        model._get_engine()
+    calls = {"n": 0}
+
+    def spec_engine():
+        key = tuple(int(v._version) for v in model.state_dict().values()) + (model._engine_key,)
+        if model._engine is None or model._engine_key is None:
+            model._engine = Engine(pack_weights(model.state_dict(), model.model_args, device="cpu"), SpecKernels())
+            model._engine_key = key
+            calls["n"] += 1
+        return model._engine
+
+    monkeypatch.setattr(model, "_get_engine", spec_engine)
+    graphs = graphgen.random_graphs(3, 5, 8, 8900)
+    w = orc.load_weights_npz(path)
+    base = orc.predict_graph(w, graphs, "efsm", batch_size=3)
+    lab = {"e": torch.tensor([float(p["e"]) + 0.05 for p in base]), "f": [torch.as_tensor(p["f"]) + 0.02 for p in base],
+           "s": [torch.as_tensor(p["s"]) - 0.05 for p in base], "m": [torch.as_tensor(p["m"]) + 0.03 for p in base]}
+    lab["f"][1] = None  # a structure without force labels
+    trainer = Trainer(model, targets="efsm", criterion="MSE", learning_rate=1e-3)
+    # parameters are views of ONE 64-byte-aligned flat buffer, padding is zero
+    lo, hi = trainer.flat.data_ptr(), trainer.flat.data_ptr() + trainer.flat.numel() * 4
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            assert lo <= p.data_ptr() < hi and (p.data_ptr() - lo) % 64 == 0, n
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    report = trainer.train_step(graphs, lab)
+
+    # reference CombinedLoss on the oracle (fp64) for the same labels
+    P = {k: torch.as_tensor(np.asarray(v)).double().requires_grad_(k != "composition_model.fc.weight") for k, v in w.items()}
+    o = orc.forward(P, graphs, "efsm", dtype=torch.float64, train=True)
+    mse = torch.nn.MSELoss()
+    keep = [i for i, f in enumerate(lab["f"]) if f is not None]
+    loss = (mse(lab["e"].double(), o["e"]) + mse(torch.cat([lab["f"][i] for i in keep]).double(), torch.cat([o["f"][i] for i in keep]))
+            + 0.1 * mse(torch.stack(lab["s"]).double(), torch.stack(o["s"])) + 0.1 * mse(torch.cat(lab["m"]).double(), torch.cat(o["m"])))
+    names = [k for k, v in P.items() if v.requires_grad]
+    want = dict(zip(names, torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)))
+    assert report["loss"] == pytest.approx(float(loss.detach()), rel=1e-3)
+    assert report["f_MAE_size"] == 3 * sum(g.atomic_number.shape[0] for i, g in enumerate(graphs) if i in keep)
+    got = trainer.grads_by_name()
+    for k in names:
+        wk = want[k] if want[k] is not None else torch.zeros_like(P[k])
+        assert float((got[k].double() - wk).abs().max()) <= 2e-2 * float(wk.abs().max()) + 1e-5, k  # fp32 spec vs fp64
+    # the fused Adam kernel == torch.optim.Adam on the same gradients; padding untouched; engine re-packed
+    ref_params = [before[n].clone().requires_grad_(True) for n in trainer.names]
+    opt = torch.optim.Adam(ref_params, lr=1e-3)
+    for p, n in zip(ref_params, trainer.names):
+        p.grad = got[n].clone()
+    opt.step()
+    sd = model.state_dict()
+    for p, n in zip(ref_params, trainer.names):
+        assert float((sd[n] - p.detach()).abs().max()) < 1e-6, n
+    mask = torch.ones_like(trainer.flat, dtype=torch.bool)
+    for o_, sz in zip(trainer.offsets, trainer.sizes):
+        mask[o_:o_ + sz] = False
+    assert float(trainer.flat[mask].abs().max()) == 0.0
+    assert torch.equal(sd["composition_model.fc.weight"], before["composition_model.fc.weight"])  # frozen
+    n_before = calls["n"]
+    report2 = trainer.train_step(graphs, lab)
+    assert calls["n"] == n_before + 1 and report2["loss"] != report["loss"]  # new weights were re-packed and used
+    with pytest.raises(ValueError):
+        Trainer(model, targets="fx")
