@@ -126,8 +126,61 @@ def _group(keys: Tensor, n_rows: int) -> tuple[Tensor, Tensor]:
     return perm.to(torch.int32), _csr_ptr(sk, n_rows)
 
 
+_PACK_LIB = None
+
+
+def _pack_lib():
+    global _PACK_LIB
+    if _PACK_LIB is None:
+        import ctypes
+
+        from chgnet_b200._lib import load_library
+
+        lib = load_library()
+        lib.chg_pack_batch_host.restype = ctypes.c_int32
+        lib.chg_pack_batch_host.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5
+        _PACK_LIB = lib
+    return _PACK_LIB
+
+
+_INT_FIELDS = ("atomic_number", "directed2undirected", "undirected2directed")
+_FLT_FIELDS = ("atom_frac_coord", "neighbor_image", "lattice")
+
+
+def _graphs_are_packable(graphs, ag_l, bg_l) -> bool:
+    """Host tensors with the hot path's dtypes (int32 / fp32), contiguous: what the C packer memcpy's.
+    Checked once per graph object (the verdict is cached on it)."""
+    for g, ag, bg in zip(graphs, ag_l, bg_l):
+        ok = getattr(g, "_packable", None)
+        if ok is None:
+            try:
+                ok = (all(getattr(g, f).dtype == torch.int32 and getattr(g, f).is_contiguous() and getattr(g, f).device.type == "cpu"
+                          for f in _INT_FIELDS)
+                      and all(getattr(g, f).dtype == torch.float32 and getattr(g, f).is_contiguous() and getattr(g, f).device.type == "cpu"
+                              for f in _FLT_FIELDS)
+                      and ag.dtype == torch.int32 and ag.is_contiguous() and bg.dtype == torch.int32 and bg.is_contiguous()
+                      and g.lattice.numel() == 9 and ag is g.atom_graph and bg is g.bond_graph or
+                      False)
+                if not ok and (ag is not g.atom_graph or bg is not g.bond_graph):
+                    # reshaped empty graphs (isolated atoms): nothing to copy from them, dtype still matters
+                    ok = (all(getattr(g, f).dtype == torch.int32 and getattr(g, f).is_contiguous() for f in _INT_FIELDS)
+                          and all(getattr(g, f).dtype == torch.float32 and getattr(g, f).is_contiguous() for f in _FLT_FIELDS)
+                          and g.lattice.numel() == 9 and ag.numel() * (ag is not g.atom_graph) == 0
+                          and bg.numel() * (bg is not g.bond_graph) == 0 and ag.dtype == torch.int32 and bg.dtype == torch.int32
+                          and ag.is_contiguous() and bg.is_contiguous())
+                try:
+                    g._packable = bool(ok)
+                except AttributeError:
+                    pass
+            except AttributeError:
+                ok = False
+        if not ok:
+            return False
+    return True
+
+
 def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True,
-                compact_bonds: bool = True) -> DeviceBatch:
+                compact_bonds: bool = True, native_pack: bool = True) -> DeviceBatch:
     device = torch.device(device)
     B = len(graphs)
     # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
@@ -150,122 +203,159 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
             raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
 
     src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
-    host_src = src_dev.type == "cpu"
-    pin = host_src and device.type == "cuda"
 
-    # (name, per-graph tensors, inner width, total rows)
-    int_fields = [
-        ("z", [g.atomic_number for g in graphs], 1, N),
-        ("ag", ag_l, 2, Ed),
-        ("d2u", [g.directed2undirected for g in graphs], 1, Ed),
-        ("u2d", [g.undirected2directed for g in graphs], 1, Eu),
-        ("bg", bg_l, 5, A),
-    ]
-    flt_fields = [
-        ("frac", [g.atom_frac_coord for g in graphs], 3, N),
-        ("image", [g.neighbor_image for g in graphs], 3, Ed),
-        ("lattice", [g.lattice for g in graphs], 3, 3 * B),
-    ]
-    counts_host = np.array([n_at, n_ed, n_eu, n_an], dtype=np.int32).reshape(-1)  # [4*B]
-    n_int = sum(f[2] * f[3] for f in int_fields) + counts_host.size
-    n_flt = sum(f[2] * f[3] for f in flt_fields)
+    def pack_legacy():
+        src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
+        host_src = src_dev.type == "cpu"
+        pin = host_src and device.type == "cuda"
 
-    def as_np(t: Tensor) -> np.ndarray:
-        return t.detach().numpy() if t.requires_grad else t.numpy()
+        # (name, per-graph tensors, inner width, total rows)
+        int_fields = [
+            ("z", [g.atomic_number for g in graphs], 1, N),
+            ("ag", ag_l, 2, Ed),
+            ("d2u", [g.directed2undirected for g in graphs], 1, Ed),
+            ("u2d", [g.undirected2directed for g in graphs], 1, Eu),
+            ("bg", bg_l, 5, A),
+        ]
+        flt_fields = [
+            ("frac", [g.atom_frac_coord for g in graphs], 3, N),
+            ("image", [g.neighbor_image for g in graphs], 3, Ed),
+            ("lattice", [g.lattice for g in graphs], 3, 3 * B),
+        ]
+        counts_host = np.array([n_at, n_ed, n_eu, n_an], dtype=np.int32).reshape(-1)  # [4*B]
+        n_int = sum(f[2] * f[3] for f in int_fields) + counts_host.size
+        n_flt = sum(f[2] * f[3] for f in flt_fields)
 
-    def stage(fields, total, dtype, tail=None):
-        """Concatenate all parts into one staging buffer and ship it with one copy.  Host
-        graphs are packed with numpy (single-threaded memcpy: torch CPU ops fork an OpenMP
-        team per call, which costs milliseconds on a many-core host) into a cached pinned
-        buffer; device-resident graphs are concatenated on the device."""
-        views, off = {}, 0
-        if host_src:
-            buf = _staging_buffer(total, dtype, pin)
-            host = buf.numpy()
+        def as_np(t: Tensor) -> np.ndarray:
+            return t.detach().numpy() if t.requires_grad else t.numpy()
+
+        def stage(fields, total, dtype, tail=None):
+            """Concatenate all parts into one staging buffer and ship it with one copy.  Host
+            graphs are packed with numpy (single-threaded memcpy: torch CPU ops fork an OpenMP
+            team per call, which costs milliseconds on a many-core host) into a cached pinned
+            buffer; device-resident graphs are concatenated on the device."""
+            views, off = {}, 0
+            if host_src:
+                buf = _staging_buffer(total, dtype, pin)
+                host = buf.numpy()
+                for name, parts, width, rows in fields:
+                    size = width * rows
+                    if size:
+                        dst = host[off : off + size]
+                        np.concatenate([as_np(p) for p in parts], axis=0,
+                                       out=dst if width == 1 else dst.reshape(rows, width), casting="unsafe")
+                    views[name] = (off, size)
+                    off += size
+                if tail is not None:
+                    host[off : off + tail.size] = tail
+                    views["_tail"] = (off, tail.size)
+                dbuf = buf.to(device, non_blocking=True)
+                _mark_staging_in_flight(dtype, pin, device)
+                return dbuf, views, host
+            buf = torch.empty(total, dtype=dtype, device=src_dev)
             for name, parts, width, rows in fields:
                 size = width * rows
                 if size:
-                    dst = host[off : off + size]
-                    np.concatenate([as_np(p) for p in parts], axis=0,
-                                   out=dst if width == 1 else dst.reshape(rows, width), casting="unsafe")
+                    torch.cat([p.detach().reshape(-1).to(dtype) for p in parts], out=buf[off : off + size])
                 views[name] = (off, size)
                 off += size
             if tail is not None:
-                host[off : off + tail.size] = tail
+                buf[off : off + tail.size] = torch.from_numpy(tail).to(src_dev)
                 views["_tail"] = (off, tail.size)
-            dbuf = buf.to(device, non_blocking=True)
-            _mark_staging_in_flight(dtype, pin, device)
-            return dbuf, views, host
-        buf = torch.empty(total, dtype=dtype, device=src_dev)
-        for name, parts, width, rows in fields:
-            size = width * rows
-            if size:
-                torch.cat([p.detach().reshape(-1).to(dtype) for p in parts], out=buf[off : off + size])
-            views[name] = (off, size)
-            off += size
-        if tail is not None:
-            buf[off : off + tail.size] = torch.from_numpy(tail).to(src_dev)
-            views["_tail"] = (off, tail.size)
-        return buf.to(device), views, None
+            return buf.to(device), views, None
 
-    ibuf, iv, ihost = stage(int_fields, n_int, torch.int32, counts_host)
-    fbuf, fv, _ = stage(flt_fields, n_flt, torch.float32)
-    h2d = (n_int + n_flt) * 4 if src_dev != device else 0
+        ibuf, iv, ihost = stage(int_fields, n_int, torch.int32, counts_host)
+        fbuf, fv, _ = stage(flt_fields, n_flt, torch.float32)
+        h2d = (n_int + n_flt) * 4 if src_dev != device else 0
 
-    # sortedness (decides whether the device has to reorder): one vectorised pass over the
-    # concatenated raw indices; a decrease is only legal at a graph boundary
-    def sorted_within_graphs(raw: np.ndarray | Tensor, sizes: list[int]) -> bool:
-        if len(raw) < 2:
-            return True
-        if isinstance(raw, Tensor):
-            return all(_is_sorted(t) for t in torch.split(raw, sizes))
-        dec = raw[1:] < raw[:-1]
-        ends = np.cumsum(sizes)[:-1] - 1
-        ends = ends[(ends >= 0) & (ends < len(dec))]
-        dec[ends] = False
-        return not bool(dec.any())
+        # sortedness (decides whether the device has to reorder): one vectorised pass over the
+        # concatenated raw indices; a decrease is only legal at a graph boundary
+        def sorted_within_graphs(raw: np.ndarray | Tensor, sizes: list[int]) -> bool:
+            if len(raw) < 2:
+                return True
+            if isinstance(raw, Tensor):
+                return all(_is_sorted(t) for t in torch.split(raw, sizes))
+            dec = raw[1:] < raw[:-1]
+            ends = np.cumsum(sizes)[:-1] - 1
+            ends = ends[(ends >= 0) & (ends < len(dec))]
+            dec[ends] = False
+            return not bool(dec.any())
 
-    if ihost is not None:
-        o, sz = iv["ag"]
-        edges_sorted = sorted_within_graphs(ihost[o : o + sz : 2].copy(), n_ed)
-        o, sz = iv["bg"]
-        angles_sorted = sorted_within_graphs(ihost[o + 1 : o + sz : 5].copy(), n_an)
-    else:
-        edges_sorted = all(_is_sorted(a[:, 0]) for a in ag_l)
-        angles_sorted = all(_is_sorted(b[:, 1]) for b in bg_l)
+        if ihost is not None:
+            o, sz = iv["ag"]
+            edges_sorted = sorted_within_graphs(ihost[o : o + sz : 2].copy(), n_ed)
+            o, sz = iv["bg"]
+            angles_sorted = sorted_within_graphs(ihost[o + 1 : o + sz : 5].copy(), n_an)
+        else:
+            edges_sorted = all(_is_sorted(a[:, 0]) for a in ag_l)
+            angles_sorted = all(_is_sorted(b[:, 1]) for b in bg_l)
 
-    def iview(name):
-        o, s = iv[name]
-        return ibuf[o : o + s]
+        def iview(name):
+            o, s = iv[name]
+            return ibuf[o : o + s]
 
-    def fview(name):
-        o, s = fv[name]
-        return fbuf[o : o + s]
+        def fview(name):
+            o, s = fv[name]
+            return fbuf[o : o + s]
 
-    cnt = iview("_tail").view(4, B).long()  # device copies of the per-graph counts
-    # exclusive prefix sums = per-graph offsets
-    offs = torch.cumsum(cnt, dim=1) - cnt
-    atom_off, ed_off, eu_off = offs[0], offs[1], offs[2]
+        cnt = iview("_tail").view(4, B).long()  # device copies of the per-graph counts
+        # exclusive prefix sums = per-graph offsets
+        offs = torch.cumsum(cnt, dim=1) - cnt
+        atom_off, ed_off, eu_off = offs[0], offs[1], offs[2]
 
-    def rep(vals: Tensor, which: int, total: int) -> Tensor:
-        return torch.repeat_interleave(vals, cnt[which], output_size=total).to(torch.int32)
+        def rep(vals: Tensor, which: int, total: int) -> Tensor:
+            return torch.repeat_interleave(vals, cnt[which], output_size=total).to(torch.int32)
 
-    z = iview("z")
-    owner = rep(torch.arange(B, device=device), 0, N)
-    ag = iview("ag").view(Ed, 2)
-    e_atom_off = rep(atom_off, 1, Ed)
-    center = (ag[:, 0] + e_atom_off).contiguous()
-    nbr = (ag[:, 1] + e_atom_off).contiguous()
-    d2u = iview("d2u") + rep(eu_off, 1, Ed)
-    u2d = iview("u2d") + rep(ed_off, 2, Eu)
-    image = fview("image").view(Ed, 3)
-    bg = iview("bg").view(A, 5)
-    a_atom_off, a_eu_off, a_ed_off = rep(atom_off, 3, A), rep(eu_off, 3, A), rep(ed_off, 3, A)
-    ang_atom = bg[:, 0] + a_atom_off
-    ang_i = bg[:, 1] + a_eu_off
-    ang_di = bg[:, 2] + a_ed_off
-    ang_j = bg[:, 3] + a_eu_off
-    ang_dj = bg[:, 4] + a_ed_off
+        z = iview("z")
+        owner = rep(torch.arange(B, device=device), 0, N)
+        ag = iview("ag").view(Ed, 2)
+        e_atom_off = rep(atom_off, 1, Ed)
+        center = (ag[:, 0] + e_atom_off).contiguous()
+        nbr = (ag[:, 1] + e_atom_off).contiguous()
+        d2u = iview("d2u") + rep(eu_off, 1, Ed)
+        u2d = iview("u2d") + rep(ed_off, 2, Eu)
+        image = fview("image").view(Ed, 3)
+        bg = iview("bg").view(A, 5)
+        a_atom_off, a_eu_off, a_ed_off = rep(atom_off, 3, A), rep(eu_off, 3, A), rep(ed_off, 3, A)
+        ang_atom = bg[:, 0] + a_atom_off
+        ang_i = bg[:, 1] + a_eu_off
+        ang_di = bg[:, 2] + a_ed_off
+        ang_j = bg[:, 3] + a_eu_off
+        ang_dj = bg[:, 4] + a_ed_off
+        return (z, owner, center, nbr, d2u, u2d, image, fview("frac").view(N, 3), fview("lattice").view(B, 9),
+                ang_atom, ang_i, ang_di, ang_j, ang_dj, edges_sorted, angles_sorted, h2d)
+
+    def pack_native():
+        """ONE pass over host memory in the C library (chg_pack_batch_host): concatenation, index offsets,
+        owners and the sortedness flags, written straight into the cached (pinned) staging buffers."""
+        import ctypes
+
+        lib = _pack_lib()
+        n_int, n_flt = 2 * N + 3 * Ed + Eu + 5 * A, 3 * N + 3 * Ed + 9 * B
+        pin = device.type == "cuda"
+        ibuf_h, fbuf_h = _staging_buffer(max(n_int, 1), torch.int32, pin), _staging_buffer(max(n_flt, 1), torch.float32, pin)
+        counts = np.ascontiguousarray(np.array([n_at, n_ed, n_eu, n_an], dtype=np.int64).T)
+        ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
+                            for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
+                                      g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
+        flags = (ctypes.c_int32 * 2)()
+        rc = lib.chg_pack_batch_host(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(), flags)
+        if rc != 0:
+            raise RuntimeError(f"chg_pack_batch_host failed: {lib.chg_last_error().decode()}")
+        on_cpu = device.type == "cpu"  # a CPU "device" would alias the reused staging buffer: copy instead
+        ibuf = ibuf_h[:n_int].clone() if on_cpu else ibuf_h[:n_int].to(device, non_blocking=True)
+        _mark_staging_in_flight(torch.int32, pin, device)
+        fbuf = fbuf_h[:n_flt].clone() if on_cpu else fbuf_h[:n_flt].to(device, non_blocking=True)
+        _mark_staging_in_flight(torch.float32, pin, device)
+        sizes = (N, N, Ed, Ed, Ed, Eu, A, A, A, A, A)
+        z, owner, center, nbr, d2u, u2d, ang_atom, ang_i, ang_di, ang_j, ang_dj = torch.split(ibuf, sizes)
+        frac, image, lattice = torch.split(fbuf, (3 * N, 3 * Ed, 9 * B))
+        return (z, owner, center, nbr, d2u, u2d, image.view(Ed, 3), frac.view(N, 3), lattice.view(B, 9), ang_atom, ang_i,
+                ang_di, ang_j, ang_dj, bool(flags[0]), bool(flags[1]), (n_int + n_flt) * 4 if device.type != "cpu" else 0)
+
+    use_native = native_pack and B > 0 and src_dev.type == "cpu" and _graphs_are_packable(graphs, ag_l, bg_l)
+    (z, owner, center, nbr, d2u, u2d, image, frac_t, lattice, ang_atom, ang_i, ang_di, ang_j, ang_dj, edges_sorted,
+     angles_sorted, h2d) = pack_native() if use_native else pack_legacy()
 
     if not edges_sorted and Ed:
         # stable sort by center; remap everything that stores a directed index
@@ -314,14 +404,13 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
     else:
         perm_js, ptr_js = torch.zeros(0, **i32), torch.zeros(Es + 1, **i32)
 
-    lattice = fview("lattice").view(B, 9)
     L = lattice.view(B, 3, 3)
     volume = (L[:, 0] * torch.linalg.cross(L[:, 1], L[:, 2])).sum(dim=1)  # model.py:834-836
 
     c = lambda t: t.contiguous()  # noqa: E731
     return DeviceBatch(
         n_graphs=B, n_atoms=N, n_edges=Ed, n_bonds=Eu, n_angles=A, atoms_per_graph=n_at,
-        z=c(z), frac=c(fview("frac").view(N, 3)), owner=c(owner), lattice=c(lattice), volume=volume,
+        z=c(z), frac=c(frac_t), owner=c(owner), lattice=c(lattice), volume=volume,
         center=c(center), nbr=c(nbr), image=c(image), d2u=c(d2u), u2d=c(u2d),
         ptr_c=ptr_c, perm_n=perm_n, ptr_n=ptr_n, perm_u=perm_u, ptr_u=ptr_u,
         ang_atom=c(ang_atom), ang_i=c(ang_i), ang_j=c(ang_j), ang_di=c(ang_di), ang_dj=c(ang_dj),

@@ -292,3 +292,81 @@ extern "C" int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* 
 }
 
 extern "C" void chg_graph_free(chg_graph* g) { delete g; }
+
+// =====================================================================================
+// Host batch packer: list of CrystalGraphs -> the concatenated, offset-adjusted SoA of
+// chgnet_b200/batch.py::DeviceBatch in ONE pass over host memory (what BatchedGraph.from_graphs does
+// with ~25 tensor ops per graph, reference model.py:820-899).  Pure host code; the caller ships the
+// two staging buffers to the device with one copy each.
+//   ibuf layout (int32): z[N] owner[N] center[Ed] nbr[Ed] d2u[Ed] u2d[Eu] ang_atom[A] ang_i[A] ang_di[A]
+//                        ang_j[A] ang_dj[A]
+//   fbuf layout (fp32) : frac[N*3] image[Ed*3] lattice[B*9]
+// flags_out[0] = edges sorted by centre within every graph, flags_out[1] = angles sorted by bond i.
+// =====================================================================================
+extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B][4]: atoms, edges, bonds, angles */,
+                                   const void* const* ptrs /* [B][8]: z, frac, atom_graph, image, d2u, u2d, bond_graph, lattice */,
+                                   int32_t* ibuf, float* fbuf, int32_t* flags_out) {
+  CHG_CHECK_ARG(n_graphs >= 0, "negative size");
+  CHG_CHECK_ARG(counts != nullptr && ptrs != nullptr && ibuf != nullptr && fbuf != nullptr && flags_out != nullptr, "null pointer");
+  int64_t N = 0, Ed = 0, Eu = 0, A = 0;
+  for (int g = 0; g < n_graphs; ++g) {
+    N += counts[4 * g];
+    Ed += counts[4 * g + 1];
+    Eu += counts[4 * g + 2];
+    A += counts[4 * g + 3];
+  }
+  CHG_CHECK_ARG(N < INT32_MAX && Ed < INT32_MAX && A < INT32_MAX, "batch too large for int32 indices");
+  int32_t* z = ibuf;
+  int32_t* owner = z + N;
+  int32_t* center = owner + N;
+  int32_t* nbr = center + Ed;
+  int32_t* d2u = nbr + Ed;
+  int32_t* u2d = d2u + Ed;
+  int32_t* ang_atom = u2d + Eu;
+  int32_t* ang_i = ang_atom + A;
+  int32_t* ang_di = ang_i + A;
+  int32_t* ang_j = ang_di + A;
+  int32_t* ang_dj = ang_j + A;
+  float* frac = fbuf;
+  float* image = frac + N * 3;
+  float* lattice = image + Ed * 3;
+  bool edges_sorted = true, angles_sorted = true;
+  int64_t a_off = 0, e_off = 0, u_off = 0, g_off = 0;
+  for (int g = 0; g < n_graphs; ++g) {
+    const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
+    const void* const* p = ptrs + 8 * g;
+    if (n > 0) {
+      std::memcpy(z + a_off, p[0], (size_t)n * 4);
+      std::memcpy(frac + a_off * 3, p[1], (size_t)n * 12);
+      for (int64_t i = 0; i < n; ++i) owner[a_off + i] = g;
+    }
+    const int32_t* ag = static_cast<const int32_t*>(p[2]);
+    const int32_t* du = static_cast<const int32_t*>(p[4]);
+    for (int64_t e = 0; e < ed; ++e) {
+      center[e_off + e] = ag[2 * e] + (int32_t)a_off;
+      nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
+      d2u[e_off + e] = du[e] + (int32_t)u_off;
+      if (e > 0 && ag[2 * e] < ag[2 * e - 2]) edges_sorted = false;
+    }
+    if (ed > 0) std::memcpy(image + e_off * 3, p[3], (size_t)ed * 12);
+    const int32_t* ud = static_cast<const int32_t*>(p[5]);
+    for (int64_t u = 0; u < eu; ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
+    const int32_t* bg = static_cast<const int32_t*>(p[6]);
+    for (int64_t a = 0; a < an; ++a) {
+      ang_atom[g_off + a] = bg[5 * a] + (int32_t)a_off;
+      ang_i[g_off + a] = bg[5 * a + 1] + (int32_t)u_off;
+      ang_di[g_off + a] = bg[5 * a + 2] + (int32_t)e_off;
+      ang_j[g_off + a] = bg[5 * a + 3] + (int32_t)u_off;
+      ang_dj[g_off + a] = bg[5 * a + 4] + (int32_t)e_off;
+      if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) angles_sorted = false;
+    }
+    std::memcpy(lattice + (size_t)g * 9, p[7], 36);
+    a_off += n;
+    e_off += ed;
+    u_off += eu;
+    g_off += an;
+  }
+  flags_out[0] = edges_sorted ? 1 : 0;
+  flags_out[1] = angles_sorted ? 1 : 0;
+  return CHG_OK;
+}

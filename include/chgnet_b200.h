@@ -278,6 +278,16 @@ int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int3
                      int32_t* bond_graph);
 void chg_graph_free(chg_graph* g);
 
+/* host batch packer: B CrystalGraphs (HOST arrays, int32 / fp32, contiguous) -> the concatenated,
+ * offset-adjusted SoA of chg_batch in one pass (BatchedGraph.from_graphs, model.py:820-899, without
+ * per-graph tensor ops).  counts [B][4] = atoms, directed edges, undirected bonds, angles; ptrs [B][8] =
+ * atomic_number, atom_frac_coord, atom_graph, neighbor_image, directed2undirected, undirected2directed,
+ * bond_graph, lattice.  ibuf (int32) = z[N] owner[N] center[Ed] nbr[Ed] d2u[Ed] u2d[Eu] ang_atom[A]
+ * ang_i[A] ang_di[A] ang_j[A] ang_dj[A]; fbuf (fp32) = frac[N*3] image[Ed*3] lattice[B*9];
+ * flags_out[0/1] = edges sorted by centre / angles sorted by bond i within every graph.               */
+int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf,
+                        float* fbuf, int32_t* flags_out);
+
 /* ======================= training (reference trainer.py:398-411, 779-869) =======================
  * The reverse pass over activations is the one above (seeded with the loss instead of 1); these
  * entry points add the parameter gradients, the loss terms and the optimizer step for losses on

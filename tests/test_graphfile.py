@@ -37,3 +37,42 @@ def test_round_trip_and_batching(tmp_path):
     (tmp_path / "bad").write_bytes(b"not a pack")
     with pytest.raises(ValueError):
         GraphStore(str(tmp_path / "bad"))
+
+
+def test_native_host_packer_equals_torch_packing():
+    """chg_pack_batch_host (one C pass: concatenation, offsets, owners, sortedness flags) builds the same
+    DeviceBatch as the tensor-op path, also for unsorted graphs, reshaped empty graphs and fp64 inputs
+    (which fall back to the tensor-op path)."""
+    import dataclasses
+
+    from chgnet_b200.graph import CrystalGraph
+
+    graphs = graphgen.random_graphs(6, 4, 12, 6200)
+    graphs.append(graphgen.make_crystal_graph([3], np.zeros((1, 3)), np.eye(3) * 20.0))
+    g = graphs[2]
+    perm = torch.randperm(len(g.atom_graph), generator=torch.Generator().manual_seed(0))  # unsorted edges
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(len(perm))
+    bgp = g.bond_graph.clone()
+    bgp[:, 2], bgp[:, 4] = inv[bgp[:, 2].long()].int(), inv[bgp[:, 4].long()].int()
+    graphs[2] = CrystalGraph(atomic_number=g.atomic_number, atom_frac_coord=g.atom_frac_coord, atom_graph=g.atom_graph[perm].contiguous(),
+                             atom_graph_cutoff=6.0, neighbor_image=g.neighbor_image[perm].contiguous(),
+                             directed2undirected=g.directed2undirected[perm].contiguous(),
+                             undirected2directed=inv[g.undirected2directed.long()].int(), bond_graph=bgp,
+                             bond_graph_cutoff=3.0, lattice=g.lattice)
+
+    def same(gs):
+        a, b = build_batch(gs, "cpu", native_pack=True), build_batch(gs, "cpu", native_pack=False)
+        for f in dataclasses.fields(a):
+            x, y = getattr(a, f.name), getattr(b, f.name)
+            if torch.is_tensor(x):
+                assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y), f.name
+            elif f.name != "h2d_bytes":
+                assert x == y, f.name
+        return a
+
+    same(graphs)
+    same(graphs[-1:])  # only an isolated atom
+    g64 = graphs[0]
+    g64 = CrystalGraph(**{**g64.to_dict(), "atom_frac_coord": g64.atom_frac_coord.double(), "lattice": g64.lattice.double()})
+    assert same([g64, graphs[1]]).frac.dtype == torch.float32  # not packable by memcpy -> converted by the tensor-op path
