@@ -127,9 +127,12 @@ class Trainer:
                  stress_loss_ratio: float = 0.1, mag_loss_ratio: float = 0.1, optimizer: str = "Adam",
                  criterion: str = "MSE", learning_rate: float = 1e-3, weight_decay: float = 0.0,
                  betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, delta: float = 0.1,
+                 scheduler: str = "CosLR", scheduler_params: dict | None = None, epochs: int = 50,
                  process_group=None, **_: object) -> None:
         if optimizer != "Adam":
             raise NotImplementedError("chgnet_b200.Trainer implements optimizer='Adam' (the reference default)")
+        self.schedule = LRSchedule(scheduler, learning_rate, epochs, scheduler_params)
+        self.epochs = epochs
         self.model = model
         self.cfg = LossConfig(targets, criterion, energy_loss_ratio, force_loss_ratio, stress_loss_ratio,
                               mag_loss_ratio, delta)
@@ -203,11 +206,54 @@ class Trainer:
         model.mark_params_updated()
         return report
 
-    def train(self, loader, epochs: int = 1) -> list[dict]:
-        """``loader`` yields (graphs, targets) like the reference's collate_graphs batches
-        (dataset.py:763-788)."""
+    def scheduler_step(self) -> float:
+        """advance the learning-rate schedule by one tick (the reference ticks 10 times per epoch,
+        trainer.py:413-415); returns the new learning rate"""
+        self.lr = self.schedule.step()
+        return self.lr
+
+    def train(self, loader, epochs: int | None = None) -> list[dict]:
+        """``loader`` (a sized iterable) yields (graphs, targets) like the reference's collate_graphs
+        batches (dataset.py:763-788); the schedule is advanced every 1/10 of an epoch."""
         history = []
-        for _ in range(epochs):
-            for graphs, targets in loader:
+        n = len(loader)
+        ticks = {int(k * n // 10) for k in range(1, 11)}  # np.arange(1, 11) * len(loader) // 10
+        for _ in range(self.epochs if epochs is None else epochs):
+            for idx, (graphs, targets) in enumerate(loader):
                 history.append(self.train_step(graphs, targets))
+                if idx + 1 in ticks:
+                    self.scheduler_step()
         return history
+
+
+class LRSchedule:
+    """Closed forms of the reference's schedulers (trainer.py:165-205): CosineAnnealingLR with
+    ``T_max = 10 * epochs`` and ``eta_min = decay_fraction * lr`` (default), ExponentialLR, MultiStepLR."""
+
+    def __init__(self, kind: str, lr: float, epochs: int, params: dict | None = None) -> None:
+        import math
+
+        self.lr0, self.t, self._math = lr, 0, math
+        params = dict(params or {})
+        if kind in {"CosineAnnealingLR", "CosLR", "Cos", "cos"}:
+            self.kind, self.t_max = "cos", 10 * epochs
+            self.eta_min = params.get("decay_fraction", 1e-2) * lr
+        elif kind in {"ExponentialLR", "Exp", "Exponential"}:
+            self.kind, self.gamma = "exp", params.get("gamma", 0.98)
+        elif kind in {"MultiStepLR", "multistep"}:
+            self.kind = "multistep"
+            self.milestones = sorted(params.get("milestones", [4 * epochs, 6 * epochs, 8 * epochs, 9 * epochs]))
+            self.gamma = params.get("gamma", 0.3)
+        else:
+            raise NotImplementedError(kind)
+
+    def value(self, t: int) -> float:
+        if self.kind == "cos":
+            return self.eta_min + (self.lr0 - self.eta_min) * (1 + self._math.cos(self._math.pi * t / self.t_max)) / 2
+        if self.kind == "exp":
+            return self.lr0 * self.gamma**t
+        return self.lr0 * self.gamma ** sum(1 for m in self.milestones if m <= t)
+
+    def step(self) -> float:
+        self.t += 1
+        return self.value(self.t)

@@ -315,3 +315,23 @@ def test_trainer_step_host_logic_with_spec_kernels(monkeypatch):
     assert calls["n"] == n_before + 1 and report2["loss"] != report["loss"]  # new weights were re-packed and used
     with pytest.raises(ValueError):
         Trainer(model, targets="fx")
+
+
+def test_lr_schedules_match_torch():
+    from torch.optim.lr_scheduler import CosineAnnealingLR, ExponentialLR, MultiStepLR
+
+    from chgnet_b200.trainer import LRSchedule
+
+    epochs, lr = 3, 1e-3
+    for kind, make in (("CosLR", lambda o: CosineAnnealingLR(o, T_max=10 * epochs, eta_min=1e-2 * lr)),
+                       ("Exp", lambda o: ExponentialLR(o, gamma=0.98)),
+                       ("MultiStepLR", lambda o: MultiStepLR(o, milestones=[4 * epochs, 6 * epochs, 8 * epochs, 9 * epochs], gamma=0.3))):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=lr)
+        ref, mine = make(opt), LRSchedule(kind, lr, epochs)
+        for _ in range(10 * epochs):
+            opt.step()
+            ref.step()
+            assert mine.step() == pytest.approx(opt.param_groups[0]["lr"], rel=1e-9), kind
+    with pytest.raises(NotImplementedError):
+        LRSchedule("nope", lr, epochs)
