@@ -131,6 +131,11 @@ class Trainer:
                  process_group=None, **_: object) -> None:
         if optimizer != "Adam":
             raise NotImplementedError("chgnet_b200.Trainer implements optimizer='Adam' (the reference default)")
+        self.trainer_args = dict(targets=targets, energy_loss_ratio=energy_loss_ratio, force_loss_ratio=force_loss_ratio,
+                                 stress_loss_ratio=stress_loss_ratio, mag_loss_ratio=mag_loss_ratio, optimizer=optimizer,
+                                 criterion=criterion, learning_rate=learning_rate, weight_decay=weight_decay, betas=betas,
+                                 eps=eps, delta=delta, scheduler=scheduler, scheduler_params=scheduler_params, epochs=epochs)
+        self.training_history: list[dict] = []
         self.schedule = LRSchedule(scheduler, learning_rate, epochs, scheduler_params)
         self.epochs = epochs
         self.model = model
@@ -206,6 +211,37 @@ class Trainer:
         model.mark_params_updated()
         return report
 
+    # ------------------------------------------------------------------ checkpoint / resume (trainer.py:614-688)
+    def save(self, filename: str = "training_result.pth.tar") -> None:
+        """model (reference ``as_dict`` layout: loadable by ``CHGNet.from_file`` here and in the reference),
+        optimizer moments, schedule position, history, constructor arguments"""
+        by_name = lambda buf: {n: buf[o:o + sz].view(sh).detach().cpu().clone()  # noqa: E731
+                               for n, o, sz, sh in zip(self.names, self.offsets, self.sizes, self.shapes)}
+        state = {"model": {"model_args": self.model.model_args,
+                           "state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}},
+                 "optimizer": {"step": self.step_count, "exp_avg": by_name(self.exp_avg), "exp_avg_sq": by_name(self.exp_avg_sq)},
+                 "scheduler": {"t": self.schedule.t, "lr": self.lr},
+                 "training_history": self.training_history, "trainer_args": self.trainer_args}
+        torch.save(state, filename)
+
+    @classmethod
+    def load(cls, path: str, device=None, **overrides):
+        """Rebuild a trainer (model on ``device``, default: CUDA) and resume where ``save`` stopped."""
+        from chgnet_b200.model import CHGNet
+
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        model = CHGNet.from_dict(state["model"])
+        model = model.to(device if device is not None else "cuda")
+        trainer = cls(model, **{**state["trainer_args"], **overrides})
+        opt = state["optimizer"]
+        trainer.step_count = int(opt["step"])
+        for n, o, sz in zip(trainer.names, trainer.offsets, trainer.sizes):
+            trainer.exp_avg[o:o + sz] = opt["exp_avg"][n].reshape(-1).to(trainer.exp_avg.device)
+            trainer.exp_avg_sq[o:o + sz] = opt["exp_avg_sq"][n].reshape(-1).to(trainer.exp_avg.device)
+        trainer.schedule.t, trainer.lr = int(state["scheduler"]["t"]), float(state["scheduler"]["lr"])
+        trainer.training_history = list(state["training_history"])
+        return trainer
+
     def scheduler_step(self) -> float:
         """advance the learning-rate schedule by one tick (the reference ticks 10 times per epoch,
         trainer.py:413-415); returns the new learning rate"""
@@ -221,6 +257,7 @@ class Trainer:
         for _ in range(self.epochs if epochs is None else epochs):
             for idx, (graphs, targets) in enumerate(loader):
                 history.append(self.train_step(graphs, targets))
+                self.training_history.append(history[-1])
                 if idx + 1 in ticks:
                     self.scheduler_step()
         return history

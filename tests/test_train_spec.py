@@ -311,8 +311,30 @@ def test_trainer_step_host_logic_with_spec_kernels(monkeypatch):
     assert float(trainer.flat[mask].abs().max()) == 0.0
     assert torch.equal(sd["composition_model.fc.weight"], before["composition_model.fc.weight"])  # frozen
     n_before = calls["n"]
+    # checkpoint / resume: a trainer restored from the file continues bit for bit
+    import tempfile
+
+    ckpt = os.path.join(tempfile.mkdtemp(), "ckpt.pth.tar")
+    trainer.scheduler_step()
+    trainer.save(ckpt)
     report2 = trainer.train_step(graphs, lab)
     assert calls["n"] == n_before + 1 and report2["loss"] != report["loss"]  # new weights were re-packed and used
+    resumed = Trainer.load(ckpt, device="cpu")
+    assert resumed.step_count == 1 and resumed.lr == pytest.approx(trainer.lr) and resumed.lr < 1e-3
+    m2 = resumed.model
+    m2._engine, m2._engine_key = None, None
+
+    def spec_engine2():
+        if m2._engine is None or m2._engine_key is None:
+            m2._engine = Engine(pack_weights(m2.state_dict(), m2.model_args, device="cpu"), SpecKernels())
+            m2._engine_key = ("spec",)
+        return m2._engine
+
+    monkeypatch.setattr(m2, "_get_engine", spec_engine2)
+    report2b = resumed.train_step(graphs, lab)
+    assert report2b["loss"] == pytest.approx(report2["loss"], rel=1e-6)
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), m2.named_parameters()):
+        assert n1 == n2 and float((p1.detach() - p2.detach()).abs().max()) < 1e-7, n1
     with pytest.raises(ValueError):
         Trainer(model, targets="fx")
 
