@@ -6,10 +6,14 @@ JSON line.  A "step" is one pass of the hot path (forward + the force/stress rev
 over one batch of synthetic CrystalGraphs.
 
 Workloads (BASELINE.json `configs`):
-  c2  (default) batch = 64 random periodic cells, 40..60 atoms, cutoffs 6 A / 3 A   [configs[1]]
-  c3  batch = 256 random cells, 20..40 atoms                                       [configs[2]]
+  c3  (default) batch = 256 random cells, 20..40 atoms, cutoffs 6 A / 3 A          [configs[2]]
+      the config the 1 -> 8 GPU curve is quoted on and the largest batched single-GPU one
+  c2  batch = 64 random periodic cells, 40..60 atoms                               [configs[1]]
   c4  one 10,000-atom LiMnO2 supercell (10x5x25), sigma = 0.02 A displacements      [configs[3]]
+      (also attached to every c2 / c3 line as the extra key "c4": the north-star's 10k-atom targets)
   c1  the 8-atom LiMnO2 cell                                                       [configs[0]]
+  c5  fine-tuning step, batch = 128 (forward, CombinedLoss, double backward, all-reduce, Adam) [configs[4]]
+      (at N > 1 a few c5 steps also run after the inference legs -> extra key "collective")
 
 value      structures/s of the kernel path, batch descriptor already resident in HBM
 e2e        the same through ``CHGNet.predict_graph`` from host CrystalGraphs (host packing,
@@ -20,8 +24,9 @@ cpu_baseline / --impl reference
            the oracle port of the reference's torch CPU path (oracle/chgnet_oracle.py) on
            the host cores, on a bounded sample of the same workload
 
-Multi-GPU: one process per GPU (torchrun), graphs sharded by rank, no device-path
-collective (inference); time = max over ranks; weak scaling (each rank owns one batch).
+Multi-GPU: one process per GPU (torchrun).  The global batch (N x the workload's batch) is assigned to
+ranks by `partition_graphs` (greedy LPT on edges + 2.5 x angles, chgnet_b200/batch.py); no device-path
+collective for inference; time = max over ranks; weak scaling (per-GPU work fixed as N grows).
 """
 from __future__ import annotations
 
@@ -43,22 +48,53 @@ WEIGHTS = os.path.join(ROOT, "tests", "golden", "chgnet_0.3.0_weights.npz")
 L2_FLUSH_BYTES = 256 << 20
 
 
-def make_workload(name: str, rank: int):
+def make_workload(name: str, rank: int, backend: str = "native"):
+    """The workload's CrystalGraphs (deterministic; `rank` shifts the seeds).  backend="numpy" builds them
+    without the kernel library (the reference arm must not map the product's .so)."""
     from chgnet_b200 import graphgen
 
+    kw = {"backend": backend}
     if name == "c1":
         z, frac, lat = graphgen.limno2_structure()
-        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="mp-18767")], "LiMnO2 mp-18767, 8 atoms"
+        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="mp-18767", **kw)], "LiMnO2 mp-18767, 8 atoms"
     if name == "c2":
-        return graphgen.random_graphs(64, 40, 60, 1000 + 100 * rank), "batch=64 random periodic cells, 40..60 atoms, rho=0.10/A^3, cutoffs 6/3 A"
+        return graphgen.random_graphs(64, 40, 60, 1000 + 100 * rank, **kw), "batch=64 random periodic cells, 40..60 atoms, rho=0.10/A^3, cutoffs 6/3 A"
     if name == "c3":
-        return graphgen.random_graphs(256, 20, 40, 2000 + 1000 * rank), "batch=256 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A"
+        return graphgen.random_graphs(256, 20, 40, 2000 + 1000 * rank, **kw), "batch=256 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A"
     if name == "c4":
         z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000 + rank)
-        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="LiMnO2-10x5x25")], "LiMnO2 10x5x25 supercell, 10,000 atoms, sigma=0.02 A"
+        return [graphgen.make_crystal_graph(z, frac, lat, graph_id="LiMnO2-10x5x25", **kw)], "LiMnO2 10x5x25 supercell, 10,000 atoms, sigma=0.02 A"
     if name == "c5":
-        return graphgen.random_graphs(128, 20, 40, 5000 + 1000 * rank), "fine-tune batch=128 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A; targets 'efsm' (MSE, ratios 1/1/0.1/0.1), Adam lr 1e-3"
+        return graphgen.random_graphs(128, 20, 40, 5000 + 1000 * rank, **kw), "fine-tune batch=128 random periodic cells, 20..40 atoms, rho=0.10/A^3, cutoffs 6/3 A; targets 'efsm' (MSE, ratios 1/1/0.1/0.1), Adam lr 1e-3"
     raise SystemExit(f"unknown workload {name}")
+
+
+L2_NOTE = "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations"
+
+
+def bench_config(workload: str, desc: str, per_job: dict, world: int, task: str = "efs") -> dict:
+    """The `config` object, IDENTICAL in the product arm and in the reference arm (the driver compares them):
+    the workload, the task, the whole-job sizes, the weights and how the L2 is treated between timed steps."""
+    return {"workload": f"{workload}: {desc}", "task": task, "whole_job": per_job, "weights": "CHGNet 0.3.0",
+            "l2": L2_NOTE, "parallelism": f"graph-sharded x{world} (LPT partition of the global batch), no inference collective"}
+
+
+def sharded_workload(name: str, rank: int, world: int, backend: str = "native"):
+    """(my graphs, description, whole-job counts).  N > 1: the global batch = the N per-rank batches of
+    `make_workload`; every rank builds it, costs it, and keeps the share `partition_graphs` (greedy LPT)
+    assigns to it - the partitioner of chgnet_b200/parallel.py::predict_sharded."""
+    from chgnet_b200.batch import graph_cost, partition_graphs
+
+    if world == 1 or name in ("c1", "c4"):  # a single structure does not shard: replicas (DESIGN.md §7)
+        graphs, desc = make_workload(name, rank, backend)
+        c = counts(graphs)
+        return graphs, desc, {k: v * world for k, v in c.items()}
+    allg: list = []
+    for r in range(world):
+        g, desc = make_workload(name, r, backend)
+        allg += g
+    parts = partition_graphs([graph_cost(g) for g in allg], world)
+    return [allg[i] for i in parts[rank]], desc, counts(allg)
 
 
 def train_labels(preds, seed: int):
@@ -78,8 +114,8 @@ def run_reference_train(args) -> None:
     cores: oracle forward (train mode) -> CombinedLoss('em', MSE) -> backward -> torch Adam."""
     from oracle import chgnet_oracle as orc
 
-    graphs, desc = make_workload("c5", 0)
-    sample = graphs[: max(1, min(len(graphs), args.cpu_sample))]
+    graphs, desc = make_workload("c5", 0, backend="numpy")  # numpy builder: the product .so is never mapped here
+    sample = graphs[: max(1, min(len(graphs), args.cpu_sample if args.cpu_sample > 0 else 4))]
     w = orc.load_weights_npz(WEIGHTS)
     base = orc.predict_graph(w, sample, "efsm", batch_size=len(sample))
     lab = train_labels(base, 5)
@@ -108,15 +144,19 @@ def run_reference_train(args) -> None:
         "impl": "reference", "metric": "train_structures_per_sec_EFSM", "value": value, "unit": "structures/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c5: {desc}", "task": "train efsm"},
+        "config": bench_config("c5", desc, {k: v * int(os.environ.get("WORLD_SIZE", 1)) for k, v in counts(graphs).items()},
+                               int(os.environ.get("WORLD_SIZE", 1)), task="train efsm"),
         "cpu_baseline": {"value": value, "unit": "structures/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sdesc},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0, "product_so_mapped": product_so_mapped()}))
 
 
-def run_train(args, rank: int, world: int, local_rank: int) -> None:
+def run_train(args, rank: int, world: int, local_rank: int, light: bool = False):
     """--workload c5: one fine-tuning step per 'step' (forward, CombinedLoss, parameter gradients,
-    one gradient all-reduce over NCCL, fused Adam, weight re-pack)."""
+    one gradient all-reduce over NCCL, fused Adam, weight re-pack).
+
+    ``light=True`` (the "collective" leg appended to a multi-GPU inference run): only the timed resident
+    steps, with the all-reduce bracketed by its own CUDA events; returns a dict on every rank, prints nothing."""
     import contextlib
     import io
 
@@ -147,26 +187,34 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
     batch = build_batch(graphs, dev, with_reverse=True)
     tg_dev = trainer._targets(lab, batch.atoms_per_graph, dev)
 
+    ar_events: list = []
+
     def step_resident():
         engine = model._get_engine()  # re-packs the weights the previous Adam step changed
         report_, G = loss_and_grads(engine, batch, trainer.cfg, tg_dev, model.is_intensive, None)
         fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
         if world > 1:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
             dist.all_reduce(fg)
+            a1.record()
+            ar_events.append((a0, a1, fg.numel() * fg.element_size()))
         trainer.step_count += 1
         K.adam_step(trainer.flat, fg, trainer.exp_avg, trainer.exp_avg_sq, trainer.lr, 0.9, 0.999, 1e-8, 0.0, trainer.step_count)
         model.mark_params_updated()
         return report_
 
-    for _ in range(max(args.warmup, 3)):
+    n_steps = min(args.steps, 5) if light else args.steps
+    for _ in range(3 if light else max(args.warmup, 3)):
         flush()
         step_resident()
     barrier()
+    ar_events.clear()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = K.launches
     elapsed_ms = 0.0
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -177,10 +225,22 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
     barrier()
     launches = K.launches - launches0
     clocks = sampler.stop()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    ar_us = [a0.elapsed_time(a1) * 1e3 for a0, a1, _ in ar_events]
+    t = torch.tensor([elapsed_ms, max(ar_us) if ar_us else 0.0, float(np.median(ar_us)) if ar_us else 0.0],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = float(t[0].item()) / n_steps
+    collective = None
+    if world > 1:
+        collective = {"op": "all_reduce(SUM) of the flat fp32 gradient buffer", "backend": "nccl", "bytes": int(ar_events[0][2]),
+                      "us": round(float(t[2].item()), 1), "us_max": round(float(t[1].item()), 1),
+                      "timing": "CUDA events around dist.all_reduce on the launching stream, median over steps, max over ranks "
+                                "(includes waiting for the slowest rank's gradients)",
+                      "train_ms_per_step": round(ms_per_step, 3), "train_structures_per_s": round(c["graphs"] * world / (ms_per_step * 1e-3), 1),
+                      "steps": n_steps, "workload": f"c5: {desc}", "per_gpu": c}
+    if light:
+        return collective
 
     # end to end: Trainer.train_step from host graphs + host labels, report read back every step
     targets = lab
@@ -249,13 +309,12 @@ def run_train(args, rank: int, world: int, local_rank: int) -> None:
         "metric": "train_structures_per_sec_EFSM", "value": total / (ms_per_step * 1e-3), "unit": "structures/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"c5: {desc}", "task": "train efsm", "per_gpu": c, "weights": "CHGNet 0.3.0",
-                   "l2": "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations",
-                   "parallelism": f"graph-sharded x{world}, one all-reduce of the flat gradient buffer per step",
-                   "second_order": "tangent pass + reverse over (primal, tangent) for the force / stress loss terms"},
+        "config": bench_config("c5", desc, {k: v * world for k, v in c.items()}, world, task="train efsm"),
+        "train": {"collective": "one all-reduce of the flat gradient buffer per step",
+                  "second_order": "tangent pass + reverse over (primal, tangent) for the force / stress loss terms"},
         "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "structures/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 48, "api": "Trainer.train_step(list[CrystalGraph] on host, labels on host)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None, "collective": collective,
         "last_report": rep_last, "breakdown": breakdown, "kernel_shares": shares}), flush=True)
     if world > 1:
         dist.barrier()
@@ -316,19 +375,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def pick_cpu_threads(fn) -> int:
-    """The torch CPU path does not scale to every core of a big host (tiny ops, OpenMP
-    fork/join): time `fn` once per candidate thread count and keep the fastest, so the CPU
-    baseline is the reference at its best, not at `os.cpu_count()`."""
+def pick_cpu_threads(fn, repeats: int = 3) -> int:
+    """The torch CPU path does not scale to every core of a big host (tiny ops, OpenMP fork/join): time
+    `fn` per candidate thread count (one warm call, then the best of `repeats` timed calls) and keep the
+    fastest, so the CPU baseline is the reference at its best, not at `os.cpu_count()`."""
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
         fn()  # warm
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(max(1, repeats)):
+            t0 = time.perf_counter()
+            fn()
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
@@ -344,31 +405,67 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------
+def product_so_mapped() -> bool:
+    """True if this process has the product's kernel library mapped (the reference arm must not)."""
+    try:
+        with open("/proc/self/maps") as f:
+            return "libchgnet_b200" in f.read()
+    except OSError:
+        return False
+
+
+REF_BUDGET_S = 900.0  # wall-clock the reference arm may spend on its warm-up + timed steps
+
+
 def run_reference(args, rank: int, world: int) -> None:
-    """--impl reference: the reference's CPU path (oracle port), bounded sample per step."""
+    """--impl reference: the reference's CPU path (oracle port = the reference's torch ops) on the host
+    cores.  Inputs are built with the numpy builder, so the product's .so is never mapped by this process.
+    Each step is `predict_graph` over the FULL batch when warm-up + steps fit REF_BUDGET_S; otherwise over the
+    largest leading power-of-two fraction that does (stated in `sample`)."""
     if rank != 0:
         return
     from oracle import chgnet_oracle as orc
 
-    graphs, desc = make_workload(args.workload, 0)
-    sample = graphs[: max(1, min(len(graphs), args.cpu_sample))]
+    graphs, desc = make_workload(args.workload, 0, backend="numpy")
+    whole = {k: v * world for k, v in counts(graphs).items()} if (world == 1 or args.workload in ("c1", "c4")) else None
+    if whole is None:
+        allg = list(graphs)
+        for r in range(1, world):
+            allg += make_workload(args.workload, r, backend="numpy")[0]
+        whole = counts(allg)
+    w = orc.load_weights_npz(WEIGHTS)
     if args.workload == "c4":
         from chgnet_b200 import graphgen
 
         z, frac, lat = graphgen.limno2_structure((5, 4, 3), 0.02, 4000)
-        sample = [graphgen.make_crystal_graph(z, frac, lat)]
-        desc_s = "LiMnO2 5x4x3 supercell (480 atoms) — largest cell timed on the CPU; value scaled by atoms"
+        sample = [graphgen.make_crystal_graph(z, frac, lat, backend="numpy")]
+        probe = sample
+        desc_s = "LiMnO2 5x4x3 supercell (480 atoms) - largest cell timed on the CPU; value scaled by atoms"
     else:
-        desc_s = f"first {len(sample)} graphs of the batch per step"
-    w = orc.load_weights_npz(WEIGHTS)
-    probe = sample[:2]
+        probe = graphs[:2]
     threads = pick_cpu_threads(lambda: orc.predict_graph(w, probe, "efs", batch_size=len(probe)))
-    desc_s += f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep)"
+    if args.workload != "c4":
+        # size the per-step sample from a measured rate: full batch if (warmup + steps) of it fit the budget
+        n_probe = min(len(graphs), 8)
+        orc.predict_graph(w, graphs[:n_probe], "efs", batch_size=n_probe)
+        t0 = time.perf_counter()
+        orc.predict_graph(w, graphs[:n_probe], "efs", batch_size=n_probe)
+        per_graph = (time.perf_counter() - t0) / n_probe
+        n = len(graphs) if args.cpu_sample <= 0 else min(len(graphs), args.cpu_sample)
+        while n > 8 and per_graph * n * (args.steps + args.warmup) > REF_BUDGET_S:
+            n = max(8, n // 2)
+        sample = graphs[:n]
+        why = ("--cpu-sample" if args.cpu_sample > 0 and n == args.cpu_sample else
+               f"the full batch would exceed {REF_BUDGET_S:.0f} s for {args.steps}+{args.warmup} steps at {1.0 / per_graph:.1f} structures/s")
+        desc_s = ("the full batch per step" if n == len(graphs) else
+                  f"first {n} of {len(graphs)} graphs per step ({n / len(graphs):.3f} of the batch: {why})")
+    desc_s += f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep, best of 3 per candidate)"
+    bs = min(len(sample), 64)  # predict_graph's batching loop (model.py:634-645); 64 per forward (reference default 16)
     for _ in range(args.warmup):
-        orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+        orc.predict_graph(w, sample, "efs", batch_size=bs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+        orc.predict_graph(w, sample, "efs", batch_size=bs)
     dt = (time.perf_counter() - t0) / args.steps
     c = counts(sample)
     value = c["graphs"] / dt
@@ -378,11 +475,11 @@ def run_reference(args, rank: int, world: int) -> None:
         "impl": "reference", "metric": "structures_per_sec_EFS", "value": value, "unit": "structures/s",
         "atoms_per_s": c["atoms"] / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "task": "efs"},
+        "data": "synthetic", "config": bench_config(args.workload, desc, whole, world),
         "cpu_baseline": {"value": value, "unit": "structures/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": desc_s},
+                         "sample": desc_s, "sample_counts": c},
         "e2e": {"value": value, "unit": "structures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "product_so_mapped": product_so_mapped(),
     }
     print(json.dumps(line))
 
@@ -458,24 +555,16 @@ class EventKernels:
                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
 
 
-def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+def infer_leg(model, graphs, dev, local_rank: int, world: int, steps: int, warmup: int) -> dict:
+    """Times one workload two ways: the kernel path on a resident batch descriptor (CUDA events per step, L2
+    flushed between steps) and `CHGNet.predict_graph` from host CrystalGraphs (wall clock per step, device
+    synchronised on both sides; host packing, H2D, CSR build, kernels, D2H inside).  Max over ranks."""
     import torch.distributed as dist
 
     from chgnet_b200.batch import build_batch
-    from chgnet_b200.engine import EV_A3_TO_GPA, Engine
-    from chgnet_b200.model import CHGNet
+    from chgnet_b200.engine import EV_A3_TO_GPA
 
-    dev = torch.device(f"cuda:{local_rank}")
-    torch.cuda.set_device(dev)
-    import contextlib
-    import io
-
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev).eval()
-    graphs, desc = make_workload(args.workload, rank)
-    c = counts(graphs)
-    engine = model._get_engine()
-    K = engine.K
+    K = model._get_engine().K
     flush = L2Flush(dev)
 
     def barrier():
@@ -483,13 +572,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- kernel path, inputs resident in HBM ----------------
     batch = build_batch(graphs, dev, with_reverse=True)
-    if args.scatter_only:  # ncu capture target: only the AtomConv scatter-reduce launches
-        ms, nbytes = time_scatter_kernel(K, batch, n_iter=5)
-        print(json.dumps({"scatter_only": True, "us_per_launch": ms * 1e3, "algorithmic_bytes": nbytes}))
-        return
-
     native = model._get_native()  # the product's inference path: ONE chg_forward call per step
 
     def step_resident():
@@ -498,7 +581,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         stress = (out["virial"].view(-1, 3, 3) * scale[:, None, None]).to(torch.float32)
         return out["energy"], out["force"].to(torch.float32), stress
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         flush()
         step_resident()
     barrier()
@@ -507,7 +590,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     launches0 = K.launches
     elapsed_ms = 0.0
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -519,10 +602,6 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     launches = K.launches - launches0
     clocks = sampler.stop()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
 
     # ---------------- end to end through the public API ----------------
     def step_e2e():
@@ -533,22 +612,78 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     d2h = sum(int(v.nbytes) for p in preds for v in p.values())
     h2d = int(model.last_batch.h2d_bytes)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2e_ms = 0.0
+    for _ in range(steps):
         flush()
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        preds = step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = float(t.item()) / args.steps
+    return {"ms_per_step": float(t[0].item()) / steps, "e2e_ms_per_step": float(t[1].item()) / steps, "launches": int(launches),
+            "clocks": clocks, "wall_ms": wall_ms, "h2d": h2d, "d2h": d2h, "preds": preds, "batch": batch}
+
+
+def scatter_roofline(K, batch, workload: str, dev) -> dict:
+    """Roofline record of the AtomConv scatter-reduce kernel at this batch's size."""
+    peaks, peak_kind = measured_peaks()
+    sc_ms, sc_bytes = time_scatter_kernel(K, batch)
+    achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "scatter_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+        with open(tpath) as f:
+            traffic = json.load(f).get(workload, {}).get("dram_bytes_per_launch")
+    return {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm",
+            "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth",
+            "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
+            "us_per_launch": round(sc_ms * 1e3, 2), "algorithmic_bytes": sc_bytes,
+            "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+    import contextlib
+    import io
+
+    import torch.distributed as dist
+
+    from chgnet_b200.batch import build_batch
+    from chgnet_b200.engine import Engine
+    from chgnet_b200.model import CHGNet
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev).eval()
+    graphs, desc, whole = sharded_workload(args.workload, rank, world)
+    c = counts(graphs)
+    engine = model._get_engine()
+    K = engine.K
+
+    if args.scatter_only:  # ncu capture target: only the AtomConv scatter-reduce launches
+        batch = build_batch(graphs, dev, with_reverse=True)
+        ms, nbytes = time_scatter_kernel(K, batch, n_iter=5)
+        print(json.dumps({"scatter_only": True, "us_per_launch": ms * 1e3, "algorithmic_bytes": nbytes}))
+        return
+
+    leg = infer_leg(model, graphs, dev, local_rank, world, args.steps, args.warmup)
+    batch = leg["batch"]
+    ms_per_step, e2e_ms_per_step = leg["ms_per_step"], leg["e2e_ms_per_step"]
+
+    # ---------------- N > 1: the path's one collective (c5 fine-tuning step), every rank ----------------
+    collective = None
+    if world > 1 and not args.no_collective:
+        collective = run_train(args, rank, world, local_rank, light=True)
 
     if rank != 0:
         if world > 1:
-            dist.barrier()  # wait for rank 0's extra legs (roofline, shares, CPU baseline)
+            dist.barrier()  # wait for rank 0's extra legs (roofline, shares, c4, CPU baseline)
         return
     # e2e breakdown (one synchronised pass, outside the timed loops)
+    native = model._get_native()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     bb = build_batch(graphs, dev, with_reverse=True)
@@ -561,21 +696,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     t3 = time.perf_counter()
     breakdown = {"pack_h2d_csr_ms": (t1 - t0) * 1e3, "kernels_ms": (t2 - t1) * 1e3, "d2h_ms": (t3 - t2) * 1e3}
     # ---------------- roofline of the AtomConv scatter kernel ----------------
-    peaks, peak_kind = measured_peaks()
-    sc_ms, sc_bytes = time_scatter_kernel(K, batch)
-    achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "scatter_traffic.json")
-    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
-    roofline = {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm",
-                "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth",
-                "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
-                "us_per_launch": round(sc_ms * 1e3, 2), "algorithmic_bytes": sc_bytes,
-                "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+    roofline = scatter_roofline(K, batch, args.workload, dev)
+    peaks, _ = measured_peaks()
     # the same kernel at the AtomConv size of the 10,000-atom cell (84 edges per atom), on
-    # synthetic uniform segments — the size the north-star's >= 50 % target is quoted for
+    # synthetic uniform segments - the size the north-star's >= 50 % target is quoted for
     if args.workload != "c4":
         class _B:  # minimal stand-in carrying the three fields time_scatter_kernel reads
             z = batch.z
@@ -591,34 +715,60 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     Engine(engine.pw, ek).run(batch, need_grad=True)
     shares = ek.table()
 
-    # ---------------- CPU baseline: oracle port on the host cores ----------------
+    # ---------------- the 10,000-atom cell (BASELINE configs[3]) as an extra key ----------------
+    c4 = None
+    if args.workload in ("c2", "c3") and not args.no_c4:
+        g4, d4 = make_workload("c4", 0)
+        c4c = counts(g4)
+        l4 = infer_leg(model, g4, dev, local_rank, 1, min(args.steps, 10), 3)
+        c4 = {"workload": f"c4: {d4}", "counts": c4c, "ms_per_step": round(l4["ms_per_step"], 4),
+              "atoms_per_s": round(c4c["atoms"] / (l4["ms_per_step"] * 1e-3), 1),
+              "structures_per_s": round(1e3 / l4["ms_per_step"], 2), "gpu_launches_per_step": l4["launches"] // min(args.steps, 10),
+              "e2e": {"ms_per_step": round(l4["e2e_ms_per_step"], 4), "atoms_per_s": round(c4c["atoms"] / (l4["e2e_ms_per_step"] * 1e-3), 1),
+                      "h2d_bytes_per_step": l4["h2d"], "d2h_bytes_per_step": l4["d2h"],
+                      "api": "CHGNet.predict_graph(CrystalGraph on host, task='efs')"},
+              "roofline": scatter_roofline(K, l4["batch"], "c4", dev), "clocks": l4["clocks"], "n_gpus": 1,
+              "note": "one structure does not shard: rank 0 alone (replicas only, DESIGN.md §7)"}
+
+    # ---------------- CPU baseline + parity: oracle port on the host cores ----------------
     cpu = None
     torch_cuda = None
+    parity = None
     if not args.no_cpu_baseline:
         from oracle import chgnet_oracle as orc
 
         w = orc.load_weights_npz(WEIGHTS)
+        n_s = min(len(graphs), args.cpu_sample if args.cpu_sample > 0 else 8)
         if args.workload == "c4":
             from chgnet_b200 import graphgen
 
             z, frac, lat = graphgen.limno2_structure((5, 4, 3), 0.02, 4000)
             sample = [graphgen.make_crystal_graph(z, frac, lat)]
             sdesc = "LiMnO2 5x4x3 (480 atoms), 1 warm-up + 2 timed; structures/s scaled by atoms to the 10,000-atom cell"
+            gpu_sample = model.predict_graph(sample, task="efs", batch_size=1)
         else:
-            sample = graphs[: min(len(graphs), args.cpu_sample)]
+            sample = graphs[:n_s]
             sdesc = f"first {len(sample)} graphs of the batch, 1 warm-up + 2 timed predict_graph(task='efs') calls"
+            gpu_sample = leg["preds"][:n_s]  # what the timed e2e call returned for the same graphs
         probe = sample[:2]
         threads = pick_cpu_threads(lambda: orc.predict_graph(w, probe, "efs", batch_size=len(probe)))
-        sdesc += f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep)"
+        sdesc += f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep, best of 3 per candidate)"
         orc.predict_graph(w, sample, "efs", batch_size=len(sample))
         t0 = time.perf_counter()
         for _ in range(2):
-            orc.predict_graph(w, sample, "efs", batch_size=len(sample))
+            ref_sample = orc.predict_graph(w, sample, "efs", batch_size=len(sample))
         dt = (time.perf_counter() - t0) / 2
         cs = counts(sample)
         v = cs["graphs"] / dt if args.workload != "c4" else (cs["atoms"] / dt) / c["atoms"]
         cpu = {"value": v, "unit": "structures/s", "atoms_per_s": cs["atoms"] / dt, "cores": torch.get_num_threads(),
                "kind": "port", "sample": sdesc}
+        # parity of the timed GPU outputs against the CPU baseline's outputs on the same graphs
+        def worst(k):
+            return max(float(np.max(np.abs(np.asarray(a[k], np.float64) - np.asarray(b[k], np.float64)))) for a, b in zip(gpu_sample, ref_sample))
+        parity = {"e": worst("e"), "f": worst("f"), "s": worst("s"), "unit": "eV/atom, eV/A, GPa (max abs)",
+                  "vs": f"oracle port (fp32 torch CPU = the reference's arithmetic) on {len(sample)} graph(s) of this run",
+                  "tolerance": {"e": 1e-4, "f": 1e-3, "s": 1e-3},
+                  "ok": bool(worst("e") < 1e-4 and worst("f") < 1e-3 and worst("s") < 1e-3)}
         # the realistic incumbent: the reference's torch ops on the SAME B200 (stock PyTorch CUDA)
         if args.workload != "c4":
             try:
@@ -632,26 +782,27 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                 dtc = (time.perf_counter() - t0) / 3
                 torch_cuda = {"value": c["graphs"] / dtc, "unit": "structures/s", "ms_per_step": dtc * 1e3,
                               "what": "oracle port = the reference's torch ops and per-graph batching loop, stock PyTorch "
-                                      "CUDA on the same B200, fp32, host graphs in / numpy out (compare with e2e)"}
+                                      "CUDA on the same B200, fp32, host graphs in / numpy out, this rank's share (compare with e2e / n_gpus)"}
             except Exception as exc:  # reported, never fatal for the bench line
                 torch_cuda = {"unavailable": repr(exc)[:200]}
 
-    total_graphs = c["graphs"] * world
+    total_graphs = whole["graphs"]
     value = total_graphs / (ms_per_step * 1e-3)
+    cfg = bench_config(args.workload, desc, whole, world)
     line = {
         "metric": "structures_per_sec_EFS", "value": value, "unit": "structures/s",
-        "atoms_per_s": c["atoms"] * world / (ms_per_step * 1e-3),
+        "atoms_per_s": whole["atoms"] / (ms_per_step * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "task": "efs", "per_gpu": c, "weights": "CHGNet 0.3.0",
-                   "l2": "256 MiB buffer written, then 256 MiB read (clean lines), between timed iterations", "parallelism": f"graph-sharded x{world}",
-                   "engine": "native chg_forward (one C call per step); kernel_shares via the Python schedule of the same kernels"},
+        "config": cfg, "rank0_share": c,
+        "engine": "native chg_forward (one C call per step); kernel_shares via the Python schedule of the same kernels",
         "e2e": {"value": total_graphs / (e2e_ms_per_step * 1e-3), "unit": "structures/s",
-                "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "CHGNet.predict_graph(list[CrystalGraph] on host, task='efs')", "breakdown": breakdown},
-        "gpu_launches": int(launches), "wall_ms_timed_region": wall_ms,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "torch_cuda_baseline": torch_cuda,
-        "kernel_shares": shares,
+                "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": leg["h2d"], "d2h_bytes_per_step": leg["d2h"],
+                "api": "CHGNet.predict_graph(list[CrystalGraph] on host, task='efs')", "breakdown": breakdown,
+                "over_kernel_path": round(e2e_ms_per_step / ms_per_step, 3)},
+        "gpu_launches": leg["launches"], "wall_ms_timed_region": leg["wall_ms"],
+        "clocks": leg["clocks"], "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "c4": c4, "collective": collective,
+        "torch_cuda_baseline": torch_cuda, "kernel_shares": shares,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -664,9 +815,11 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("CHGNET_BENCH_WORKLOAD", "c2"), choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--cpu-sample", type=int, default=8)
+    ap.add_argument("--workload", default=os.environ.get("CHGNET_BENCH_WORKLOAD", "c3"), choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reference arm: graphs per step (0 = as many as fit the time budget); cpu_baseline leg of the product arm: 8 when 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 10,000-atom extra leg of a c2 / c3 run")
+    ap.add_argument("--no-collective", action="store_true", help="N > 1: skip the c5 all-reduce leg")
     ap.add_argument("--scatter-only", action="store_true", help="run only the AtomConv scatter kernel timing (ncu target)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -109,16 +109,26 @@ class CudaKernels:
 
     name = "cuda"
 
-    def __init__(self) -> None:
+    def __init__(self, device: torch.device | str | int | None = None) -> None:
+        """``device``: the CUDA device whose tensors this object will be handed (default: the current one).
+        Every launch runs with that device current and on ITS current stream, whatever the process's
+        current device is (``CHGNet.load(use_device='cuda:1')`` in a process sitting on cuda:0)."""
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise ChgnetB200Error("chgnet_b200 needs a CUDA device (B200 / sm_100a); none is visible")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ChgnetB200Error(f"chgnet_b200 kernels run on CUDA devices only (got {dev})")
+        self.device_index = torch.cuda.current_device() if dev.index is None else dev.index
 
     # ------------------------------------------------------------------
     def _stream(self):
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(self.device_index).cuda_stream
 
     def _call(self, name: str, *args) -> None:
+        if torch.cuda.current_device() != self.device_index:
+            with torch.cuda.device(self.device_index):
+                return self._call(name, *args)
         rc = getattr(self.lib, name)(*args, self._stream())
         if rc != 0:
             raise ChgnetB200Error(f"{name} failed ({rc}): {self.lib.chg_last_error().decode()}")

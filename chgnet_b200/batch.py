@@ -78,6 +78,8 @@ class DeviceBatch:
     h2d_bytes: int = 0
 
 
+MAX_Z = 94  # rows of the atom embedding / AtomRef tables (reference encoders.py:22-32)
+
 _STAGING: dict = {}  # (dtype, pinned) -> [buffer, event of the last H2D copy that read it]
 
 
@@ -249,7 +251,8 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
                 if tail is not None:
                     host[off : off + tail.size] = tail
                     views["_tail"] = (off, tail.size)
-                dbuf = buf.to(device, non_blocking=True)
+                # a CPU "device" would alias the reused staging buffer: copy instead
+                dbuf = buf.clone() if device.type == "cpu" else buf.to(device, non_blocking=True)
                 _mark_staging_in_flight(dtype, pin, device)
                 return dbuf, views, host
             buf = torch.empty(total, dtype=dtype, device=src_dev)
@@ -307,6 +310,11 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
             return torch.repeat_interleave(vals, cnt[which], output_size=total).to(torch.int32)
 
         z = iview("z")
+        if N:
+            zsrc = ihost[iv["z"][0] : iv["z"][0] + N] if ihost is not None else z
+            zmin, zmax = int(zsrc.min()), int(zsrc.max())
+            if zmin < 1 or zmax > MAX_Z:
+                raise IndexError(f"index out of range in self: atomic numbers span [{zmin}, {zmax}], outside [1, {MAX_Z}]")
         owner = rep(torch.arange(B, device=device), 0, N)
         ag = iview("ag").view(Ed, 2)
         e_atom_off = rep(atom_off, 1, Ed)
@@ -338,10 +346,13 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
                             for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
                                       g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
-        flags = (ctypes.c_int32 * 2)()
+        flags = (ctypes.c_int32 * 3)()
         rc = lib.chg_pack_batch_host(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(), flags)
         if rc != 0:
             raise RuntimeError(f"chg_pack_batch_host failed: {lib.chg_last_error().decode()}")
+        if flags[2] >= 0:  # nn.Embedding(94, .) of the reference raises the same (tests/test_encoders.py:25-28)
+            raise IndexError(f"index out of range in self: atomic number {int(ibuf_h[flags[2]])} of atom {int(flags[2])} "
+                             f"is outside [1, {MAX_Z}]")
         on_cpu = device.type == "cpu"  # a CPU "device" would alias the reused staging buffer: copy instead
         ibuf = ibuf_h[:n_int].clone() if on_cpu else ibuf_h[:n_int].to(device, non_blocking=True)
         _mark_staging_in_flight(torch.int32, pin, device)

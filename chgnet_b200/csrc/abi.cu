@@ -21,13 +21,14 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-int sm_count() {
-  static int n = 0;
+int sm_count() {  // of the CURRENT device (cached per device ordinal)
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -67,5 +68,5 @@ extern "C" int chg_set_option(const char* name, int32_t value) {
 }
 
 extern "C" const char* chg_last_error(void) { return chg::g_err; }
-extern "C" int chg_abi_version(void) { return 2; }
+extern "C" int chg_abi_version(void) { return 3; }
 extern "C" int64_t chg_launch_count(void) { return chg::g_launches.load(std::memory_order_relaxed); }

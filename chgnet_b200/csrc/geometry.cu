@@ -18,7 +18,11 @@ __global__ void embed_atoms_kernel(const int32_t* __restrict__ z, const float* _
   const int atom = idx >> 4, c4 = idx & 15;
   if (atom >= n_atoms) return;
   const int row = z[atom] - 1;
-  stg4(x + (size_t)atom * 64 + c4 * 4, ldg4(emb + (size_t)row * 64 + c4 * 4));
+  // Z outside [1, 94]: the host raises IndexError before launching (batch.py, reference tests/test_encoders.py:25-28);
+  // a raw C-ABI caller gets NaN features instead of an out-of-bounds read
+  const float qnan = __int_as_float(0x7fc00000);
+  const float4 v = (row >= 0 && row < CHG_MAX_Z) ? ldg4(emb + (size_t)row * 64 + c4 * 4) : make_float4(qnan, qnan, qnan, qnan);
+  stg4(x + (size_t)atom * 64 + c4 * 4, v);
 }
 
 __global__ void edge_geometry_kernel(const float* __restrict__ frac, const float* __restrict__ lattice,

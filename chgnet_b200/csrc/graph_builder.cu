@@ -331,6 +331,7 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
   float* image = frac + N * 3;
   float* lattice = image + Ed * 3;
   bool edges_sorted = true, angles_sorted = true;
+  int64_t bad_z = -1;
   int64_t a_off = 0, e_off = 0, u_off = 0, g_off = 0;
   for (int g = 0; g < n_graphs; ++g) {
     const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
@@ -338,7 +339,11 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
     if (n > 0) {
       std::memcpy(z + a_off, p[0], (size_t)n * 4);
       std::memcpy(frac + a_off * 3, p[1], (size_t)n * 12);
-      for (int64_t i = 0; i < n; ++i) owner[a_off + i] = g;
+      for (int64_t i = 0; i < n; ++i) {
+        owner[a_off + i] = g;
+        const int32_t zi = z[a_off + i];
+        if ((zi < 1 || zi > CHG_MAX_Z) && bad_z < 0) bad_z = a_off + i;
+      }
     }
     const int32_t* ag = static_cast<const int32_t*>(p[2]);
     const int32_t* du = static_cast<const int32_t*>(p[4]);
@@ -368,5 +373,6 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
   }
   flags_out[0] = edges_sorted ? 1 : 0;
   flags_out[1] = angles_sorted ? 1 : 0;
+  flags_out[2] = (int32_t)bad_z;
   return CHG_OK;
 }

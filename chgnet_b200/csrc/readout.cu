@@ -70,7 +70,10 @@ readout_kernel(const float* __restrict__ x, const int32_t* __restrict__ z, const
       site_e[atom] = se;
       const int g = owner[atom];
       atomicAdd(e_graph + g, (double)se);
-      atomicAdd(e_ref + g, (double)atom_ref[z[atom] - 1]);
+      {
+        const int zi = z[atom] - 1;  // range-checked on the host (IndexError); NaN for raw C-ABI callers
+        atomicAdd(e_ref + g, (zi >= 0 && zi < CHG_MAX_Z) ? (double)atom_ref[zi] : (double)__int_as_float(0x7fc00000));
+      }
     }
     if (need_grad) {
       // g_h_last = w_last; walk back: g_z = g_h * silu'(z); g_h_prev[k] = sum_n g_z[n] W[n][k]

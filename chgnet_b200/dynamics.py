@@ -121,8 +121,9 @@ class CHGNetCalculator(_Base):
 
         graph = graphgen.make_crystal_graph(numbers, frac, cell, atom_graph_cutoff=self.model.graph_converter.atom_graph_cutoff,
                                             bond_graph_cutoff=self.model.graph_converter.bond_graph_cutoff)
-        if self.on_isolated_atoms != "ignore" and len(graph.atom_graph):
-            isolated = set(range(len(numbers))) - set(graph.atom_graph[:, 0].tolist())
+        if self.on_isolated_atoms != "ignore":
+            centers = graph.atom_graph[:, 0].tolist() if graph.atom_graph.dim() == 2 else []
+            isolated = set(range(len(numbers))) - set(centers)
             if isolated:
                 msg = f"structure has isolated atoms {sorted(isolated)} (no neighbour within the atom-graph cutoff)"
                 if self.on_isolated_atoms == "error":

@@ -164,18 +164,26 @@ class _ParamGradBridge(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, eng_out, names, keys, *tensors):
+        # everything backward needs is captured HERE: another forward (a validation pass, a second batch of
+        # the same loss) before backward() must not change which batch / engine this node differentiates
         ctx.model, ctx.eng_out, ctx.names, ctx.keys = model, eng_out, names, keys
+        ctx.engine = model._get_engine()
+        ctx.atoms_per_graph = list(eng_out.extras["train_state"]["b"].atoms_per_graph)
+        ctx.is_intensive = bool(model.is_intensive)
         return tuple(t.clone() for t in tensors[: len(keys)])
 
     @staticmethod
     def backward(ctx, *g_outs):
-        model, out = ctx.model, ctx.eng_out
-        engine = model._get_engine()
+        out = ctx.eng_out
+        if "train_state" not in out.extras:
+            raise RuntimeError(
+                "chgnet_b200: backward through this CHGNet.forward output ran twice; the saved activations are "
+                "released by the first backward (retain_graph is not supported) - call forward again")
         g = {k: v.contiguous() for k, v in zip(ctx.keys, g_outs)}
-        n = torch.tensor(model.last_batch.atoms_per_graph, device=g["e"].device, dtype=g["e"].dtype)
-        seed_e = g["e"] / n if model.is_intensive else g["e"]  # d/d(extensive model energy)
-        G = engine.param_grads(out, seed_e.contiguous(), g.get("m"), g.get("f"), g.get("s"))
-        grads = unpack_grads(G, model.state_dict())
+        n = torch.tensor(ctx.atoms_per_graph, device=g["e"].device, dtype=g["e"].dtype)
+        seed_e = g["e"] / n if ctx.is_intensive else g["e"]  # d/d(extensive model energy)
+        G = ctx.engine.param_grads(out, seed_e.contiguous(), g.get("m"), g.get("f"), g.get("s"))
+        grads = unpack_grads(G, ctx.model.state_dict())
         return (None, None, None, None, *[None] * len(ctx.keys), *[grads[k] for k in ctx.names])
 
 
@@ -190,9 +198,13 @@ class GraphConverter:
     ``frac_coords``, ``lattice.matrix`` and ``atomic_numbers`` (pymatgen
     ``Structure`` qualifies) or a ``(atomic_numbers, frac_coords, lattice)`` tuple."""
 
-    def __init__(self, atom_graph_cutoff: float = 6, bond_graph_cutoff: float = 3, **_: Any) -> None:
+    def __init__(self, atom_graph_cutoff: float = 6, bond_graph_cutoff: float = 3, *,
+                 on_isolated_atoms: str = "error", **_: Any) -> None:
+        if on_isolated_atoms not in ("ignore", "warn", "error"):
+            raise ValueError(f"{on_isolated_atoms=} must be 'ignore', 'warn' or 'error'")
         self.atom_graph_cutoff = atom_graph_cutoff
-        self.bond_graph_cutoff = bond_graph_cutoff
+        self.bond_graph_cutoff = atom_graph_cutoff if bond_graph_cutoff is None else bond_graph_cutoff
+        self.on_isolated_atoms = on_isolated_atoms  # reference converter.py:42, 160-174
 
     def __call__(self, structure, graph_id=None, mp_id=None) -> CrystalGraph:
         from chgnet_b200 import graphgen
@@ -209,6 +221,19 @@ class GraphConverter:
             np.asarray(z), np.asarray(frac), np.asarray(lat), atom_graph_cutoff=self.atom_graph_cutoff,
             bond_graph_cutoff=self.bond_graph_cutoff, graph_id=graph_id)
         g.mp_id = mp_id
+        if self.on_isolated_atoms != "ignore":
+            n_atoms = len(g.atomic_number)
+            centers = g.atom_graph[:, 0] if g.atom_graph.dim() == 2 and len(g.atom_graph) else torch.zeros(0, dtype=torch.int64)
+            n_isolated_atoms = n_atoms - int(torch.unique(centers).numel())
+            if n_isolated_atoms:
+                atom_graph_cutoff = self.atom_graph_cutoff
+                msg = (f"Structure {graph_id=} has {n_isolated_atoms} isolated atom(s) with "
+                       f"{atom_graph_cutoff=}. CHGNet calculation will likely go wrong")
+                if self.on_isolated_atoms == "error":
+                    raise ValueError(msg)
+                import sys
+
+                print(msg, file=sys.stderr)
         return g
 
     def __repr__(self) -> str:
@@ -335,7 +360,7 @@ class CHGNet(nn.Module):
 
             self._get_engine_checks()
             pw = pack_weights(sd, self.model_args, device=dev)
-            self._engine = Engine(pw, CudaKernels())
+            self._engine = Engine(pw, CudaKernels(dev))
             self._engine_key = key
         return self._engine
 
@@ -504,10 +529,13 @@ class CHGNet(nn.Module):
 
     @classmethod
     def from_file(cls, path: str, **kwargs):
-        if path.endswith(".npz"):  # plain-array export of a state_dict (tests/golden)
+        if path.endswith(".npz"):  # plain-array export of a state_dict (tests/golden), optionally with its model_args
+            import json
+
             with np.load(path) as f:
-                sd = {k: torch.from_numpy(f[k]) for k in f.files}
-            args = {k: v for k, v in kwargs.items()}
+                sd = {k: torch.from_numpy(f[k]) for k in f.files if k != "__model_args__"}
+                args = json.loads(str(f["__model_args__"])) if "__model_args__" in f.files else {}
+            args.update(kwargs)
             return cls.from_dict({"model_args": args, "state_dict": sd})
         state = torch.load(path, map_location=torch.device("cpu"), weights_only=False)
         return cls.from_dict(state["model"], **kwargs)
@@ -540,7 +568,7 @@ class CHGNet(nn.Module):
             npz = os.path.join(_REPO, "tests", "golden", f"chgnet_{model_name}_weights.npz")
             if not os.path.exists(npz):
                 raise FileNotFoundError(f"no checkpoint for {model_name=}; set CHGNET_PRETRAINED_DIR")
-            model = cls.from_file(npz, version=model_name)
+            model = cls.from_file(npz, version=model_name, **({"mlp_out_bias": True} if model_name == "0.2.0" else {}))
         device = use_device or os.environ.get("CHGNET_DEVICE") or "cuda"
         if not str(device).startswith("cuda"):
             raise RuntimeError(f"chgnet_b200 runs on CUDA devices only (requested {device!r})")

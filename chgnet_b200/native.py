@@ -196,8 +196,9 @@ class NativeForward:
             self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=dev)
         base = (self.workspace.data_ptr() + 255) // 256 * 256
         room = self.workspace.numel() - (base - self.workspace.data_ptr())
-        rc = self.lib.chg_forward(ctypes.byref(self.hps), self.weights.data_ptr(), ctypes.byref(bs), ctypes.byref(outs), base, room,
-                                  torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.device(dev):  # launches go to the model's device and its current stream
+            rc = self.lib.chg_forward(ctypes.byref(self.hps), self.weights.data_ptr(), ctypes.byref(bs), ctypes.byref(outs), base, room,
+                                      torch.cuda.current_stream(dev).cuda_stream)
         _check(self.lib, rc, "chg_forward")
         self.calls += 1
         return res

@@ -35,6 +35,7 @@ extern "C" {
 
 #define CHG_FEA 64
 #define CHG_MAX_CONV 8
+#define CHG_MAX_Z 94 /* rows of the atom embedding / AtomRef tables (encoders.py:22-32) */
 #define CHG_OK 0
 #define CHG_ERR_ARG (-1)
 #define CHG_ERR_CUDA (-2)
@@ -284,7 +285,9 @@ void chg_graph_free(chg_graph* g);
  * atomic_number, atom_frac_coord, atom_graph, neighbor_image, directed2undirected, undirected2directed,
  * bond_graph, lattice.  ibuf (int32) = z[N] owner[N] center[Ed] nbr[Ed] d2u[Ed] u2d[Eu] ang_atom[A]
  * ang_i[A] ang_di[A] ang_j[A] ang_dj[A]; fbuf (fp32) = frac[N*3] image[Ed*3] lattice[B*9];
- * flags_out[0/1] = edges sorted by centre / angles sorted by bond i within every graph.               */
+ * flags_out[0/1] = edges sorted by centre / angles sorted by bond i within every graph;
+ * flags_out[2] = index (in the batch) of the first atom whose atomic number is outside [1, CHG_MAX_Z],
+ * or -1 (the caller raises IndexError like the reference's nn.Embedding, tests/test_encoders.py:25-28). */
 int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf,
                         float* fbuf, int32_t* flags_out);
 

@@ -48,7 +48,7 @@ def test_binding_table_matches_header(lib):
 
 
 def test_library_metadata(lib):
-    assert lib.chg_abi_version() == 2
+    assert lib.chg_abi_version() == 3
     assert lib.chg_launch_count() >= 0
     assert lib.chg_last_error() is not None
 

@@ -27,6 +27,8 @@ def test_reference_arm_prints_the_contract_line():
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert d["vs_baseline"] is None and d["higher_is_better"] is True and "workload" in d["config"]
+        assert d["product_so_mapped"] is False  # inputs come from the numpy builder: the product .so is never loaded
+        assert {"task", "whole_job", "weights", "l2", "parallelism"} <= set(d["config"])  # same object as the product arm's
 
 
 def test_default_arm_needs_cuda():
