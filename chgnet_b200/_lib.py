@@ -32,6 +32,8 @@ SIGNATURES: dict[str, list] = {
     "chg_atom_conv_fwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P],
     "chg_atom_conv_bwd": [P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
     "chg_segment_sum": [P, I, P, P, I, I, I, P, I, P],
+    "chg_atom_conv_fused": [P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, P],
+    "chg_bond_conv_fused": [P, P, P, P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
     "chg_bond_conv_fwd": [P, P, P, P, P, P, P, I, P, P, P, P, P, P, P],
     "chg_bond_conv_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P],
     "chg_angle_update_fwd": [P, P, P, P, P, P, P, I, P, P, P, P],
@@ -90,6 +92,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     lib.chg_set_option.argtypes = [c_char_p, c_int32]
     lib.chg_wgrad_workspace_floats.restype = c_int64
     lib.chg_wgrad_workspace_floats.argtypes = [c_int32]
+    lib.chg_gated_fused_workspace_floats.restype = c_int64
+    lib.chg_gated_fused_workspace_floats.argtypes = [c_int32]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int32
@@ -142,7 +146,7 @@ class CudaKernels:
     def set_option(self, name: str, value: int) -> None:
         """A/B switches (include/chgnet_b200.h): 'linear_impl' 0 FFMA | 1 tcgen05 | 2 tcgen05+TMA rows |
         3 warp-specialised tcgen05 + TMA tensor maps (default),
-        'gated_impl' 0 FFMA 4x8 | 1 tcgen05 | 2 FFMA 8x8."""
+        'gated_impl' 3 fused warp-specialised tcgen05 message + aggregation (default) | 0 FFMA 4x8 | 1 tcgen05 | 2 FFMA 8x8."""
         if self.lib.chg_set_option(name.encode(), int(value)) != 0:
             raise ChgnetB200Error(self.lib.chg_last_error().decode())
 
@@ -206,6 +210,27 @@ class CudaKernels:
         self._chk(pcn, pe, wag, center, nbr, d2u, save_p, g_agg, w2, ln, g_pre, g_w, g_p, g_ln)
         self._call("chg_atom_conv_bwd", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), center.shape[0],
                    _p(save_p), _p(g_agg), _p(w2), _p(ln), _p(g_pre), _p(g_w), _p(g_p), _p(g_ln))
+
+    def _fused_work(self, n_rows: int, device) -> Tensor:
+        """Grow-only scratch of the fused message + aggregation kernels (strip partials; the message itself
+        for the unfused A/B implementations)."""
+        need = int(self.lib.chg_gated_fused_workspace_floats(int(n_rows)))
+        ws = getattr(self, "_fws", None)
+        if ws is None or ws.device != device or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.float32, device=device)
+            self._fws = ws
+        return ws
+
+    def atom_conv_fused(self, pcn, pe, wag, center, nbr, d2u, ptr_c, w2t, b2, ln, agg, save_p):
+        self._chk(pcn, pe, wag, center, nbr, d2u, ptr_c, w2t, b2, ln, agg, save_p)
+        self._call("chg_atom_conv_fused", _p(pcn), _p(pe), _p(wag), _p(center), _p(nbr), _p(d2u), _p(ptr_c), center.shape[0],
+                   agg.shape[0], _p(w2t), _p(b2), _p(ln), _p(agg), _p(save_p), _p(self._fused_work(center.shape[0], agg.device)))
+
+    def bond_conv_fused(self, pij, px, pa, wbg, ang_atom, ang_i, ang_j, ptr_i, w2t, b2, ln, agg, save_pre, save_p):
+        self._chk(pij, px, pa, wbg, ang_atom, ang_i, ang_j, ptr_i, w2t, b2, ln, agg, save_pre, save_p)
+        self._call("chg_bond_conv_fused", _p(pij), _p(px), _p(pa), _p(wbg), _p(ang_atom), _p(ang_i), _p(ang_j), _p(ptr_i),
+                   ang_i.shape[0], agg.shape[0], _p(w2t), _p(b2), _p(ln), _p(agg), _p(save_pre), _p(save_p),
+                   _p(self._fused_work(ang_i.shape[0], agg.device)))
 
     def segment_sum(self, data, perm, ptr, accumulate, out):
         self._chk(data, perm, ptr)

@@ -36,9 +36,10 @@ int sm_count() {  // of the CURRENT device (cached per device ordinal)
 
 namespace chg {
 namespace {
-// implementation switches: 1 = tcgen05 (tensor memory), 0 = FFMA.  Defaults follow the measured
-// A/B (profiles/): the dense feature-mixing GEMM runs on tcgen05; the AtomConv/BondConv tile
-// kernels default to FFMA until their tcgen05 version is warp-specialised.
+// implementation switches.  Defaults follow the measured A/B (profiles/): the dense feature-mixing GEMM runs on
+// the warp-specialised tcgen05 kernel (linear_impl 3); the AtomConv / BondConv message + aggregation runs as the
+// fused warp-specialised tcgen05 kernel of gated_ws.cu (gated_impl 3) wherever the engine calls the fused entry
+// points; gated_impl 0..2 select the older unfused kernels (FFMA 4x8 / tcgen05 / FFMA 8x8) for A/B runs.
 std::atomic<int> g_linear_impl{-1}, g_gated_impl{-1};
 int env_default(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -54,7 +55,7 @@ int linear_impl() {
 }
 int gated_impl() {
   int v = g_gated_impl.load();
-  if (v < 0) { v = env_default("CHG_GATED_IMPL", 0); g_gated_impl.store(v); }
+  if (v < 0) { v = env_default("CHG_GATED_IMPL", 3); g_gated_impl.store(v); }
   return v;
 }
 }  // namespace chg
@@ -62,7 +63,7 @@ int gated_impl() {
 extern "C" int chg_set_option(const char* name, int32_t value) {
   if (name == nullptr) return CHG_ERR_ARG;
   if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 3 ? 3 : value)); return CHG_OK; }
-  if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return CHG_OK; }
+  if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value < 0 ? 0 : (value > 3 ? 3 : value)); return CHG_OK; }
   chg::set_error("chg_set_option: unknown option %s", name);
   return CHG_ERR_ARG;
 }

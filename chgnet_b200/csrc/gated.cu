@@ -765,7 +765,7 @@ extern "C" int chg_atom_conv_fwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && w2t && b2 && msg, "null pointer");
   FwdArgs a{pcn, pe, nullptr, nullptr, wag, center, nbr, d2u, n_edges, w2t, b2, ln, msg, save_pre, save_p};
   const bool train = save_pre != nullptr;  // training extras exist in the default implementation only
-  if (gated_impl() == 1 && !train) return atom_conv_fwd_tc(a, as_stream(stream));
+  if (gated_impl() == 1 && !train) return atom_conv_fwd_tc(a, as_stream(stream));  // 3 (fused default) -> FFMA here
   if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;
     return launch2(gated2_fwd_kernel<ATOM>, a, slots, as_stream(stream));

@@ -150,5 +150,14 @@ int bond_conv_fwd_tc(const FwdArgs& a, cudaStream_t stream);
 int atom_conv_bwd_tc(const BwdArgs& a, cudaStream_t stream);
 int bond_conv_bwd_tc(const BwdArgs& a, cudaStream_t stream);
 
+// warp-specialised tcgen05 message + aggregation kernels (gated_ws.cu); `parts` = strip partials workspace
+int atom_conv_fused_ws(const float* pcn, const float* pe, const float* wag, const int32_t* center, const int32_t* nbr,
+                       const int32_t* d2u, const int32_t* ptr_c, int n_edges, int n_atoms, const float* w2t, const float* b2,
+                       const float* ln, float* agg, float* save_p, float* parts, cudaStream_t stream);
+int bond_conv_fused_ws(const float* pij, const float* px, const float* pa, const float* wbg, const int32_t* ang_atom,
+                       const int32_t* ang_i, const int32_t* ang_j, const int32_t* ptr_i, int n_angles, int n_slots,
+                       const float* w2t, const float* b2, const float* ln, float* agg, float* save_pre, float* save_p,
+                       float* parts, cudaStream_t stream);
+
 }  // namespace gated
 }  // namespace chg

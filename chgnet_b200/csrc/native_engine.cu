@@ -234,11 +234,12 @@ int run_schedule(const chg_hparams& hp, const Weights& W, const chg_batch& b, co
     float* pe = c.f(grad, (size_t)Eu * 128);
     lin(xin, nullptr, N, 64, g.a_t, nullptr, nullptr, nullptr, 256, pcn);
     lin(e, nullptr, Eu, 64, g.b_t, g.bias1, nullptr, nullptr, 128, pe);
-    float* msg = c.f(false, (size_t)Ed * 64);
     float* save_p = grad ? c.f(true, (size_t)Ed * 128) : nullptr;
-    RUN(c, "atom_conv_fwd", chg_atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, Ed, g.w2t, g.b2, g.ln, msg, save_p, nullptr, st));
     float* agg = c.f(false, (size_t)N * 64);
-    seg(msg, 64, nullptr, b.ptr_c, N, Ed, 0, agg, 64);
+    float* work = c.f(false, (size_t)chg_gated_fused_workspace_floats(Ed));
+    // message + aggregation in one kernel (gated_ws.cu): the [Ed][64] message never reaches HBM
+    RUN(c, "atom_conv_fused", chg_atom_conv_fused(pcn, pe, wag, b.center, b.nbr, b.d2u, b.ptr_c, Ed, N, g.w2t, g.b2, g.ln, agg, save_p,
+                                                  work, st));
     sa[t] = SavedAtom{pcn, pe, save_p};
     lin(agg, nullptr, N, 64, g.wo_t, g.bo, xin, nullptr, 64, xout);
     c.ar.reset_tmp();
@@ -257,13 +258,12 @@ int run_schedule(const chg_hparams& hp, const Weights& W, const chg_batch& b, co
       lin(e, b.short_ids, Es, 64, g.a_t, g.bias1, nullptr, nullptr, 256, pij);
       lin(x, nullptr, N, 64, g.b_t, nullptr, nullptr, nullptr, 128, px);
       lin(ang, nullptr, A, 64, g.c_t, nullptr, nullptr, nullptr, 128, pa);
-      float* upd = c.f(false, (size_t)A * 64);
       float* s_pre = grad ? c.f(true, (size_t)A * 128) : nullptr;
       float* s_p = grad ? c.f(true, (size_t)A * 128) : nullptr;
-      RUN(c, "bond_conv_fwd", chg_bond_conv_fwd(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, A, g.w2t, g.b2, g.ln, upd,
-                                                s_pre, s_p, st));
       float* agg = c.f(false, (size_t)Es * 64);
-      seg(upd, 64, nullptr, b.ptr_is, Es, A, 0, agg, 64);
+      float* work = c.f(false, (size_t)chg_gated_fused_workspace_floats(A));
+      RUN(c, "bond_conv_fused", chg_bond_conv_fused(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, b.ptr_is, A, Es, g.w2t, g.b2,
+                                                    g.ln, agg, s_pre, s_p, work, st));
       lin(agg, nullptr, Es, 64, g.wo_t, g.bo, e, b.short_ids, 64, e);  // e[sid] += Wo agg (+ bias)
       sb[t] = SavedBond{s_pre, s_p};
       c.ar.reset_tmp();

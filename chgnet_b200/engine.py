@@ -127,14 +127,15 @@ class Engine:
             gp = pw.atom[t]
             pcn = self._lin(b, x, gp.extra["wcn_t"])
             pe = self._lin(b, e, gp.extra["we_t"], bias=gp.extra["b1"])
-            msg = self._new(b, Ed, 64)
             save_p = self._new(b, Ed, 128) if need_grad else None
-            if train:
+            agg = self._new(b, N, 64)
+            if train:  # training also keeps `pre` and the message: unfused pair
+                msg = self._new(b, Ed, 64)
                 save_pre = self._new(b, Ed, 128)
                 K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p, save_pre)
-            else:
-                K.atom_conv_fwd(pcn, pe, wag, b.center, b.nbr, b.d2u, gp.w2t, gp.b2, gp.ln, msg, save_p)
-            agg = self._seg(b, msg, None, b.ptr_c, N)
+                K.segment_sum(msg, None, b.ptr_c, 0, agg)
+            else:  # message + aggregation in one kernel: the [Ed, 64] message never reaches HBM
+                K.atom_conv_fused(pcn, pe, wag, b.center, b.nbr, b.d2u, b.ptr_c, gp.w2t, gp.b2, gp.ln, agg, save_p)
             if need_grad:
                 saved_atom.append(dict(pcn=pcn, pe=pe, p=save_p))
             if train:
@@ -156,12 +157,17 @@ class Engine:
                 pij = self._lin(b, e, gp.extra["wij_t"], bias=gp.extra["bij"], x_rows=sid)
                 px = self._lin(b, x, gp.extra["wx_t"])
                 pa = self._lin(b, ang, gp.extra["w1a_t"])  # angle block of the first layer, per angle
-                upd = self._new(b, A, 64)
                 s_pre = self._new(b, A, 128) if need_grad else None
                 s_p = self._new(b, A, 128) if need_grad else None
-                K.bond_conv_fwd(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, gp.w2t, gp.b2, gp.ln,
-                                upd, s_pre, s_p)
-                agg = self._seg(b, upd, None, b.ptr_is, Es)
+                agg = self._new(b, Es, 64)
+                if train:
+                    upd = self._new(b, A, 64)
+                    K.bond_conv_fwd(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, gp.w2t, gp.b2, gp.ln,
+                                    upd, s_pre, s_p)
+                    K.segment_sum(upd, None, b.ptr_is, 0, agg)
+                else:
+                    K.bond_conv_fused(pij, px, pa, wbg_s, b.ang_atom, b.ang_is, b.ang_js, b.ptr_is, gp.w2t, gp.b2, gp.ln,
+                                      agg, s_pre, s_p)
                 # e[sid] += Wo agg (+ bias); bonds outside the bond graph keep their features
                 # (with mlp_out bias the batch is built with identity compaction, Es == Eu)
                 e_in = e

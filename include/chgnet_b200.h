@@ -48,8 +48,10 @@ int64_t chg_launch_count(void);
  *   "linear_impl": 0 FFMA, 1 tcgen05 register-staged, 2 tcgen05 + TMA row copies,
  *                  3 warp-specialised tcgen05 fed by 2-D TMA tensor maps (default; calls with
  *                    row indirection or k = 256 use 1)
- *   "gated_impl" : 0 FFMA 4x8 tiles (default), 1 tcgen05, 2 FFMA 8x8 tiles
- * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3 / 0..2 set the defaults).                      */
+ *   "gated_impl" : 3 fused warp-specialised tcgen05 message + aggregation (default; chg_*_conv_fused),
+ *                  0 FFMA 4x8 tiles, 1 tcgen05 (un-pipelined), 2 FFMA 8x8 tiles (all unfused; with 3 the
+ *                  unfused entry points chg_*_conv_fwd / _bwd run the FFMA 4x8 kernels)
+ * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3 set the defaults).                             */
 int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */
@@ -133,6 +135,27 @@ int chg_segment_sum(const float* data, int32_t width, const int32_t* perm,
                     const int32_t* ptr, int32_t n_rows,
                     int32_t n_items /* ptr[n_rows]; scheduling hint only */, int32_t accumulate,
                     float* out, int32_t out_ld /* row stride of out, in floats */, void* stream);
+
+/* ---- K4f / K5f: message + aggregation fused (the default inference path; layers.py:113-126, 238-254)
+ * agg[s] = sum over the rows r of segment s of  G(pre_r) * w_r,  rows sorted by segment:
+ *   AtomConv: rows = directed edges sorted by centre, segment = centre atom (ptr_c [N+1]), w = wag[d2u];
+ *   BondConv: rows = angles sorted by bond slot i, segment = slot i (ptr_i [Es+1]), w = wbg[i] * wbg[j].
+ * One warp-specialised tcgen05 kernel (csrc/gated_ws.cu): gather + add of the first-layer rows, the two 64x64
+ * second-layer products as 3xTF32 on the tensor cores, LayerNorm / SiLU x sigmoid, and the segmented sum inside the
+ * CTA (the [rows][64] message never reaches HBM), followed by a small stitch kernel for segments that span
+ * 16-row strips (fixed order: deterministic).  save_p / save_pre [rows][128] may be NULL (no reverse pass).
+ * `work`: caller scratch of chg_gated_fused_workspace_floats(rows) floats.  With gated_impl 0..2 the same entry
+ * points run the unfused pair chg_*_conv_fwd -> chg_segment_sum (A/B).                                        */
+int64_t chg_gated_fused_workspace_floats(int32_t n_rows);
+int chg_atom_conv_fused(const float* pcn, const float* pe, const float* wag, const int32_t* center,
+                        const int32_t* nbr, const int32_t* d2u, const int32_t* ptr_c, int32_t n_edges,
+                        int32_t n_atoms, const float* w2t, const float* b2, const float* ln, float* agg,
+                        float* save_p, float* work, void* stream);
+int chg_bond_conv_fused(const float* pij, const float* px, const float* pa, const float* wbg,
+                        const int32_t* ang_atom, const int32_t* ang_i, const int32_t* ang_j,
+                        const int32_t* ptr_i, int32_t n_angles, int32_t n_slots, const float* w2t,
+                        const float* b2, const float* ln, float* agg, float* save_pre, float* save_p,
+                        float* work, void* stream);
 
 /* ---- K5: BondConv message (layers.py:238-249)
  * pre = pij[i][0:128] + pij[j][128:256] + px[c] + pa[a], pa = ang @ W1a (chg_linear);

@@ -297,6 +297,17 @@ class SpecKernels:
         g_h = torch.cat([g_p[:, :64] @ w2[:64], g_p[:, 64:] @ w2[64:]], dim=1)
         g_pre.copy_(g_h * _dsilu(pre))
 
+    # ---- K4f / K5f: message + aggregation fused (chg_atom_conv_fused / chg_bond_conv_fused)
+    def atom_conv_fused(self, pcn, pe, wag, center, nbr, d2u, ptr_c, w2t, b2, ln, agg, save_p):
+        msg = torch.empty(center.shape[0], 64, dtype=agg.dtype)
+        SpecKernels.atom_conv_fwd(self, pcn, pe, wag, center, nbr, d2u, w2t, b2, ln, msg, save_p)  # unbound: not re-recorded
+        SpecKernels.segment_sum(self, msg, None, ptr_c, 0, agg)
+
+    def bond_conv_fused(self, pij, px, pa, wbg, ang_atom, ang_i, ang_j, ptr_i, w2t, b2, ln, agg, save_pre, save_p):
+        upd = torch.empty(ang_i.shape[0], 64, dtype=agg.dtype)
+        SpecKernels.bond_conv_fwd(self, pij, px, pa, wbg, ang_atom, ang_i, ang_j, w2t, b2, ln, upd, save_pre, save_p)
+        SpecKernels.segment_sum(self, upd, None, ptr_i, 0, agg)
+
     # ---- K4s
     def segment_sum(self, data, perm, ptr, accumulate, out):
         n_rows = ptr.shape[0] - 1

@@ -21,6 +21,8 @@ OUT_ARGS = {
     "atom_conv_fwd": [9, 10, 11],
     "atom_conv_bwd": [10, 11, 12, 13],
     "segment_sum": [4],
+    "atom_conv_fused": [10, 11],
+    "bond_conv_fused": [11, 12, 13],
     "bond_conv_fwd": [10, 11, 12],
     "bond_conv_bwd": [8, 9, 10, 11, 12],
     "angle_update_fwd": [8, 9],
@@ -50,7 +52,8 @@ OUT_ARGS = {
 SECOND_ORDER_KERNELS = {"edge_tangent", "bond_basis_tangent", "bond_basis_bwd2", "angle_basis_tangent", "angle_basis_bwd2",
                         "atom_conv_tan", "atom_conv_bwd2", "bond_conv_tan", "bond_conv_bwd2", "angle_update_tan",
                         "angle_update_bwd2", "readout_bwd2"}
-TRAIN_KERNELS = {"wgrad", "colsum", "readout_bwd", "magmom_bwd"} | SECOND_ORDER_KERNELS
+# the unfused message kernels only run in training mode (they also save `pre`); inference uses the fused pair
+TRAIN_KERNELS = {"wgrad", "colsum", "readout_bwd", "magmom_bwd", "atom_conv_fwd", "bond_conv_fwd"} | SECOND_ORDER_KERNELS
 INFER_KERNELS = set(OUT_ARGS) - TRAIN_KERNELS
 
 

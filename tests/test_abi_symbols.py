@@ -35,7 +35,7 @@ def test_binding_table_matches_header(lib):
     from chgnet_b200 import _lib
 
     declared = set(_declared()) - {"chg_last_error", "chg_abi_version", "chg_launch_count", "chg_set_option",
-                                   "chg_wgrad_workspace_floats", "chg_packed_floats", "chg_pack_weights_host",
+                                   "chg_wgrad_workspace_floats", "chg_gated_fused_workspace_floats", "chg_packed_floats", "chg_pack_weights_host",
                                    "chg_forward_plan", "chg_forward",
                                    "chg_graph_build", "chg_graph_sizes", "chg_graph_export", "chg_graph_free",
                                    "chg_pack_batch_host"}

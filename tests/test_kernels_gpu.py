@@ -38,9 +38,9 @@ def recorded(weights030):
     return _record(weights030, graphs, need_grad=True, need_magmom=True, need_atom_fea=True, need_crystal_fea=True)
 
 
-@pytest.mark.parametrize("linear_impl,gated_impl", [(3, 0), (1, 0), (0, 1), (2, 2)],
-                         ids=["linear=tcgen05-ws,gated=ffma4x8", "linear=tcgen05,gated=ffma4x8", "linear=ffma,gated=tcgen05",
-                              "linear=tcgen05+tma,gated=ffma8x8"])
+@pytest.mark.parametrize("linear_impl,gated_impl", [(3, 3), (3, 0), (1, 0), (0, 1), (2, 2)],
+                         ids=["defaults: linear=tcgen05-ws,gated=fused-tcgen05-ws", "linear=tcgen05-ws,gated=ffma4x8",
+                              "linear=tcgen05,gated=ffma4x8", "linear=ffma,gated=tcgen05", "linear=tcgen05+tma,gated=ffma8x8"])
 def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
     """Both implementations of every entry point (tcgen05 3xTF32 and FFMA) against the spec."""
     from chgnet_b200._lib import CudaKernels
@@ -61,7 +61,7 @@ def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
         print({k: f"{v:.2e}" for k, v in seen.items()})
     finally:
         K.set_option("linear_impl", 3)
-        K.set_option("gated_impl", 0)
+        K.set_option("gated_impl", 3)
 
 
 def test_every_training_kernel_matches_its_spec(weights030):

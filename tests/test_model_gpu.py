@@ -47,7 +47,7 @@ def test_limno2_known_answers(model, limno2_graph, golden):
     print({k: f"{_maxabs(out[k], golden[f'limno2.oracle64.{k}']):.2e}" for k in TOL})
 
 
-@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 1), (0, 0)], ids=["all-tcgen05", "all-ffma"])
+@pytest.mark.parametrize("linear_impl,gated_impl", [(1, 1), (0, 0), (3, 3)], ids=["all-tcgen05", "all-ffma", "defaults"])
 def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, linear_impl, gated_impl):
     from chgnet_b200._lib import CudaKernels
 
@@ -60,7 +60,7 @@ def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, lin
             assert _maxabs(out[k], golden[f"limno2.oracle64.{k}"]) < tol, k
     finally:
         K.set_option("linear_impl", 3)
-        K.set_option("gated_impl", 0)
+        K.set_option("gated_impl", 3)
 
 
 def test_random_batch_vs_reference_golden(model, golden):
