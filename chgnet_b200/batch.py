@@ -22,6 +22,7 @@ Segment structures (all int32, device):
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -131,6 +132,64 @@ def _group(keys: Tensor, n_rows: int) -> tuple[Tensor, Tensor]:
 _PACK_LIB = None
 
 
+class _CsrIn(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_atoms", "n_edges", "n_bonds", "n_angles", "n_short", "with_reverse")] + \
+               [(n, ctypes.c_void_p) for n in ("center", "nbr", "d2u", "ang_atom", "ang_i", "ang_j")]
+
+
+_CSR_OUT = ("ptr_c", "perm_n", "ptr_n", "perm_u", "ptr_u", "ptr_i", "perm_j", "ptr_j", "perm_x", "ptr_x",
+            "short_ids", "ang_is", "ang_js", "ptr_is", "ptr_js")
+
+
+class _CsrOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _CSR_OUT]
+
+
+_CSR_SCRATCH: dict = {}  # device -> grow-only int32 scratch of chg_build_csr
+
+
+def _csr_device(device, N, Ed, Eu, A, Es, with_reverse, center, nbr, d2u, ang_atom, ang_i, ang_j) -> dict:
+    """All segment structures of the batch in ONE C call (csrc/batch_csr.cu): boundary searches for the sorted
+    keys, counting sorts for the transposed groupings, the compact bond-graph slots - no ATen sorts, no host
+    synchronisation.  ``Es`` < 0: no compaction (every bond keeps its index)."""
+    import ctypes
+
+    lib = _pack_lib()
+    sizes = {"ptr_c": N + 1, "perm_n": Ed, "ptr_n": N + 1, "perm_u": Ed, "ptr_u": Eu + 1, "ptr_i": Eu + 1, "perm_j": A,
+             "ptr_j": Eu + 1, "perm_x": A, "ptr_x": N + 1, "short_ids": max(Es, 0), "ang_is": A if Es >= 0 else 0,
+             "ang_js": A if Es >= 0 else 0, "ptr_is": Es + 1 if Es >= 0 else 0, "ptr_js": Es + 1 if Es >= 0 else 0}
+    if not with_reverse:
+        for k in ("perm_n", "perm_u", "perm_j", "perm_x", "ptr_js"):
+            sizes[k] = 0
+    pad = lambda n: (n + 3) // 4 * 4  # noqa: E731  16-byte aligned pieces
+    buf = torch.empty(sum(pad(n) for n in sizes.values()) + 4, dtype=torch.int32, device=device)
+    views, off = {}, 0
+    for k in _CSR_OUT:
+        views[k] = buf[off : off + sizes[k]]
+        off += pad(sizes[k])
+    need = int(lib.chg_build_csr_scratch_ints(N, Ed, Eu, A))
+    scr = _CSR_SCRATCH.get(device)
+    if scr is None or scr.numel() < need:
+        scr = torch.empty(int(need * 1.25) + 16, dtype=torch.int32, device=device)
+        _CSR_SCRATCH[device] = scr
+    ptr = lambda t: t.data_ptr() if t is not None and t.numel() else None  # noqa: E731
+    cin = _CsrIn(n_atoms=N, n_edges=Ed, n_bonds=Eu, n_angles=A, n_short=Es, with_reverse=int(with_reverse),
+                 center=ptr(center), nbr=ptr(nbr), d2u=ptr(d2u), ang_atom=ptr(ang_atom), ang_i=ptr(ang_i), ang_j=ptr(ang_j))
+    # zero-size outputs still get a valid (never written) address so that the C side can tell "absent" from "empty"
+    cout = _CsrOut(**{k: (views[k].data_ptr() if sizes[k] else buf[-4:].data_ptr()) for k in _CSR_OUT})
+    with torch.cuda.device(device):
+        rc = lib.chg_build_csr(ctypes.byref(cin), ctypes.byref(cout), scr.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"chg_build_csr failed: {lib.chg_last_error().decode()}")
+    if not with_reverse:
+        i32 = dict(dtype=torch.int32, device=device)
+        views["ptr_n"] = views["ptr_x"] = torch.zeros(N + 1, **i32)
+        views["ptr_u"] = views["ptr_j"] = torch.zeros(Eu + 1, **i32)
+        if Es >= 0:
+            views["ptr_js"] = torch.zeros(Es + 1, **i32)
+    return views
+
+
 def _pack_lib():
     global _PACK_LIB
     if _PACK_LIB is None:
@@ -141,6 +200,10 @@ def _pack_lib():
         lib = load_library()
         lib.chg_pack_batch_host.restype = ctypes.c_int32
         lib.chg_pack_batch_host.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5
+        lib.chg_build_csr_scratch_ints.restype = ctypes.c_int64
+        lib.chg_build_csr_scratch_ints.argtypes = [ctypes.c_int32] * 4
+        lib.chg_build_csr.restype = ctypes.c_int32
+        lib.chg_build_csr.argtypes = [ctypes.POINTER(_CsrIn), ctypes.POINTER(_CsrOut), ctypes.c_void_p, ctypes.c_void_p]
         _PACK_LIB = lib
     return _PACK_LIB
 
@@ -182,7 +245,9 @@ def _graphs_are_packable(graphs, ag_l, bg_l) -> bool:
 
 
 def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True,
-                compact_bonds: bool = True, native_pack: bool = True) -> DeviceBatch:
+                compact_bonds: bool = True, native_pack: bool = True, native_csr: bool = True) -> DeviceBatch:
+    """list[CrystalGraph] -> DeviceBatch.  ``native_pack`` / ``native_csr`` = False select the older torch
+    implementations of the host packing / the segment structures (kept as the checkers of the C paths)."""
     device = torch.device(device)
     B = len(graphs)
     # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
@@ -346,7 +411,7 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
                             for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
                                       g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
-        flags = (ctypes.c_int32 * 3)()
+        flags = (ctypes.c_int32 * 4)()
         rc = lib.chg_pack_batch_host(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(), flags)
         if rc != 0:
             raise RuntimeError(f"chg_pack_batch_host failed: {lib.chg_last_error().decode()}")
@@ -361,9 +426,12 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         sizes = (N, N, Ed, Ed, Ed, Eu, A, A, A, A, A)
         z, owner, center, nbr, d2u, u2d, ang_atom, ang_i, ang_di, ang_j, ang_dj = torch.split(ibuf, sizes)
         frac, image, lattice = torch.split(fbuf, (3 * N, 3 * Ed, 9 * B))
+        nonlocal n_short_host
+        n_short_host = int(flags[3])
         return (z, owner, center, nbr, d2u, u2d, image.view(Ed, 3), frac.view(N, 3), lattice.view(B, 9), ang_atom, ang_i,
                 ang_di, ang_j, ang_dj, bool(flags[0]), bool(flags[1]), (n_int + n_flt) * 4 if device.type != "cpu" else 0)
 
+    n_short_host = -1  # number of bond-graph bonds, counted by the C packer (no device sync needed later)
     use_native = native_pack and B > 0 and src_dev.type == "cpu" and _graphs_are_packable(graphs, ag_l, bg_l)
     (z, owner, center, nbr, d2u, u2d, image, frac_t, lattice, ang_atom, ang_i, ang_di, ang_j, ang_dj, edges_sorted,
      angles_sorted, h2d) = pack_native() if use_native else pack_legacy()
@@ -382,38 +450,56 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         _, perm = torch.sort(ang_i, stable=True)
         ang_atom, ang_i, ang_j, ang_di, ang_dj = (t[perm] for t in (ang_atom, ang_i, ang_j, ang_di, ang_dj))
 
-    ptr_c = _csr_ptr(center, N)
-    ptr_i = _csr_ptr(ang_i, Eu)
     i32 = dict(dtype=torch.int32, device=device)
-    if with_reverse:
-        perm_n, ptr_n = _group(nbr, N)
-        perm_u, _ = _group(d2u, Eu)
-        ptr_u = torch.arange(Eu + 1, **i32) * 2
-        perm_j, ptr_j = _group(ang_j, Eu)
-        perm_x, ptr_x = _group(ang_atom, N)
+    if device.type == "cuda" and use_native and native_csr and n_short_host >= 0:
+        # ---- device CSR build: one C call, no sorts, no host sync (csrc/batch_csr.cu) ----
+        center, nbr, d2u = center.contiguous(), nbr.contiguous(), d2u.contiguous()
+        ang_atom, ang_i, ang_j = ang_atom.contiguous(), ang_i.contiguous(), ang_j.contiguous()
+        do_compact = bool(A and compact_bonds)
+        v = _csr_device(device, N, Ed, Eu, A, n_short_host if do_compact else -1, with_reverse, center, nbr, d2u,
+                        ang_atom, ang_i, ang_j)
+        ptr_c, ptr_i = v["ptr_c"], v["ptr_i"]
+        perm_n, ptr_n, perm_u, ptr_u = v["perm_n"], v["ptr_n"], v["perm_u"], v["ptr_u"]
+        perm_j, ptr_j, perm_x, ptr_x = v["perm_j"], v["ptr_j"], v["perm_x"], v["ptr_x"]
+        if do_compact:
+            short_ids, ang_is, ang_js, ptr_is = v["short_ids"], v["ang_is"], v["ang_js"], v["ptr_is"]
+            perm_js, ptr_js = perm_j, v["ptr_js"]  # slot numbers are monotone in the bond index: same permutation
+            Es = n_short_host
+        else:
+            short_ids = torch.arange(Eu, **i32)
+            ang_is, ang_js, ptr_is, perm_js, ptr_js, Es = ang_i, ang_j, ptr_i, perm_j, ptr_j, Eu
     else:
-        empty = torch.zeros(0, **i32)
-        perm_n = perm_u = perm_j = perm_x = empty
-        ptr_n = ptr_x = torch.zeros(N + 1, **i32)
-        ptr_u = ptr_j = torch.zeros(Eu + 1, **i32)
+        ptr_c = _csr_ptr(center, N)
+        ptr_i = _csr_ptr(ang_i, Eu)
+        if with_reverse:
+            perm_n, ptr_n = _group(nbr, N)
+            perm_u, _ = _group(d2u, Eu)
+            ptr_u = torch.arange(Eu + 1, **i32) * 2
+            perm_j, ptr_j = _group(ang_j, Eu)
+            perm_x, ptr_x = _group(ang_atom, N)
+        else:
+            empty = torch.zeros(0, **i32)
+            perm_n = perm_u = perm_j = perm_x = empty
+            ptr_n = ptr_x = torch.zeros(N + 1, **i32)
+            ptr_u = ptr_j = torch.zeros(Eu + 1, **i32)
 
-    # ---- compact index space of the bond-graph bonds (one host sync: the slot count) ----
-    if A and compact_bonds:
-        mask = torch.zeros(Eu, dtype=torch.int32, device=device)
-        mask[ang_i.long()] = 1
-        mask[ang_j.long()] = 1
-        slot = torch.cumsum(mask, 0, dtype=torch.int32) - 1
-        short_ids = torch.nonzero(mask).view(-1).to(torch.int32)  # syncs; ascending
-        ang_is, ang_js = slot[ang_i.long()], slot[ang_j.long()]
-    else:  # identity "compaction": every bond has a slot
-        short_ids = torch.arange(Eu, **i32)
-        ang_is, ang_js = ang_i, ang_j
-    Es = int(short_ids.shape[0])
-    ptr_is = _csr_ptr(ang_is, Es)
-    if with_reverse:
-        perm_js, ptr_js = _group(ang_js, Es)
-    else:
-        perm_js, ptr_js = torch.zeros(0, **i32), torch.zeros(Es + 1, **i32)
+        # ---- compact index space of the bond-graph bonds (one host sync: the slot count) ----
+        if A and compact_bonds:
+            mask = torch.zeros(Eu, dtype=torch.int32, device=device)
+            mask[ang_i.long()] = 1
+            mask[ang_j.long()] = 1
+            slot = torch.cumsum(mask, 0, dtype=torch.int32) - 1
+            short_ids = torch.nonzero(mask).view(-1).to(torch.int32)  # syncs; ascending
+            ang_is, ang_js = slot[ang_i.long()], slot[ang_j.long()]
+        else:  # identity "compaction": every bond has a slot
+            short_ids = torch.arange(Eu, **i32)
+            ang_is, ang_js = ang_i, ang_j
+        Es = int(short_ids.shape[0])
+        ptr_is = _csr_ptr(ang_is, Es)
+        if with_reverse:
+            perm_js, ptr_js = _group(ang_js, Es)
+        else:
+            perm_js, ptr_js = torch.zeros(0, **i32), torch.zeros(Es + 1, **i32)
 
     L = lattice.view(B, 3, 3)
     volume = (L[:, 0] * torch.linalg.cross(L[:, 1], L[:, 2])).sum(dim=1)  # model.py:834-836

@@ -332,6 +332,9 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
   float* lattice = image + Ed * 3;
   bool edges_sorted = true, angles_sorted = true;
   int64_t bad_z = -1;
+  static thread_local std::vector<uint8_t> in_bond_graph;  // one flag per bond of the batch
+  in_bond_graph.assign((size_t)Eu, 0);
+  int64_t n_short = 0;
   int64_t a_off = 0, e_off = 0, u_off = 0, g_off = 0;
   for (int g = 0; g < n_graphs; ++g) {
     const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
@@ -364,6 +367,13 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
       ang_j[g_off + a] = bg[5 * a + 3] + (int32_t)u_off;
       ang_dj[g_off + a] = bg[5 * a + 4] + (int32_t)e_off;
       if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) angles_sorted = false;
+      for (int which = 1; which <= 3; which += 2) {  // bond i, bond j
+        const int64_t u = u_off + bg[5 * a + which];
+        if (u >= 0 && u < Eu && !in_bond_graph[(size_t)u]) {
+          in_bond_graph[(size_t)u] = 1;
+          ++n_short;
+        }
+      }
     }
     std::memcpy(lattice + (size_t)g * 9, p[7], 36);
     a_off += n;
@@ -374,5 +384,6 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
   flags_out[0] = edges_sorted ? 1 : 0;
   flags_out[1] = angles_sorted ? 1 : 0;
   flags_out[2] = (int32_t)bad_z;
+  flags_out[3] = (int32_t)n_short;
   return CHG_OK;
 }

@@ -302,6 +302,26 @@ int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int3
                      int32_t* bond_graph);
 void chg_graph_free(chg_graph* g);
 
+/* ---- device CSR build: the segment structures of chg_batch from the packed index arrays
+ * (replaces the torch sorts / searchsorted / nonzero of BatchedGraph-side preprocessing; csrc/batch_csr.cu).
+ * Inputs: directed edges sorted by centre, angles sorted by bond i (chg_pack_batch_host reports both).
+ * Outputs (caller-allocated int32): ptr_c [N+1]; perm_n [Ed], ptr_n [N+1] (edges by neighbour); perm_u [Ed],
+ * ptr_u [Eu+1] (the 2 directed edges of every bond); ptr_i [Eu+1]; perm_j [A], ptr_j [Eu+1] (angles by bond j);
+ * perm_x [A], ptr_x [N+1] (angles by atom); and, when n_short >= 0 (= the number of distinct bonds that occur in
+ * angles, counted by chg_pack_batch_host): short_ids [Es], ang_is / ang_js [A], ptr_is [Es+1], ptr_js [Es+1]
+ * (perm_js == perm_j).  Inside every segment the permutations are ascending (== a stable sort by key).
+ * with_reverse = 0 skips the transposed groupings.  scratch: chg_build_csr_scratch_ints(...) int32.           */
+typedef struct chg_csr_in {
+  int32_t n_atoms, n_edges, n_bonds, n_angles, n_short, with_reverse;
+  const int32_t *center, *nbr, *d2u, *ang_atom, *ang_i, *ang_j;
+} chg_csr_in;
+typedef struct chg_csr_out {
+  int32_t *ptr_c, *perm_n, *ptr_n, *perm_u, *ptr_u, *ptr_i, *perm_j, *ptr_j, *perm_x, *ptr_x;
+  int32_t *short_ids, *ang_is, *ang_js, *ptr_is, *ptr_js;
+} chg_csr_out;
+int64_t chg_build_csr_scratch_ints(int32_t n_atoms, int32_t n_edges, int32_t n_bonds, int32_t n_angles);
+int chg_build_csr(const chg_csr_in* in, const chg_csr_out* out, int32_t* scratch, void* stream);
+
 /* host batch packer: B CrystalGraphs (HOST arrays, int32 / fp32, contiguous) -> the concatenated,
  * offset-adjusted SoA of chg_batch in one pass (BatchedGraph.from_graphs, model.py:820-899, without
  * per-graph tensor ops).  counts [B][4] = atoms, directed edges, undirected bonds, angles; ptrs [B][8] =
@@ -310,7 +330,8 @@ void chg_graph_free(chg_graph* g);
  * ang_i[A] ang_di[A] ang_j[A] ang_dj[A]; fbuf (fp32) = frac[N*3] image[Ed*3] lattice[B*9];
  * flags_out[0/1] = edges sorted by centre / angles sorted by bond i within every graph;
  * flags_out[2] = index (in the batch) of the first atom whose atomic number is outside [1, CHG_MAX_Z],
- * or -1 (the caller raises IndexError like the reference's nn.Embedding, tests/test_encoders.py:25-28). */
+ * or -1 (the caller raises IndexError like the reference's nn.Embedding, tests/test_encoders.py:25-28);
+ * flags_out[3] = number of distinct bonds that occur in angles (n_short of chg_build_csr: no device sync). */
 int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf,
                         float* fbuf, int32_t* flags_out);
 
