@@ -250,24 +250,38 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
     implementations of the host packing / the segment structures (kept as the checkers of the C paths)."""
     device = torch.device(device)
     B = len(graphs)
-    # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
+    # fast path: chgnet_b200.CrystalGraph caches its sizes and raw data pointers (graph.pack_info), so the per-graph
+    # Python work is one attribute call; any other graph-like object goes through the generic reads below
+    fast = None
+    if native_pack and B > 0:
+        infos = [g.pack_info() if hasattr(g, "pack_info") else False for g in graphs]
+        if all(i is not False for i in infos):
+            fast = (np.stack([i[0] for i in infos]), np.stack([i[1] for i in infos]))
     ag_l, bg_l = [], []
-    for g in graphs:
-        ag, bg = g.atom_graph, g.bond_graph
-        if ag.dim() != 2:  # structure with every atom isolated (model.py:841-843)
-            ag = ag.reshape(0, 2)
-        if bg.dim() != 2:
-            bg = bg.reshape(0, 5)
-        ag_l.append(ag)
-        bg_l.append(bg)
-    n_at = [g.atomic_number.shape[0] for g in graphs]
-    n_ed = [a.shape[0] for a in ag_l]
-    n_eu = [g.undirected2directed.shape[0] for g in graphs]
-    n_an = [b.shape[0] for b in bg_l]
-    N, Ed, Eu, A = sum(n_at), sum(n_ed), sum(n_eu), sum(n_an)
-    for g, e_d, e_u in zip(graphs, n_ed, n_eu):
-        if e_d != 2 * e_u or g.directed2undirected.shape[0] != e_d:
+    if fast is not None:
+        cnt = fast[0]
+        n_at, n_ed, n_eu, n_an = (cnt[:, k].tolist() for k in range(4))
+        bad = np.nonzero((cnt[:, 1] != 2 * cnt[:, 2]))[0]
+        if len(bad) or any(g.directed2undirected.shape[0] != e for g, e in zip(graphs, n_ed)):
             raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
+    else:
+        # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
+        for g in graphs:
+            ag, bg = g.atom_graph, g.bond_graph
+            if ag.dim() != 2:  # structure with every atom isolated (model.py:841-843)
+                ag = ag.reshape(0, 2)
+            if bg.dim() != 2:
+                bg = bg.reshape(0, 5)
+            ag_l.append(ag)
+            bg_l.append(bg)
+        n_at = [g.atomic_number.shape[0] for g in graphs]
+        n_ed = [a.shape[0] for a in ag_l]
+        n_eu = [g.undirected2directed.shape[0] for g in graphs]
+        n_an = [b.shape[0] for b in bg_l]
+        for g, e_d, e_u in zip(graphs, n_ed, n_eu):
+            if e_d != 2 * e_u or g.directed2undirected.shape[0] != e_d:
+                raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
+    N, Ed, Eu, A = sum(n_at), sum(n_ed), sum(n_eu), sum(n_an)
 
     src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
 
@@ -407,10 +421,13 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         n_int, n_flt = 2 * N + 3 * Ed + Eu + 5 * A, 3 * N + 3 * Ed + 9 * B
         pin = device.type == "cuda"
         ibuf_h, fbuf_h = _staging_buffer(max(n_int, 1), torch.int32, pin), _staging_buffer(max(n_flt, 1), torch.float32, pin)
-        counts = np.ascontiguousarray(np.array([n_at, n_ed, n_eu, n_an], dtype=np.int64).T)
-        ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
-                            for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
-                                      g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
+        if fast is not None:
+            counts, ptrs = np.ascontiguousarray(fast[0]), np.ascontiguousarray(fast[1])
+        else:
+            counts = np.ascontiguousarray(np.array([n_at, n_ed, n_eu, n_an], dtype=np.int64).T)
+            ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
+                                for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
+                                          g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
         flags = (ctypes.c_int32 * 4)()
         rc = lib.chg_pack_batch_host(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(), flags)
         if rc != 0:
@@ -432,7 +449,7 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
                 ang_di, ang_j, ang_dj, bool(flags[0]), bool(flags[1]), (n_int + n_flt) * 4 if device.type != "cpu" else 0)
 
     n_short_host = -1  # number of bond-graph bonds, counted by the C packer (no device sync needed later)
-    use_native = native_pack and B > 0 and src_dev.type == "cpu" and _graphs_are_packable(graphs, ag_l, bg_l)
+    use_native = fast is not None or (native_pack and B > 0 and src_dev.type == "cpu" and _graphs_are_packable(graphs, ag_l, bg_l))
     (z, owner, center, nbr, d2u, u2d, image, frac_t, lattice, ang_atom, ang_i, ang_di, ang_j, ang_dj, edges_sorted,
      angles_sorted, h2d) = pack_native() if use_native else pack_legacy()
 

@@ -7,26 +7,27 @@
 // SiLU x sigmoid in the epilogue, and the segmented reduction over the centre-sorted (bond-i-sorted) rows done
 // inside the CTA: the [rows, 64] message never goes to HBM.
 //
-// One persistent CTA per SM, 13 warps (416 threads, <= 128 registers each), three roles connected by mbarriers:
+// One persistent CTA per SM, 17 warps (544 threads, <= 96 registers each), three roles connected by mbarriers:
 //
-//   warps 4-7   producer of the CORE half, warps 8-11 producer of the GATE half of every 128-row tile (two
+//   warps 8-11  producer of the CORE half, warps 12-15 producer of the GATE half of every 128-row tile (two
 //               independent groups, so one gathers while the other converts): 16 lanes x float4 per 64-float
 //               half-row (coalesced) gather + add the first-layer rows, SiLU, store the [128 x 64] half-tile to
 //               shared memory (16-byte chunks XOR-swizzled by row), group barrier, then thread t reads ITS row
 //               (conflict-free), splits hi / lo and tcgen05.st's it into the group's A stage of tensor memory;
 //               BondConv also writes save_pre
-//   warp 12     MMA: one lane issues 8 k-steps x 3 split terms of tcgen05.mma.kind::tf32 (M=128, N=64) per
+//   warp 16     MMA: one lane issues 8 k-steps x 3 split terms of tcgen05.mma.kind::tf32 (M=128, N=64) per
 //               half into one of two D stages, tcgen05.commit -> mbarriers
-//   warps 0-3   epilogue: thread t owns row t: tcgen05.ld sweeps (mean, variance, normalise: LayerNorm is
-//               in-thread, no shuffles), SiLU x sigmoid -> o row -> shared memory; then the 8 half-warps each
-//               reduce a 16-row strip (x bond weights, read coalesced) over runs of equal segment id: complete
-//               segments are stored, strip-boundary partials go to `parts`
+//   warps 0-3   epilogue of the CORE half, warps 4-7 of the GATE half: thread t owns (half of) row t: two
+//               tcgen05.ld sweeps (shifted one-pass mean / variance, then normalise: LayerNorm is in-thread, no
+//               shuffles), SiLU (core) / sigmoid (gate) -> two [128 x 64] tiles in shared memory; then each of the
+//               8 warps reduces a 16-row strip (core x gate x bond weights, the weights read coalesced) over runs
+//               of equal segment id: complete segments are stored, strip-boundary partials go to `parts`
 //
 // A tiny second kernel (seg_stitch) adds the strip partials of every segment that spans strips, in strip
 // order (deterministic, no atomics), and zeroes empty segments.
 //
 // TMEM: 2 x (64 hi + 64 lo) A + 2 x 128 D = 512 columns.  Shared memory: 4 weight images (64 KB) + 2 half-tiles
-// (64 KB) + the o tile (32 KB) + indices.
+// (64 KB) + the core / gate output tiles (64 KB) + indices.
 #include "gated_common.cuh"
 #include "tc.cuh"
 
@@ -34,7 +35,7 @@ namespace chg {
 namespace gated {
 namespace {
 
-constexpr int WS_THREADS = 416;  // 13 warps
+constexpr int WS_THREADS = 544;  // 17 warps: 8 epilogue, 8 producer, 1 MMA
 constexpr int TR = 128;          // rows per tile
 constexpr int HALF_BYTES = TR * 64 * 4;
 constexpr int IMG_BYTES = 64 * 64 * 4;
@@ -43,10 +44,10 @@ constexpr int STRIP = 16;        // rows per reduction strip (one half-warp)
 struct WsSmem {
   static constexpr int IMG_OFF = 0;                          // Bc_hi, Bc_lo, Bg_hi, Bg_lo
   static constexpr int HS_OFF = 4 * IMG_BYTES;               // 2 x [128][64] fp32, swizzled (core | gate producer)
-  static constexpr int O_OFF = HS_OFF + 2 * HALF_BYTES;      // [128][64] fp32, swizzled
-  static constexpr int GIDX_OFF = O_OFF + HALF_BYTES;        // 2 groups x 3 x 128 int
-  static constexpr int EIDX_OFF = GIDX_OFF + 2 * 3 * TR * 4;  // 2 x 128 int
-  static constexpr int B2_OFF = EIDX_OFF + 2 * TR * 4;       // 128 floats
+  static constexpr int O_OFF = HS_OFF + 2 * HALF_BYTES;      // 2 x [128][64] fp32, swizzled: silu(core), sigmoid(gate)
+  static constexpr int GIDX_OFF = O_OFF + 2 * HALF_BYTES;    // 2 groups x 3 x 128 int
+  static constexpr int EIDX_OFF = GIDX_OFF + 2 * 3 * TR * 4;  // 4 x 128 int: segment id, weight row, segment begin / end
+  static constexpr int B2_OFF = EIDX_OFF + 4 * TR * 4;       // 128 floats
   static constexpr int LN_OFF = B2_OFF + 128 * 4;            // 256 floats
   static constexpr int TOTAL = LN_OFF + 256 * 4;
 };
@@ -95,79 +96,60 @@ __device__ __forceinline__ void build_image_ws(uint8_t* hi, uint8_t* lo, const f
 }
 
 // ---- epilogue helper: one 64-wide half of row t out of tensor memory ----------------------------------------
-// p = acc + b2; y = LN(p) (or p); CORE: a[j] = silu(y[j]);  GATE: a[j] *= sigmoid(y[j]).  save_row != null: p is stored.
+// p = acc + b2; y = LN(p) (or p); CORE: out = silu(y);  GATE: out = sigmoid(y); out -> row t of the swizzled tile.
+// LayerNorm statistics in one sweep, shifted by the row's first element (no cancellation for |mean| >> std).
 template <bool GATE>
 __device__ __forceinline__ void epilogue_half(uint32_t d_addr, const float* s_b2, const float* s_gamma, const float* s_beta,
-                                              bool use_ln, float (&a)[64], float* save_row) {
+                                              bool use_ln, uint8_t* s_tile, int t, float* save_row) {
   float mean = 0.f, rstd = 1.f;
   if (use_ln) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f, x0 = 0.f;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t v[16];
-      tc::tmem_ld16(d_addr + g * 16, v);
+    for (int g = 0; g < 2; ++g) {
+      uint32_t v[32];
+      tc::tmem_ld32(d_addr + g * 32, v);
       tc::tmem_ld_wait();
+      if (g == 0) x0 = __uint_as_float(v[0]) + s_b2[0];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = lds4(s_b2 + g * 16 + q * 4);  // broadcast
-        s.x += __uint_as_float(v[q * 4]) + b.x;
-        s.y += __uint_as_float(v[q * 4 + 1]) + b.y;
-        s.z += __uint_as_float(v[q * 4 + 2]) + b.z;
-        s.w += __uint_as_float(v[q * 4 + 3]) + b.w;
+      for (int q = 0; q < 8; ++q) {
+        const float4 b = lds4(s_b2 + g * 32 + q * 4);  // broadcast
+        const float d0 = __uint_as_float(v[q * 4]) + b.x - x0, d1 = __uint_as_float(v[q * 4 + 1]) + b.y - x0;
+        const float d2 = __uint_as_float(v[q * 4 + 2]) + b.z - x0, d3 = __uint_as_float(v[q * 4 + 3]) + b.w - x0;
+        s1 += d0 + d1;
+        s1b += d2 + d3;
+        s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+        s2b = fmaf(d2, d2, fmaf(d3, d3, s2b));
       }
     }
-    mean = ((s.x + s.y) + (s.z + s.w)) * (1.f / 64.f);
-    s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t v[16];
-      tc::tmem_ld16(d_addr + g * 16, v);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b = lds4(s_b2 + g * 16 + q * 4);
-        const float d0 = __uint_as_float(v[q * 4]) + b.x - mean;
-        const float d1 = __uint_as_float(v[q * 4 + 1]) + b.y - mean;
-        const float d2 = __uint_as_float(v[q * 4 + 2]) + b.z - mean;
-        const float d3 = __uint_as_float(v[q * 4 + 3]) + b.w - mean;
-        s.x = fmaf(d0, d0, s.x);
-        s.y = fmaf(d1, d1, s.y);
-        s.z = fmaf(d2, d2, s.z);
-        s.w = fmaf(d3, d3, s.w);
-      }
-    }
-    rstd = 1.f / sqrtf(((s.x + s.y) + (s.z + s.w)) * (1.f / 64.f) + LN_EPS);
+    const float m1 = (s1 + s1b) * (1.f / 64.f);
+    mean = x0 + m1;
+    rstd = 1.f / sqrtf(fmaxf((s2 + s2b) * (1.f / 64.f) - m1 * m1, 0.f) + LN_EPS);
   }
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint32_t v[16];
-    tc::tmem_ld16(d_addr + g * 16, v);
+  for (int g = 0; g < 2; ++g) {
+    uint32_t v[32];
+    tc::tmem_ld32(d_addr + g * 32, v);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 b = lds4(s_b2 + g * 16 + q * 4);
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = lds4(s_b2 + g * 32 + q * 4);
       float4 p = make_float4(__uint_as_float(v[q * 4]) + b.x, __uint_as_float(v[q * 4 + 1]) + b.y,
                              __uint_as_float(v[q * 4 + 2]) + b.z, __uint_as_float(v[q * 4 + 3]) + b.w);
-      if (save_row != nullptr) stg4(save_row + g * 16 + q * 4, p);
+      if (save_row != nullptr) stg4(save_row + g * 32 + q * 4, p);
       if (use_ln) {
-        const float4 ga = lds4(s_gamma + g * 16 + q * 4), be = lds4(s_beta + g * 16 + q * 4);
+        const float4 ga = lds4(s_gamma + g * 32 + q * 4), be = lds4(s_beta + g * 32 + q * 4);
         p.x = fmaf((p.x - mean) * rstd, ga.x, be.x);
         p.y = fmaf((p.y - mean) * rstd, ga.y, be.y);
         p.z = fmaf((p.z - mean) * rstd, ga.z, be.z);
         p.w = fmaf((p.w - mean) * rstd, ga.w, be.w);
       }
-      const int j = g * 16 + q * 4;
+      float4 o;
       if (GATE) {
-        a[j] *= sigmoid_f(p.x);
-        a[j + 1] *= sigmoid_f(p.y);
-        a[j + 2] *= sigmoid_f(p.z);
-        a[j + 3] *= sigmoid_f(p.w);
+        o = make_float4(sigmoid_f(p.x), sigmoid_f(p.y), sigmoid_f(p.z), sigmoid_f(p.w));
       } else {
-        a[j] = silu_f(p.x);
-        a[j + 1] = silu_f(p.y);
-        a[j + 2] = silu_f(p.z);
-        a[j + 3] = silu_f(p.w);
+        o = make_float4(silu_f(p.x), silu_f(p.y), silu_f(p.z), silu_f(p.w));
       }
+      *reinterpret_cast<float4*>(s_tile + swz(t, g * 8 + q)) = o;
     }
   }
 }
@@ -199,11 +181,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
       tc::mbar_init(&bars.a_full[i], 128);
       tc::mbar_init(&bars.a_empty[i], 1);
       tc::mbar_init(&bars.d_full[i], 1);
-      tc::mbar_init(&bars.d_empty[i], 128);
+      tc::mbar_init(&bars.d_empty[i], 256);
     }
     tc::mbar_fence_init();
   }
-  if (warp == 12) tc::tmem_alloc(&s_tmem, 512);
+  if (warp == 16) tc::tmem_alloc(&s_tmem, 512);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -212,10 +194,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
   // TMEM columns: A stage h (h = 0 core, 1 gate) at h*128 (hi) / h*128 + 64 (lo); D stage s at 256 + s*128
   // (core 0..63 | gate 64..127)
 
-  if (warp >= 4 && warp < 12) {
+  if (warp >= 8 && warp < 16) {
     // ============================ producer groups (gather -> SiLU -> A operand) ============================
-    const int half = (warp - 4) >> 2;            // 0: core columns, 1: gate columns
-    const int gt = tid - 128 - half * 128;       // 0..127 inside the group; also this thread's tile row / TMEM lane
+    const int half = (warp - 8) >> 2;            // 0: core columns, 1: gate columns
+    const int gt = tid - 256 - half * 128;       // 0..127 inside the group; also this thread's tile row / TMEM lane
     const int tx = gt & 15, ty = gt >> 4;        // 16 lanes per row, 8 rows per pass
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     int* gi = s_gidx + half * 3 * TR;
@@ -273,7 +255,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
       tc::fence_before_sync();
       mbar_arrive(&bars.a_full[half]);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_tf32(128, 64);
@@ -302,87 +284,98 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
         }
       }
     }
-  } else if (warp < 4) {
-    // ============================ epilogue warpgroup ============================
-    const int t = tid;  // tile row == TMEM lane
+  } else if (warp < 8) {
+    // ============================ epilogue: warps 0-3 core half, warps 4-7 gate half ============================
+    const int eh = warp >> 2;        // 0: core, 1: gate
+    const int t = tid & 127;         // tile row == TMEM lane
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const int hw = t >> 4, l = t & 15;  // reduction: half-warp hw owns rows 16 hw .. +15, lane l the float4 column chunk l
+    int* s_seg = s_eidx;             // segment id of every tile row
+    int* s_wrow = s_eidx + TR;       // row of the bond weight (ATOM: d2u; BOND: slot j - slot i is the segment id)
+    int* s_sa = s_eidx + 2 * TR;     // ptr[seg], ptr[seg + 1] of every tile row
+    int* s_sb = s_eidx + 3 * TR;
+    uint8_t* s_o1 = s_o;
+    uint8_t* s_o2 = s_o + HALF_BYTES;
     int tl = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
       const int base = tile * TR;
       const int ds = tl & 1;
       {
         const int r = min(base + t, a.n_rows - 1);
-        s_eidx[t] = a.idx0[r];
-        s_eidx[TR + t] = MODE == BOND ? a.idx1[r] : a.idx2[r];  // row of the (second) weight
+        if (eh == 0) {
+          const int seg = a.idx0[r];
+          s_seg[t] = seg;
+          s_sa[t] = __ldg(a.ptr + seg);
+          s_sb[t] = __ldg(a.ptr + seg + 1);
+        } else {
+          s_wrow[t] = MODE == BOND ? a.idx1[r] : a.idx2[r];
+        }
       }
       tc::mbar_wait(&bars.d_full[ds], (tl >> 1) & 1);
       tc::fence_after_sync();
-      const uint32_t d_acc = tmem_base + 256 + ds * 128 + lane_sel;
-      float o[64];
-      float* save_row = (a.save_p != nullptr && base + t < a.n_rows) ? a.save_p + (size_t)(base + t) * 128 : nullptr;
-      epilogue_half<false>(d_acc, s_b2, s_ln, s_ln + 64, use_ln, o, save_row);
-      epilogue_half<true>(d_acc + 64, s_b2 + 64, s_ln + 128, s_ln + 192, use_ln, o, save_row != nullptr ? save_row + 64 : nullptr);
+      const uint32_t d_acc = tmem_base + 256 + ds * 128 + eh * 64 + lane_sel;
+      float* save_row = (a.save_p != nullptr && base + t < a.n_rows) ? a.save_p + (size_t)(base + t) * 128 + eh * 64 : nullptr;
+      if (eh == 0) {
+        epilogue_half<false>(d_acc, s_b2, s_ln, s_ln + 64, use_ln, s_o1, t, save_row);
+      } else {
+        epilogue_half<true>(d_acc, s_b2 + 64, s_ln + 128, s_ln + 192, use_ln, s_o2, t, save_row);
+      }
       tc::fence_before_sync();
       mbar_arrive(&bars.d_empty[ds]);  // the accumulator stage can be overwritten
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        *reinterpret_cast<float4*>(s_o + swz(t, c)) = make_float4(o[c * 4], o[c * 4 + 1], o[c * 4 + 2], o[c * 4 + 3]);
-      tc::wg_barrier(3, 128);
+      tc::wg_barrier(3, 256);
 
-      // ---- segmented reduction of this half-warp's 16-row strip --------------------------------------------
-      const int strip_lo = base + hw * STRIP;
+      // ---- segmented reduction: warp w owns the 16-row strip w, lane l the columns 2l, 2l+1 ----------------
+      const int strip_lo = base + warp * STRIP;
       const int strip_hi = min(strip_lo + STRIP, a.n_rows);
       if (strip_lo < a.n_rows) {
-        float4 w[STRIP];
+        float2 w[STRIP];
 #pragma unroll
         for (int i = 0; i < STRIP; ++i) {
-          const int rr = hw * STRIP + i;
+          const int rr = warp * STRIP + i;
+          const float2 w0 = __ldg(reinterpret_cast<const float2*>(a.wgt + (size_t)s_wrow[rr] * 64) + lane);
           if (MODE == ATOM) {
-            w[i] = ldg4(a.wgt + (size_t)s_eidx[TR + rr] * 64 + l * 4);
+            w[i] = w0;
           } else {
-            w[i] = ldg4(a.wgt + (size_t)s_eidx[rr] * 64 + l * 4) * ldg4(a.wgt + (size_t)s_eidx[TR + rr] * 64 + l * 4);
+            const float2 wi = __ldg(reinterpret_cast<const float2*>(a.wgt + (size_t)s_seg[rr] * 64) + lane);
+            w[i] = make_float2(wi.x * w0.x, wi.y * w0.y);  // (o * w_i) * w_j
           }
         }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cur = s_eidx[hw * STRIP];
-        auto emit = [&](int seg, const float4& v) {
-          const int sa = __ldg(a.ptr + seg), sb = __ldg(a.ptr + seg + 1);
+        float2 acc = make_float2(0.f, 0.f);
+        int cur_row = warp * STRIP;  // first row of the current run
+        auto emit = [&](int row0, const float2& v) {
+          const int seg = s_seg[row0], sa = s_sa[row0], sb = s_sb[row0];
           float* dst;
           if (sa >= strip_lo && sb <= strip_hi) {
             dst = a.out + (size_t)seg * 64;  // the whole segment lies in this strip
           } else {
             dst = a.parts + ((size_t)(strip_lo / STRIP) * 2 + (sa < strip_lo ? 0 : 1)) * 64;
           }
-          stg4(dst + l * 4, v);
+          *reinterpret_cast<float2*>(dst + lane * 2) = v;
         };
 #pragma unroll
         for (int i = 0; i < STRIP; ++i) {
-          const int rr = hw * STRIP + i;
+          const int rr = warp * STRIP + i;
           if (strip_lo + i < strip_hi) {
-            const int seg = s_eidx[rr];
-            if (seg != cur) {
-              emit(cur, acc);
-              cur = seg;
-              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s_seg[rr] != s_seg[cur_row]) {
+              emit(cur_row, acc);
+              cur_row = rr;
+              acc = make_float2(0.f, 0.f);
             }
-            const float4 ov = *reinterpret_cast<const float4*>(s_o + swz(rr, l));
-            if (MODE == ATOM) {
-              acc = acc + ov * w[i];
-            } else {
-              acc = acc + ov * w[i];
-            }
+            const int off = swz(rr, lane >> 1) + (lane & 1) * 8;
+            const float2 c = *reinterpret_cast<const float2*>(s_o1 + off);
+            const float2 g = *reinterpret_cast<const float2*>(s_o2 + off);
+            acc.x = fmaf(c.x * g.x, w[i].x, acc.x);
+            acc.y = fmaf(c.y * g.y, w[i].y, acc.y);
           }
         }
-        emit(cur, acc);
+        emit(cur_row, acc);
       }
-      tc::wg_barrier(3, 128);  // the o tile and the index rows are free for the next tile
+      tc::wg_barrier(3, 256);  // the output tiles and the index rows are free for the next tile
     }
   }
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 12) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == 16) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // out[s] for every segment that spans more than one strip (sum of its strip partials, in strip order) and for

@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -308,13 +310,12 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
                                    int32_t* ibuf, float* fbuf, int32_t* flags_out) {
   CHG_CHECK_ARG(n_graphs >= 0, "negative size");
   CHG_CHECK_ARG(counts != nullptr && ptrs != nullptr && ibuf != nullptr && fbuf != nullptr && flags_out != nullptr, "null pointer");
-  int64_t N = 0, Ed = 0, Eu = 0, A = 0;
-  for (int g = 0; g < n_graphs; ++g) {
-    N += counts[4 * g];
-    Ed += counts[4 * g + 1];
-    Eu += counts[4 * g + 2];
-    A += counts[4 * g + 3];
-  }
+  // per-graph offsets (exclusive prefix sums of the counts)
+  std::vector<int64_t> off((size_t)(n_graphs + 1) * 4, 0);
+  for (int g = 0; g < n_graphs; ++g)
+    for (int k = 0; k < 4; ++k) off[(size_t)(g + 1) * 4 + k] = off[(size_t)g * 4 + k] + counts[4 * g + k];
+  const int64_t N = off[(size_t)n_graphs * 4], Ed = off[(size_t)n_graphs * 4 + 1], Eu = off[(size_t)n_graphs * 4 + 2],
+                A = off[(size_t)n_graphs * 4 + 3];
   CHG_CHECK_ARG(N < INT32_MAX && Ed < INT32_MAX && A < INT32_MAX, "batch too large for int32 indices");
   int32_t* z = ibuf;
   int32_t* owner = z + N;
@@ -330,56 +331,93 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
   float* frac = fbuf;
   float* image = frac + N * 3;
   float* lattice = image + Ed * 3;
-  bool edges_sorted = true, angles_sorted = true;
-  int64_t bad_z = -1;
-  static thread_local std::vector<uint8_t> in_bond_graph;  // one flag per bond of the batch
+  static thread_local std::vector<uint8_t> in_bond_graph;  // one flag per bond of the batch (bonds never cross graphs)
   in_bond_graph.assign((size_t)Eu, 0);
-  int64_t n_short = 0;
-  int64_t a_off = 0, e_off = 0, u_off = 0, g_off = 0;
-  for (int g = 0; g < n_graphs; ++g) {
-    const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
-    const void* const* p = ptrs + 8 * g;
-    if (n > 0) {
-      std::memcpy(z + a_off, p[0], (size_t)n * 4);
-      std::memcpy(frac + a_off * 3, p[1], (size_t)n * 12);
-      for (int64_t i = 0; i < n; ++i) {
-        owner[a_off + i] = g;
-        const int32_t zi = z[a_off + i];
-        if ((zi < 1 || zi > CHG_MAX_Z) && bad_z < 0) bad_z = a_off + i;
-      }
-    }
-    const int32_t* ag = static_cast<const int32_t*>(p[2]);
-    const int32_t* du = static_cast<const int32_t*>(p[4]);
-    for (int64_t e = 0; e < ed; ++e) {
-      center[e_off + e] = ag[2 * e] + (int32_t)a_off;
-      nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
-      d2u[e_off + e] = du[e] + (int32_t)u_off;
-      if (e > 0 && ag[2 * e] < ag[2 * e - 2]) edges_sorted = false;
-    }
-    if (ed > 0) std::memcpy(image + e_off * 3, p[3], (size_t)ed * 12);
-    const int32_t* ud = static_cast<const int32_t*>(p[5]);
-    for (int64_t u = 0; u < eu; ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
-    const int32_t* bg = static_cast<const int32_t*>(p[6]);
-    for (int64_t a = 0; a < an; ++a) {
-      ang_atom[g_off + a] = bg[5 * a] + (int32_t)a_off;
-      ang_i[g_off + a] = bg[5 * a + 1] + (int32_t)u_off;
-      ang_di[g_off + a] = bg[5 * a + 2] + (int32_t)e_off;
-      ang_j[g_off + a] = bg[5 * a + 3] + (int32_t)u_off;
-      ang_dj[g_off + a] = bg[5 * a + 4] + (int32_t)e_off;
-      if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) angles_sorted = false;
-      for (int which = 1; which <= 3; which += 2) {  // bond i, bond j
-        const int64_t u = u_off + bg[5 * a + which];
-        if (u >= 0 && u < Eu && !in_bond_graph[(size_t)u]) {
-          in_bond_graph[(size_t)u] = 1;
-          ++n_short;
+  uint8_t* bg_flag = in_bond_graph.data();
+
+  struct Partial {
+    bool edges_sorted = true, angles_sorted = true;
+    int64_t bad_z = -1, n_short = 0;
+  };
+  auto pack_range = [&](int g0, int g1, Partial& res) {
+    for (int g = g0; g < g1; ++g) {
+      const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
+      const int64_t a_off = off[(size_t)g * 4], e_off = off[(size_t)g * 4 + 1], u_off = off[(size_t)g * 4 + 2], g_off = off[(size_t)g * 4 + 3];
+      const void* const* p = ptrs + 8 * g;
+      if (n > 0) {
+        std::memcpy(z + a_off, p[0], (size_t)n * 4);
+        std::memcpy(frac + a_off * 3, p[1], (size_t)n * 12);
+        for (int64_t i = 0; i < n; ++i) {
+          owner[a_off + i] = g;
+          const int32_t zi = z[a_off + i];
+          if ((zi < 1 || zi > CHG_MAX_Z) && res.bad_z < 0) res.bad_z = a_off + i;
         }
       }
+      const int32_t* ag = static_cast<const int32_t*>(p[2]);
+      const int32_t* du = static_cast<const int32_t*>(p[4]);
+      for (int64_t e = 0; e < ed; ++e) {
+        center[e_off + e] = ag[2 * e] + (int32_t)a_off;
+        nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
+        d2u[e_off + e] = du[e] + (int32_t)u_off;
+        if (e > 0 && ag[2 * e] < ag[2 * e - 2]) res.edges_sorted = false;
+      }
+      if (ed > 0) std::memcpy(image + e_off * 3, p[3], (size_t)ed * 12);
+      const int32_t* ud = static_cast<const int32_t*>(p[5]);
+      for (int64_t u = 0; u < eu; ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
+      const int32_t* bg = static_cast<const int32_t*>(p[6]);
+      for (int64_t a = 0; a < an; ++a) {
+        ang_atom[g_off + a] = bg[5 * a] + (int32_t)a_off;
+        ang_i[g_off + a] = bg[5 * a + 1] + (int32_t)u_off;
+        ang_di[g_off + a] = bg[5 * a + 2] + (int32_t)e_off;
+        ang_j[g_off + a] = bg[5 * a + 3] + (int32_t)u_off;
+        ang_dj[g_off + a] = bg[5 * a + 4] + (int32_t)e_off;
+        if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) res.angles_sorted = false;
+        for (int which = 1; which <= 3; which += 2) {  // bond i, bond j: this graph's own range of the flag array
+          const int64_t ul = bg[5 * a + which];
+          if (ul >= 0 && ul < eu && !bg_flag[u_off + ul]) {
+            bg_flag[u_off + ul] = 1;
+            ++res.n_short;
+          }
+        }
+      }
+      std::memcpy(lattice + (size_t)g * 9, p[7], 36);
     }
-    std::memcpy(lattice + (size_t)g * 9, p[7], 36);
-    a_off += n;
-    e_off += ed;
-    u_off += eu;
-    g_off += an;
+  };
+
+  // graphs are independent: contiguous ranges of graphs of about equal bytes per worker thread
+  const int64_t total_items = N * 5 + Ed * 6 + Eu + A * 5;
+  int n_thr = 1;
+  if (total_items > (1 << 20)) {
+    const unsigned hc = std::thread::hardware_concurrency();
+    n_thr = (int)std::min<int64_t>(std::min<unsigned>(hc == 0 ? 4 : hc, 16), std::max<int64_t>(1, total_items >> 19));
+    n_thr = std::min(n_thr, n_graphs);
+    if (const char* e = std::getenv("CHG_PACK_THREADS")) n_thr = std::max(1, std::min(std::atoi(e), std::max(1, n_graphs)));
+  }
+  std::vector<Partial> parts((size_t)n_thr);
+  if (n_thr <= 1) {
+    pack_range(0, n_graphs, parts[0]);
+  } else {
+    auto weight = [&](int g) { return off[(size_t)g * 4] * 5 + off[(size_t)g * 4 + 1] * 6 + off[(size_t)g * 4 + 2] + off[(size_t)g * 4 + 3] * 5; };
+    std::vector<int> cut((size_t)n_thr + 1, n_graphs);
+    cut[0] = 0;
+    for (int t = 1, g = 0; t < n_thr; ++t) {
+      const int64_t target = total_items * t / n_thr;
+      while (g < n_graphs && weight(g) < target) ++g;
+      cut[t] = g;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)n_thr - 1);
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(pack_range, cut[t], cut[t + 1], std::ref(parts[t]));
+    pack_range(cut[0], cut[1], parts[0]);
+    for (auto& th : pool) th.join();
+  }
+  bool edges_sorted = true, angles_sorted = true;
+  int64_t bad_z = -1, n_short = 0;
+  for (const Partial& r : parts) {
+    edges_sorted = edges_sorted && r.edges_sorted;
+    angles_sorted = angles_sorted && r.angles_sorted;
+    if (r.bad_z >= 0 && (bad_z < 0 || r.bad_z < bad_z)) bad_z = r.bad_z;
+    n_short += r.n_short;
   }
   flags_out[0] = edges_sorted ? 1 : 0;
   flags_out[1] = angles_sorted ? 1 : 0;

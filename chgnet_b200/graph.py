@@ -78,6 +78,41 @@ class CrystalGraph:
                 f" 2 * number of undirected indices ({2 * len(undirected2directed)})!"
             )
 
+    def __setattr__(self, name: str, value: Any) -> None:
+        if name in _TENSOR_FIELDS:
+            object.__setattr__(self, "_pack", None)  # cached raw-pointer view of the tensors (pack_info) is stale
+        object.__setattr__(self, name, value)
+
+    def pack_info(self):
+        """``(counts, ptrs)`` for the C batch packer (``chg_pack_batch_host``): int64 [4] = atoms, directed edges,
+        bonds, angles and uint64 [8] = the data pointers of the eight tensor fields - or ``False`` when the tensors are
+        not host-resident, contiguous int32 / fp32 (the packer then goes through the generic torch path).  Cached; the
+        cache is dropped whenever a tensor field is reassigned."""
+        cached = self.__dict__.get("_pack")
+        if cached is not None:
+            return cached
+        import numpy as np
+
+        ints = (self.atomic_number, self.atom_graph, self.directed2undirected, self.undirected2directed, self.bond_graph)
+        flts = (self.atom_frac_coord, self.neighbor_image, self.lattice)
+        ok = (all(t.dtype == torch.int32 and t.is_contiguous() and t.device.type == "cpu" for t in ints)
+              and all(t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu" for t in flts)
+              and self.lattice.numel() == 9
+              and (self.atom_graph.dim() == 2 or self.atom_graph.numel() == 0)
+              and (self.bond_graph.dim() == 2 or self.bond_graph.numel() == 0))
+        if not ok:
+            info = False
+        else:
+            n_ed = self.atom_graph.shape[0] if self.atom_graph.dim() == 2 else 0
+            n_an = self.bond_graph.shape[0] if self.bond_graph.dim() == 2 else 0
+            counts = np.array([self.atomic_number.shape[0], n_ed, self.undirected2directed.shape[0], n_an], dtype=np.int64)
+            ptrs = np.array([t.data_ptr() for t in (self.atomic_number, self.atom_frac_coord, self.atom_graph, self.neighbor_image,
+                                                    self.directed2undirected, self.undirected2directed, self.bond_graph,
+                                                    self.lattice)], dtype=np.uint64)
+            info = (counts, ptrs)
+        object.__setattr__(self, "_pack", info)
+        return info
+
     def to(self, device: str | torch.device = "cpu") -> CrystalGraph:
         """Return a copy of the graph with every tensor on ``device``."""
         kw = self.to_dict()
