@@ -216,6 +216,12 @@ __global__ void gather_ptr_kernel(const int32_t* __restrict__ ptr_j, const int32
 inline unsigned blocks(int n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace
+
+// out[0..n] = exclusive prefix sums of in[0..n) (out[n] = total); sums: >= 4096 int32 of scratch.  Shared with
+// graph_device.cu.
+int exclusive_scan_i32(const int32_t* in, int n, int32_t* out, int32_t* sums, cudaStream_t st) {
+  return exclusive_scan(in, n, out, sums, st);
+}
 }  // namespace chg
 
 using namespace chg;
@@ -317,5 +323,27 @@ extern "C" int chg_build_csr(const chg_csr_in* in, const chg_csr_out* out, int32
     set_error("chg_build_csr: launch failed: %s", cudaGetErrorString(e));
     return CHG_ERR_CUDA;
   }
+  return CHG_OK;
+}
+
+// number of distinct bonds that occur as bond i or bond j of an angle (n_short of chg_build_csr) for index arrays that
+// live on the device (the device graph builder): mark -> scan -> one int32 to the host (synchronises the stream).
+extern "C" int chg_bond_graph_count(const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles, int32_t n_bonds,
+                                    int32_t* scratch /* 2 * (n_bonds + 1) + 4096 int32 */, int32_t* count_out, void* stream) {
+  CHG_CHECK_ARG(n_angles >= 0 && n_bonds >= 0 && count_out != nullptr, "bad arguments");
+  *count_out = 0;
+  if (n_angles == 0 || n_bonds == 0) return CHG_OK;
+  CHG_CHECK_ARG(ang_i && ang_j && scratch, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  int32_t* mask = scratch;
+  int32_t* slot = mask + (n_bonds + 1);
+  int32_t* sums = slot + (n_bonds + 1);
+  CHG_CUDA(cudaMemsetAsync(mask, 0, (size_t)(n_bonds + 1) * 4, st));
+  mark_kernel<<<blocks(n_angles), 256, 0, st>>>(ang_i, ang_j, n_angles, mask);
+  count_launch();
+  const int rc = exclusive_scan_i32(mask, n_bonds, slot, sums, st);
+  if (rc != CHG_OK) return rc;
+  CHG_CUDA(cudaMemcpyAsync(count_out, slot + n_bonds, 4, cudaMemcpyDeviceToHost, st));
+  CHG_CUDA(cudaStreamSynchronize(st));
   return CHG_OK;
 }

@@ -150,6 +150,10 @@ int bond_conv_fwd_tc(const FwdArgs& a, cudaStream_t stream);
 int atom_conv_bwd_tc(const BwdArgs& a, cudaStream_t stream);
 int bond_conv_bwd_tc(const BwdArgs& a, cudaStream_t stream);
 
+// warp-specialised tcgen05 reverse kernels (gated_ws.cu): same outputs as gated_bwd_kernel<MODE, false>
+int atom_conv_bwd_ws(const BwdArgs& a, cudaStream_t stream);
+int bond_conv_bwd_ws(const BwdArgs& a, cudaStream_t stream);
+
 // warp-specialised tcgen05 message + aggregation kernels (gated_ws.cu); `parts` = strip partials workspace
 int atom_conv_fused_ws(const float* pcn, const float* pe, const float* wag, const int32_t* center, const int32_t* nbr,
                        const int32_t* d2u, const int32_t* ptr_c, int n_edges, int n_atoms, const float* w2t, const float* b2,

@@ -481,3 +481,326 @@ extern "C" int chg_bond_conv_fused(const float* pij, const float* px, const floa
   if (rc != CHG_OK) return rc;
   return chg_segment_sum(work, 64, nullptr, ptr_i, n_slots, n_angles, 0, agg, 64, stream);
 }
+
+// =====================================================================================================================
+// Reverse of the AtomConv / BondConv message (same entry points and arithmetic as gated_bwd_kernel<MODE, false> in
+// gated.cu; reference: autograd of layers.py:113-121, 238-249): warp-specialised tcgen05 version.
+//
+//   warps 0-7   P  16 lanes x float4 per 64-wide half-row: saved p -> LayerNorm statistics (shuffles) -> gates,
+//                  bond-weight gradients (stored), LayerNorm reverse -> g_p tile in shared memory (two swizzled
+//                  halves); group barrier; then thread t converts ITS half-row (t < 128: core, else gate) hi / lo into
+//                  the A operand in tensor memory
+//   warp 16     M  one lane: g_h = g_p . W2 per half (8 k-steps x 3 split terms of tcgen05.mma.kind::tf32 each)
+//   warps 8-15  F  thread t reads its half-row of the accumulator (tcgen05.ld) into a shared-memory tile; group
+//                  barrier; then 16 lanes x float4 per half-row: g_pre = g_h * silu'(pre), pre recomputed from the
+//                  first-layer rows (AtomConv) or read from save_pre (BondConv), coalesced stores
+// TMEM: A (64 hi + 64 lo) x 2 halves = 256 columns, D 2 stages x 128 = 256 columns.
+// =====================================================================================================================
+namespace chg {
+namespace gated {
+namespace {
+
+struct WsBwdSmem {
+  static constexpr int IMG_OFF = 0;                         // W2 images: core hi, lo, gate hi, lo
+  static constexpr int T1_OFF = 4 * IMG_BYTES;              // g_p tile: 2 x [128][64] fp32 swizzled
+  static constexpr int T2_OFF = T1_OFF + 2 * HALF_BYTES;    // g_h tile: 2 x [128][64] fp32 swizzled
+  static constexpr int PIDX_OFF = T2_OFF + 2 * HALF_BYTES;  // 3 x 128 int (P group)
+  static constexpr int FIDX_OFF = PIDX_OFF + 3 * TR * 4;    // 3 x 128 int (F group)
+  static constexpr int LN_OFF = FIDX_OFF + 3 * TR * 4;      // 256 floats
+  static constexpr int TOTAL = LN_OFF + 256 * 4;
+};
+
+struct WsBwdBars {
+  uint64_t a_full, a_empty;
+  uint64_t d_full[2], d_empty[2];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_bwd_kernel(const BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* s_img = smem_raw + WsBwdSmem::IMG_OFF;
+  uint8_t* s_t1 = smem_raw + WsBwdSmem::T1_OFF;
+  uint8_t* s_t2 = smem_raw + WsBwdSmem::T2_OFF;
+  int* s_pidx = reinterpret_cast<int*>(smem_raw + WsBwdSmem::PIDX_OFF);
+  int* s_fidx = reinterpret_cast<int*>(smem_raw + WsBwdSmem::FIDX_OFF);
+  float* s_ln = reinterpret_cast<float*>(smem_raw + WsBwdSmem::LN_OFF);
+  __shared__ __align__(8) WsBwdBars bars;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool use_ln = a.ln != nullptr;
+  const int n_tiles = (a.n_rows + TR - 1) / TR;
+
+  // g_h[k] = sum_c g_p[c] W2[c][k]: image element (n = k, kk = c) = w2[c][k]
+  build_image_ws(s_img, s_img + IMG_BYTES, a.w2, 64, 0, tid);
+  build_image_ws(s_img + 2 * IMG_BYTES, s_img + 3 * IMG_BYTES, a.w2 + 64 * 64, 64, 0, tid);
+  if (tid < 256) s_ln[tid] = use_ln ? a.ln[tid] : 0.f;
+  if (tid == 0) {
+    tc::mbar_init(&bars.a_full, 256);
+    tc::mbar_init(&bars.a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&bars.d_full[i], 1);
+      tc::mbar_init(&bars.d_empty[i], 256);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 16) tc::tmem_alloc(&s_tmem, 512);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = s_tmem;
+  // TMEM columns: A half h at h*128 (hi) / h*128 + 64 (lo); D stage s at 256 + s*128 (core 0..63 | gate 64..127)
+
+  if (warp < 8) {
+    // ============================ P: saved p -> g_p -> A operand ============================
+    const int t = tid;                   // 0..255
+    const int tx = t & 15, ty = t >> 4;  // 16 lanes per row, 16 rows per pass
+    const int c0 = tx * 4;
+    const int crow = t & 127, chalf = t >> 7;  // conversion: this thread's tile row and half
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int base = tile * TR;
+      if (t < TR) {
+        const int r = min(base + t, a.n_rows - 1);
+        s_pidx[t] = a.idx0[r];
+        s_pidx[TR + t] = a.idx1[r];
+        if (MODE == ATOM) s_pidx[2 * TR + t] = a.idx2[r];
+      }
+      tc::wg_barrier(1, 256);  // indices visible; every thread has converted the previous tile
+      float4 g1, g2, b1, b2v;
+      if (use_ln) {
+        g1 = lds4(s_ln + c0);
+        b1 = lds4(s_ln + 64 + c0);
+        g2 = lds4(s_ln + 128 + c0);
+        b2v = lds4(s_ln + 192 + c0);
+      }
+#pragma unroll 2
+      for (int pass = 0; pass < 8; ++pass) {
+        const int row = pass * 16 + ty;
+        const int g = base + row;
+        const bool valid = g < a.n_rows;
+        const int r = min(g, a.n_rows - 1);
+        const float4 pc4 = ldg4(a.save_p + (size_t)r * 128 + c0);
+        const float4 pg4 = ldg4(a.save_p + (size_t)r * 128 + 64 + c0);
+        float4 gm, wv;
+        if (MODE == ATOM) {
+          gm = ldg4(a.g_in + (size_t)s_pidx[row] * 64 + c0);
+          wv = ldg4(a.wgt + (size_t)s_pidx[2 * TR + row] * 64 + c0);
+        } else {
+          gm = ldg4(a.g_in + (size_t)s_pidx[row] * 64 + c0);
+          wv = ldg4(a.wgt + (size_t)s_pidx[row] * 64 + c0);
+        }
+        float y1[4] = {pc4.x, pc4.y, pc4.z, pc4.w};
+        float y2[4] = {pg4.x, pg4.y, pg4.z, pg4.w};
+        float xh1[4], xh2[4], rstd1 = 1.f, rstd2 = 1.f;
+        if (use_ln) {
+          ln_stats(y1, xh1, rstd1);
+          ln_stats(y2, xh2, rstd2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y1[j] = fmaf(xh1[j], f4at(g1, j), f4at(b1, j));
+            y2[j] = fmaf(xh2[j], f4at(g2, j), f4at(b2v, j));
+          }
+        }
+        float s1[4], core[4], gate[4];
+        float4 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s1[j] = sigmoid_f(y1[j]);
+          core[j] = y1[j] * s1[j];
+          gate[j] = sigmoid_f(y2[j]);
+          f4at(o, j) = core[j] * gate[j];
+        }
+        float4 go;
+        if (MODE == ATOM) {
+          if (valid) stg4(a.g_w0 + (size_t)g * 64 + c0, gm * o);
+          go = gm * wv;
+        } else {
+          const float4 wj = ldg4(a.wgt + (size_t)s_pidx[TR + row] * 64 + c0);
+          const float4 gmo = gm * o;
+          if (valid) {
+            stg4(a.g_w0 + (size_t)g * 64 + c0, gmo * wj);
+            stg4(a.g_w1 + (size_t)g * 64 + c0, gmo * wv);
+          }
+          go = gm * wv * wj;
+        }
+        float gy1[4], gy2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gj = f4at(go, j);
+          gy1[j] = gj * gate[j] * (s1[j] * fmaf(y1[j], 1.f - s1[j], 1.f));
+          gy2[j] = gj * core[j] * gate[j] * (1.f - gate[j]);
+        }
+        if (use_ln) {
+          // g_p = rstd * (gx - mean(gx) - xhat * mean(gx * xhat)), gx = gy * gamma
+          float gx[4], sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gx[j] = gy1[j] * f4at(g1, j);
+            sa += gx[j];
+            sb = fmaf(gx[j], xh1[j], sb);
+          }
+          sa = sum16(sa) * (1.f / 64.f);
+          sb = sum16(sb) * (1.f / 64.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gy1[j] = rstd1 * (gx[j] - sa - xh1[j] * sb);
+          sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gx[j] = gy2[j] * f4at(g2, j);
+            sa += gx[j];
+            sb = fmaf(gx[j], xh2[j], sb);
+          }
+          sa = sum16(sa) * (1.f / 64.f);
+          sb = sum16(sb) * (1.f / 64.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gy2[j] = rstd2 * (gx[j] - sa - xh2[j] * sb);
+        }
+        *reinterpret_cast<float4*>(s_t1 + swz(row, tx)) = make_float4(gy1[0], gy1[1], gy1[2], gy1[3]);
+        *reinterpret_cast<float4*>(s_t1 + HALF_BYTES + swz(row, tx)) = make_float4(gy2[0], gy2[1], gy2[2], gy2[3]);
+      }
+      tc::wg_barrier(1, 256);  // the g_p tile is complete
+      tc::mbar_wait(&bars.a_empty, (tl & 1) ^ 1);  // the MMAs of the previous tile have read the A operand
+      tc::fence_after_sync();
+      const uint8_t* src = s_t1 + chalf * HALF_BYTES;
+      const uint32_t a_hi = tmem_base + chalf * 128 + lane_sel, a_lo = a_hi + 64;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(src + swz(crow, g * 4 + q));
+          tc::split_tf32(v.x, hi[q * 4 + 0], lo[q * 4 + 0]);
+          tc::split_tf32(v.y, hi[q * 4 + 1], lo[q * 4 + 1]);
+          tc::split_tf32(v.z, hi[q * 4 + 2], lo[q * 4 + 2]);
+          tc::split_tf32(v.w, hi[q * 4 + 3], lo[q * 4 + 3]);
+        }
+        tc::tmem_st16(a_hi + g * 16, hi);
+        tc::tmem_st16(a_lo + g * 16, lo);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      mbar_arrive(&bars.a_full);
+    }
+  } else if (warp == 16) {
+    // ============================ M: g_h = g_p . W2 ============================
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_tf32(128, 64);
+      const uint32_t img = tc::smem_u32(s_img);
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int ds = tl & 1;
+        tc::mbar_wait(&bars.a_full, tl & 1);
+        tc::mbar_wait(&bars.d_empty[ds], ((tl >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t d_acc = tmem_base + 256 + ds * 128 + half * 64;
+          const uint32_t a_hi = tmem_base + half * 128, a_lo = a_hi + 64;
+          const uint32_t bhi = img + half * 2 * IMG_BYTES, blo = bhi + IMG_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t bh = tc::smem_desc_kmajor(bhi + j * 256, 128, 2048);
+            const uint64_t bl = tc::smem_desc_kmajor(blo + j * 256, 128, 2048);
+            tc::mma_tf32_ts(d_acc, a_hi + j * 8, bh, idesc, j > 0 ? 1u : 0u);
+            tc::mma_tf32_ts(d_acc, a_lo + j * 8, bh, idesc, 1u);
+            tc::mma_tf32_ts(d_acc, a_hi + j * 8, bl, idesc, 1u);
+          }
+        }
+        tc::mma_commit(&bars.a_empty);
+        tc::mma_commit(&bars.d_full[ds]);
+      }
+    }
+  } else if (warp < 16) {
+    // ============================ F: g_h -> g_pre = g_h * silu'(pre) ============================
+    const int t = tid - 256;             // 0..255
+    const int tx = t & 15, ty = t >> 4;
+    const int c0 = tx * 4;
+    const int crow = t & 127, chalf = t >> 7;
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      const int base = tile * TR;
+      const int ds = tl & 1;
+      if (MODE == ATOM && t < TR) {
+        const int r = min(base + t, a.n_rows - 1);
+        s_fidx[t] = a.idx0[r];
+        s_fidx[TR + t] = a.idx1[r];
+        s_fidx[2 * TR + t] = a.idx2[r];
+      }
+      tc::mbar_wait(&bars.d_full[ds], (tl >> 1) & 1);
+      tc::fence_after_sync();
+      {
+        const uint32_t d_acc = tmem_base + 256 + ds * 128 + chalf * 64 + lane_sel;
+        uint8_t* dst = s_t2 + chalf * HALF_BYTES;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t v[32];
+          tc::tmem_ld32(d_acc + g * 32, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(dst + swz(crow, g * 8 + q)) =
+                make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                            __uint_as_float(v[q * 4 + 3]));
+        }
+      }
+      tc::fence_before_sync();
+      mbar_arrive(&bars.d_empty[ds]);
+      tc::wg_barrier(2, 256);  // the g_h tile (and the index rows) are complete
+#pragma unroll 2
+      for (int pass = 0; pass < 8; ++pass) {
+        const int row = pass * 16 + ty;
+        const int g = base + row;
+        float4 vc, vg;
+        if (MODE == ATOM) {
+          const float* s0 = a.p_a + (size_t)s_fidx[row] * 256 + c0;
+          const float* s1 = a.p_a + (size_t)s_fidx[TR + row] * 256 + 128 + c0;
+          const float* s2 = a.p_b + (size_t)s_fidx[2 * TR + row] * 128 + c0;
+          vc = ldg4(s0) + ldg4(s1) + ldg4(s2);
+          vg = ldg4(s0 + 64) + ldg4(s1 + 64) + ldg4(s2 + 64);
+        } else {
+          const int r = min(g, a.n_rows - 1);
+          vc = ldg4(a.save_pre + (size_t)r * 128 + c0);
+          vg = ldg4(a.save_pre + (size_t)r * 128 + 64 + c0);
+        }
+        const float4 hc = *reinterpret_cast<const float4*>(s_t2 + swz(row, tx));
+        const float4 hg = *reinterpret_cast<const float4*>(s_t2 + HALF_BYTES + swz(row, tx));
+        if (g < a.n_rows) {
+          stg4(a.g_pre + (size_t)g * 128 + c0,
+               make_float4(hc.x * dsilu_f(vc.x), hc.y * dsilu_f(vc.y), hc.z * dsilu_f(vc.z), hc.w * dsilu_f(vc.w)));
+          stg4(a.g_pre + (size_t)g * 128 + 64 + c0,
+               make_float4(hg.x * dsilu_f(vg.x), hg.y * dsilu_f(vg.y), hg.z * dsilu_f(vg.z), hg.w * dsilu_f(vg.w)));
+        }
+      }
+      tc::wg_barrier(2, 256);  // the g_h tile can be overwritten
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tc::tmem_dealloc(tmem_base, 512);
+}
+
+template <int MODE>
+int launch_ws_bwd(const BwdArgs& a, cudaStream_t stream) {
+  if (a.n_rows == 0) return CHG_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CHG_CUDA(cudaFuncSetAttribute(gated_ws_bwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsBwdSmem::TOTAL));
+    attr_set = true;
+  }
+  const int n_tiles = (a.n_rows + TR - 1) / TR;
+  gated_ws_bwd_kernel<MODE><<<min(n_tiles, sm_count()), WS_THREADS, WsBwdSmem::TOTAL, stream>>>(a);
+  CHG_LAUNCH_END();
+}
+
+}  // namespace
+
+int atom_conv_bwd_ws(const BwdArgs& a, cudaStream_t stream) { return launch_ws_bwd<ATOM>(a, stream); }
+int bond_conv_bwd_ws(const BwdArgs& a, cudaStream_t stream) { return launch_ws_bwd<BOND>(a, stream); }
+
+}  // namespace gated
+}  // namespace chg

@@ -302,6 +302,22 @@ int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int3
                      int32_t* bond_graph);
 void chg_graph_free(chg_graph* g);
 
+/* ---- device graph builder (one structure): fractional coordinates -> the edge / angle arrays of chg_batch, on the device
+ * (csrc/graph_device.cu).  Replaces the host-side neighbour list + create_graph.c / cygraph.pyx + line graph
+ * (converter.py:102-190, graph.py:132-328, fast_converter_libraries/create_graph.c:100-219) that the reference
+ * runs on the CPU every MD step (dynamics.py:156-157).  Integer outputs are bit-identical to chg_graph_build.
+ * frac [N][3] fp64 on the DEVICE; lattice [9] fp64 on the host (rows = lattice vectors).  Outputs (device,
+ * caller-allocated): center / nbr / d2u [cap_edges], image [cap_edges][3] fp32, u2d [cap_edges / 2], ptr_c [N + 1],
+ * ang_atom / ang_i / ang_di / ang_j / ang_dj [cap_angles] (undirected / directed indices as in bond_graph).
+ * sizes_out (host) = {n_edges, n_bonds, n_angles, 0}; synchronises the stream twice (one int32 each).
+ * CHG_ERR_ARG + "capacity" in chg_last_error() when a capacity is too small (sizes_out holds what is needed).      */
+int64_t chg_graph_device_scratch_bytes(int32_t n_atoms, int32_t cap_edges);
+int chg_graph_build_device(const double* frac, const double* lattice, int32_t n_atoms, double r_atom, double r_bond,
+                           int32_t cap_edges, int32_t cap_angles, int32_t* center, int32_t* nbr, float* image,
+                           int32_t* d2u, int32_t* u2d, int32_t* ptr_c, int32_t* ang_atom, int32_t* ang_i,
+                           int32_t* ang_di, int32_t* ang_j, int32_t* ang_dj, void* scratch, int32_t* sizes_out,
+                           void* stream);
+
 /* ---- device CSR build: the segment structures of chg_batch from the packed index arrays
  * (replaces the torch sorts / searchsorted / nonzero of BatchedGraph-side preprocessing; csrc/batch_csr.cu).
  * Inputs: directed edges sorted by centre, angles sorted by bond i (chg_pack_batch_host reports both).
@@ -321,6 +337,10 @@ typedef struct chg_csr_out {
 } chg_csr_out;
 int64_t chg_build_csr_scratch_ints(int32_t n_atoms, int32_t n_edges, int32_t n_bonds, int32_t n_angles);
 int chg_build_csr(const chg_csr_in* in, const chg_csr_out* out, int32_t* scratch, void* stream);
+/* n_short for index arrays that live on the device (device graph builder): one int32 to the host, synchronises.
+ * scratch: 2 * (n_bonds + 1) + 4096 int32.                                                                  */
+int chg_bond_graph_count(const int32_t* ang_i, const int32_t* ang_j, int32_t n_angles, int32_t n_bonds,
+                         int32_t* scratch, int32_t* count_out, void* stream);
 
 /* host batch packer: B CrystalGraphs (HOST arrays, int32 / fp32, contiguous) -> the concatenated,
  * offset-adjusted SoA of chg_batch in one pass (BatchedGraph.from_graphs, model.py:820-899, without
