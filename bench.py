@@ -627,6 +627,42 @@ def infer_leg(model, graphs, dev, local_rank: int, world: int, steps: int, warmu
             "clocks": clocks, "wall_ms": wall_ms, "h2d": h2d, "d2h": d2h, "preds": preds, "batch": batch}
 
 
+def md_leg(model, dev, steps: int = 20) -> dict:
+    """NVE molecular dynamics of the 10,000-atom cell (BASELINE configs[3] is "one MD step"): device-resident driver
+    (positions / velocities / forces on the GPU, device graph builder with a Verlet skin, one CUDA graph per step) next to
+    the host-driven loop the reference's CHGNetCalculator implies (host graph build -> H2D -> model -> D2H every step)."""
+    from chgnet_b200 import graphgen
+    from chgnet_b200.dynamics import Atoms, CHGNetCalculator, VelocityVerlet
+    from chgnet_b200.dynamics_device import DeviceMD
+
+    z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000)
+    pos = frac @ lat
+    md = DeviceMD(model, z, pos, lat, timestep=2.0, skin=0.5)
+    md.set_temperature(300.0, seed=1)
+    md.run(5, log_every=0)
+    torch.cuda.synchronize()
+    b0 = md.n_builds
+    t0 = time.perf_counter()
+    md.run(steps, log_every=0)
+    torch.cuda.synchronize()
+    dt_dev = (time.perf_counter() - t0) / steps
+    e_tot = md.potential_energy + md.kinetic_energy
+    host = VelocityVerlet(Atoms(z, pos, lat), CHGNetCalculator(model=model, on_isolated_atoms="ignore"), timestep=2.0)
+    host.set_temperature(300.0, seed=1)
+    host.run(2)
+    t0 = time.perf_counter()
+    host.run(5)
+    dt_host = (time.perf_counter() - t0) / 5
+    return {"atoms": int(len(z)), "timestep_fs": 2.0, "temperature_K": 300.0,
+            "device_driver": {"ms_per_step": round(dt_dev * 1e3, 3), "steps_per_s": round(1.0 / dt_dev, 2), "steps": steps,
+                              "graph_rebuilds": md.n_builds - b0, "skin_A": 0.5,
+                              "what": "DeviceMD: kick+drift -> chg_forward -> kick as one CUDA graph per step, "
+                                      "chg_graph_build_device when an atom moved > skin/2", "e_total_eV": e_tot},
+            "host_driver": {"ms_per_step": round(dt_host * 1e3, 3), "steps_per_s": round(1.0 / dt_host, 2), "steps": 5,
+                            "what": "CHGNetCalculator loop (the reference's structure, dynamics.py:129-181): host graph build "
+                                    "(native C++), H2D, chg_forward, D2H, numpy integrator"}}
+
+
 def scatter_roofline(K, batch, workload: str, dev) -> dict:
     """Roofline record of the AtomConv scatter-reduce kernel at this batch's size."""
     peaks, peak_kind = measured_peaks()
@@ -729,6 +765,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                       "api": "CHGNet.predict_graph(CrystalGraph on host, task='efs')"},
               "roofline": scatter_roofline(K, l4["batch"], "c4", dev), "clocks": l4["clocks"], "n_gpus": 1,
               "note": "one structure does not shard: rank 0 alone (replicas only, DESIGN.md §7)"}
+        if not args.no_md:
+            try:
+                c4["md"] = md_leg(model, dev)
+            except Exception as exc:  # reported, never fatal for the bench line
+                c4["md"] = {"unavailable": repr(exc)[:300]}
 
     # ---------------- CPU baseline + parity: oracle port on the host cores ----------------
     cpu = None
@@ -820,6 +861,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the 10,000-atom extra leg of a c2 / c3 run")
     ap.add_argument("--no-collective", action="store_true", help="N > 1: skip the c5 all-reduce leg")
+    ap.add_argument("--no-md", action="store_true", help="skip the MD sub-leg of the c4 extra leg")
     ap.add_argument("--scatter-only", action="store_true", help="run only the AtomConv scatter kernel timing (ncu target)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -12,7 +12,6 @@ no H2D copy of index arrays.  The integer arrays are bit-identical to the host b
 from __future__ import annotations
 
 import ctypes
-import math
 
 import numpy as np
 import torch
@@ -176,8 +175,10 @@ def crystal_graph_from_device(builder: DeviceGraphBuilder, atomic_numbers, frac,
     g = builder.graph_arrays(f64, lattice)
     torch.cuda.synchronize(builder.device)
     host = {k: v.cpu() for k, v in g.items()}
-    bond_graph = torch.stack([host["ang_atom"], host["ang_i"], host["ang_di"], host["ang_j"], host["ang_dj"]], dim=1) \\
-        if host["ang_atom"].numel() else torch.zeros(0, 5, dtype=torch.int32)
+    if host["ang_atom"].numel():
+        bond_graph = torch.stack([host["ang_atom"], host["ang_i"], host["ang_di"], host["ang_j"], host["ang_dj"]], dim=1)
+    else:
+        bond_graph = torch.zeros(0, 5, dtype=torch.int32)
     return CrystalGraph(
         atomic_number=torch.as_tensor(np.asarray(atomic_numbers), dtype=torch.int32),
         atom_frac_coord=torch.as_tensor(np.asarray(frac), dtype=TORCH_DTYPE),
@@ -188,4 +189,3 @@ def crystal_graph_from_device(builder: DeviceGraphBuilder, atomic_numbers, frac,
 
 
 __all__ = ["DeviceGraphBuilder", "crystal_graph_from_device"]
-_ = math

@@ -318,6 +318,20 @@ int chg_graph_build_device(const double* frac, const double* lattice, int32_t n_
                            int32_t* ang_di, int32_t* ang_j, int32_t* ang_dj, void* scratch, int32_t* sizes_out,
                            void* stream);
 
+/* ---- device-resident MD / relaxation updates (csrc/md.cu; the reference integrates on the host through ASE,
+ * dynamics.py:129-181, 190-204).  x, v, f [N][3] fp64 on the device; inv_mass [N]; inv_lattice [9] on the HOST
+ * (frac = x @ inv_lattice).  frac64 feeds chg_graph_build_device, frac32 is chg_batch.frac.
+ *   chg_md_kick_drift: v += dt/2 f/m; x += dt v; frac; max_disp2 (device double, may be NULL) = max |x - x_ref|^2
+ *   chg_md_kick      : v += dt/2 f/m; *e_kin (device double, may be NULL) += kinetic energy
+ *   chg_fire_step    : one FIRE update with its state in device memory (12 doubles: dt, alpha, n_pos, sums, ...)   */
+int chg_md_kick_drift(double* x, double* v, const double* f, const double* inv_mass, int32_t n_atoms, double dt,
+                      const double* inv_lattice, double* frac64, float* frac32, const double* x_ref,
+                      double* max_disp2, void* stream);
+int chg_md_kick(double* v, const double* f, const double* inv_mass, int32_t n_atoms, double dt, double* e_kin,
+                void* stream);
+int chg_fire_step(double* x, double* v, const double* f, int32_t n_atoms, double* state, const double* inv_lattice,
+                  double* frac64, float* frac32, double dt_max, double max_step, void* stream);
+
 /* ---- device CSR build: the segment structures of chg_batch from the packed index arrays
  * (replaces the torch sorts / searchsorted / nonzero of BatchedGraph-side preprocessing; csrc/batch_csr.cu).
  * Inputs: directed edges sorted by centre, angles sorted by bond i (chg_pack_batch_host reports both).

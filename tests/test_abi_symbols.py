@@ -39,7 +39,8 @@ def test_binding_table_matches_header(lib):
                                    "chg_forward_plan", "chg_forward",
                                    "chg_graph_build", "chg_graph_sizes", "chg_graph_export", "chg_graph_free",
                                    "chg_pack_batch_host", "chg_build_csr", "chg_build_csr_scratch_ints", "chg_bond_graph_count",
-                                   "chg_graph_build_device", "chg_graph_device_scratch_bytes"}
+                                   "chg_graph_build_device", "chg_graph_device_scratch_bytes", "chg_md_kick_drift", "chg_md_kick",
+                                   "chg_fire_step"}
     assert declared == set(_lib.SIGNATURES)
     # argument counts of the ctypes table follow the header prototypes
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "chgnet_b200.h")).read(), flags=re.S)
