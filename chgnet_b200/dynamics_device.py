@@ -59,6 +59,8 @@ class _DeviceSystem:
         self.dev = model.device
         if self.dev.type != "cuda":
             raise ChgnetB200Error("device MD needs the model on a CUDA device")
+        if self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.numbers = np.asarray(numbers, dtype=np.int64).reshape(-1)
         self.n = len(self.numbers)
         self.cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
@@ -74,6 +76,8 @@ class _DeviceSystem:
         self.max_disp2 = torch.zeros(1, **f64)
         self.e_kin = torch.zeros(1, **f64)
         self.skin = float(skin)
+        if self.skin <= 0.0:
+            raise ValueError("skin must be positive: the neighbour lists are reused until an atom has moved skin / 2")
         gc = model.graph_converter
         self.builder = DeviceGraphBuilder(self.dev, float(gc.atom_graph_cutoff) + self.skin, float(gc.bond_graph_cutoff) + self.skin)
         self.compact = not model._arch.get("mlp_out_bias", False)
@@ -161,10 +165,13 @@ class DeviceMD(_DeviceSystem):
                 s = torch.cuda.Stream(self.dev)
                 s.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(s):
-                    self._step_body()  # warm-up on the side stream (workspace growth, lazy attributes)
-                    s.synchronize()
-                    x0, v0, f0, d0 = self._capture_state
-                    self.x.copy_(x0), self.v.copy_(v0), self.f.copy_(f0), self.max_disp2.copy_(d0)
+                    if not getattr(self, "_warmed", False):
+                        # once: a real step on the side stream (workspace growth, lazily set kernel attributes), undone
+                        self._step_body()
+                        s.synchronize()
+                        x0, v0, f0, d0 = self._capture_state
+                        self.x.copy_(x0), self.v.copy_(v0), self.f.copy_(f0), self.max_disp2.copy_(d0)
+                        self._warmed = True
                     with torch.cuda.graph(g, stream=s):
                         self._step_body()
                 torch.cuda.current_stream(self.dev).wait_stream(s)

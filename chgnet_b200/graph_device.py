@@ -45,6 +45,8 @@ class DeviceGraphBuilder:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ChgnetB200Error("DeviceGraphBuilder needs a CUDA device (the host builders are chg_graph_build / graphgen)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.r_atom, self.r_bond = float(atom_graph_cutoff), float(bond_graph_cutoff)
         self.cap_edges = self.cap_angles = 0
         self.buf: dict[str, Tensor] = {}
@@ -171,7 +173,7 @@ def crystal_graph_from_device(builder: DeviceGraphBuilder, atomic_numbers, frac,
     want the reference's input type)."""
     from chgnet_b200.graph import TORCH_DTYPE, CrystalGraph
 
-    f64 = torch.as_tensor(np.asarray(frac, dtype=np.float64)).to(builder.device).contiguous()
+    f64 = torch.as_tensor(np.ascontiguousarray(np.asarray(frac, dtype=np.float64).reshape(-1, 3))).to(builder.device).contiguous()
     g = builder.graph_arrays(f64, lattice)
     torch.cuda.synchronize(builder.device)
     host = {k: v.cpu() for k, v in g.items()}

@@ -389,7 +389,7 @@ class CHGNet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _run(self, graphs, task, return_site_energies, return_atom_feas, return_crystal_feas,
-             train: bool = False) -> dict[str, Any]:
+             train: bool = False, batch: DeviceBatch | None = None) -> dict[str, Any]:
         """One batch through the kernels; returns BATCHED device tensors.
 
         Inference = one native ``chg_forward`` call (native.py; ``CHGNET_B200_ENGINE=python`` selects the
@@ -397,7 +397,8 @@ class CHGNet(nn.Module):
         need_grad = "f" in task or "s" in task
         # mlp_out bias (0.2.0) touches every bond: no bond-graph compaction in that case
         compact = not self._arch.get("mlp_out_bias", False)
-        batch = build_batch(graphs, self.device, with_reverse=need_grad or train, compact_bonds=compact)
+        if batch is None:
+            batch = build_batch(graphs, self.device, with_reverse=need_grad or train, compact_bonds=compact)
         self.last_batch = batch
         if not train and os.environ.get("CHGNET_B200_ENGINE", "native") != "python":
             nat = self._get_native()
@@ -483,11 +484,59 @@ class CHGNet(nn.Module):
         if self.graph_converter is None:
             raise ValueError("graph_converter cannot be None!")
         single = hasattr(structure, "frac_coords") or isinstance(structure, tuple)
+        if (single and isinstance(self.graph_converter, GraphConverter) and self.device.type == "cuda"
+                and os.environ.get("CHGNET_B200_GRAPH", "device") == "device"):
+            return self._predict_structure_device(structure, task, return_site_energies, return_atom_feas, return_crystal_feas)
         structures = [structure] if single else structure
         graphs = [self.graph_converter(s) for s in structures]
         return self.predict_graph(graphs[0] if single else graphs, task=task,
                                   return_site_energies=return_site_energies, return_atom_feas=return_atom_feas,
                                   return_crystal_feas=return_crystal_feas, batch_size=batch_size)
+
+    def _predict_structure_device(self, structure, task, return_site_energies, return_atom_feas, return_crystal_feas):
+        """One structure, graph built ON THE DEVICE (chgnet_b200.graph_device: the same edges / angles as the host
+        converter, bit for bit): only the atomic numbers, fractional coordinates and the lattice cross PCIe."""
+        from chgnet_b200.graph_device import DeviceGraphBuilder
+
+        valid_tasks = get_args(PredTask)
+        if task not in valid_tasks:
+            raise ValueError(f"Invalid {task=}. Must be one of {valid_tasks}.")
+        if isinstance(structure, tuple):
+            z, frac, lat = structure
+        else:
+            z = getattr(structure, "atomic_numbers", None)
+            if z is None:
+                z = [site.specie.Z for site in structure]
+            frac = structure.frac_coords
+            lat = structure.lattice.matrix if hasattr(structure.lattice, "matrix") else structure.lattice
+        gc = self.graph_converter
+        key = (str(self.device), float(gc.atom_graph_cutoff), float(gc.bond_graph_cutoff))
+        if getattr(self, "_dev_builder_key", None) != key:
+            self._dev_builder = DeviceGraphBuilder(self.device, gc.atom_graph_cutoff, gc.bond_graph_cutoff)
+            self._dev_builder_key = key
+        self.eval()
+        need_grad = "f" in task or "s" in task
+        f64 = torch.as_tensor(np.ascontiguousarray(np.asarray(frac, dtype=np.float64).reshape(-1, 3))).to(self.device)
+        batch = self._dev_builder.build_batch(np.asarray(z), f64, np.asarray(lat, dtype=np.float64), with_reverse=need_grad,
+                                              compact_bonds=not self._arch.get("mlp_out_bias", False))
+        if gc.on_isolated_atoms != "ignore" and batch.n_atoms:
+            n_isolated_atoms = int((batch.ptr_c[1:] == batch.ptr_c[:-1]).sum().item())
+            if n_isolated_atoms:
+                atom_graph_cutoff, graph_id = gc.atom_graph_cutoff, None
+                msg = (f"Structure {graph_id=} has {n_isolated_atoms} isolated atom(s) with "
+                       f"{atom_graph_cutoff=}. CHGNet calculation will likely go wrong")
+                if gc.on_isolated_atoms == "error":
+                    raise ValueError(msg)
+                import sys
+
+                print(msg, file=sys.stderr)
+        raw = self._run(None, task, return_site_energies, return_atom_feas, return_crystal_feas, batch=batch)
+        out: dict[str, np.ndarray] = {}
+        for key_ in ("e", "f", "s", "m", "site_energies", "atom_fea", "crystal_fea"):
+            if key_ in raw:
+                host = raw[key_].cpu().numpy()
+                out[key_] = np.asarray(host if key_ in self._PER_ATOM else host[0])
+        return out
 
     def predict_graph(self, graph, *, task: PredTask = "efsm", return_site_energies: bool = False,
                       return_atom_feas: bool = False, return_crystal_feas: bool = False, batch_size: int = 16):
