@@ -161,6 +161,7 @@ class DeviceMD(_DeviceSystem):
             if self.graph is None:
                 # capture [kick + drift] -> chg_forward -> [kick] for this topology (a side stream, as CUDA requires)
                 self._capture_state = (self.x.clone(), self.v.clone(), self.f.clone(), self.max_disp2.clone())
+                self.model._get_native().reserve(self.batch, need_grad=True)  # never reallocate inside a capture
                 g = torch.cuda.CUDAGraph()
                 s = torch.cuda.Stream(self.dev)
                 s.wait_stream(torch.cuda.current_stream(self.dev))

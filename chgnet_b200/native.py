@@ -173,6 +173,13 @@ class NativeForward:
             self.atom_ref = state_dict["composition_model.fc.weight"].detach().reshape(-1).to(device=device, dtype=torch.float32)
         self.calls = 0
 
+    def reserve(self, b: DeviceBatch, *, need_grad: bool = True) -> None:
+        """Grow the workspace for this batch NOW (e.g. before a CUDA-graph capture, where it must not be reallocated)."""
+        outs = Outputs(energy=1, e_ref=1, site_e=1, force=1 if need_grad else None, virial=1 if need_grad else None)
+        need, _ = plan(self.hps, batch_struct(b, None), outs)
+        if self.workspace.numel() < need + 256:
+            self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+
     def __call__(self, b: DeviceBatch, *, need_grad: bool, need_magmom: bool = False, need_atom_fea: bool = False,
                  need_crystal_fea: bool = False) -> dict[str, Tensor]:
         dev, N, B = self.device, b.n_atoms, b.n_graphs
