@@ -641,6 +641,7 @@ def md_leg(model, dev, steps: int = 20) -> dict:
     md.set_temperature(300.0, seed=1)
     md.run(5, log_every=0)
     torch.cuda.synchronize()
+    md.t_rebuild = md.t_capture = 0.0
     b0 = md.n_builds
     t0 = time.perf_counter()
     md.run(steps, log_every=0)
@@ -655,7 +656,8 @@ def md_leg(model, dev, steps: int = 20) -> dict:
     dt_host = (time.perf_counter() - t0) / 5
     return {"atoms": int(len(z)), "timestep_fs": 2.0, "temperature_K": 300.0,
             "device_driver": {"ms_per_step": round(dt_dev * 1e3, 3), "steps_per_s": round(1.0 / dt_dev, 2), "steps": steps,
-                              "graph_rebuilds": md.n_builds - b0, "skin_A": 0.5,
+                              "graph_rebuilds": md.n_builds - b0, "skin_A": 0.5, "model_edges_with_skin": int(md.batch.n_edges),
+                              "host_s_in_rebuilds": round(md.t_rebuild, 4), "host_s_in_captures": round(md.t_capture, 4),
                               "what": "DeviceMD: kick+drift -> chg_forward -> kick as one CUDA graph per step, "
                                       "chg_graph_build_device when an atom moved > skin/2", "e_total_eV": e_tot},
             "host_driver": {"ms_per_step": round(dt_host * 1e3, 3), "steps_per_s": round(1.0 / dt_host, 2), "steps": 5,

@@ -339,15 +339,19 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
     bool edges_sorted = true, angles_sorted = true;
     int64_t bad_z = -1, n_short = 0;
   };
-  auto pack_range = [&](int g0, int g1, Partial& res) {
+  // [part, parts): this worker's share of every array of the graphs g0..g1-1 (parts == 1: whole graphs)
+  auto pack_range = [&](int g0, int g1, int part, int parts, Partial& res) {
     for (int g = g0; g < g1; ++g) {
       const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
       const int64_t a_off = off[(size_t)g * 4], e_off = off[(size_t)g * 4 + 1], u_off = off[(size_t)g * 4 + 2], g_off = off[(size_t)g * 4 + 3];
       const void* const* p = ptrs + 8 * g;
+      auto lo = [&](int64_t len) { return len * part / parts; };
+      auto hi = [&](int64_t len) { return len * (part + 1) / parts; };
       if (n > 0) {
-        std::memcpy(z + a_off, p[0], (size_t)n * 4);
-        std::memcpy(frac + a_off * 3, p[1], (size_t)n * 12);
-        for (int64_t i = 0; i < n; ++i) {
+        const int64_t i0 = lo(n), i1 = hi(n);
+        std::memcpy(z + a_off + i0, static_cast<const int32_t*>(p[0]) + i0, (size_t)(i1 - i0) * 4);
+        std::memcpy(frac + (a_off + i0) * 3, static_cast<const float*>(p[1]) + i0 * 3, (size_t)(i1 - i0) * 12);
+        for (int64_t i = i0; i < i1; ++i) {
           owner[a_off + i] = g;
           const int32_t zi = z[a_off + i];
           if ((zi < 1 || zi > CHG_MAX_Z) && res.bad_z < 0) res.bad_z = a_off + i;
@@ -355,17 +359,18 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
       }
       const int32_t* ag = static_cast<const int32_t*>(p[2]);
       const int32_t* du = static_cast<const int32_t*>(p[4]);
-      for (int64_t e = 0; e < ed; ++e) {
+      const int64_t e0 = lo(ed), e1 = hi(ed);
+      for (int64_t e = e0; e < e1; ++e) {
         center[e_off + e] = ag[2 * e] + (int32_t)a_off;
         nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
         d2u[e_off + e] = du[e] + (int32_t)u_off;
         if (e > 0 && ag[2 * e] < ag[2 * e - 2]) res.edges_sorted = false;
       }
-      if (ed > 0) std::memcpy(image + e_off * 3, p[3], (size_t)ed * 12);
+      if (e1 > e0) std::memcpy(image + (e_off + e0) * 3, static_cast<const float*>(p[3]) + e0 * 3, (size_t)(e1 - e0) * 12);
       const int32_t* ud = static_cast<const int32_t*>(p[5]);
-      for (int64_t u = 0; u < eu; ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
+      for (int64_t u = lo(eu); u < hi(eu); ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
       const int32_t* bg = static_cast<const int32_t*>(p[6]);
-      for (int64_t a = 0; a < an; ++a) {
+      for (int64_t a = lo(an); a < hi(an); ++a) {
         ang_atom[g_off + a] = bg[5 * a] + (int32_t)a_off;
         ang_i[g_off + a] = bg[5 * a + 1] + (int32_t)u_off;
         ang_di[g_off + a] = bg[5 * a + 2] + (int32_t)e_off;
@@ -374,29 +379,28 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
         if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) res.angles_sorted = false;
         for (int which = 1; which <= 3; which += 2) {  // bond i, bond j: this graph's own range of the flag array
           const int64_t ul = bg[5 * a + which];
-          if (ul >= 0 && ul < eu && !bg_flag[u_off + ul]) {
-            bg_flag[u_off + ul] = 1;
-            ++res.n_short;
-          }
+          // test-and-set: workers that share a graph may meet the same bond
+          if (ul >= 0 && ul < eu && __atomic_exchange_n(&bg_flag[u_off + ul], (uint8_t)1, __ATOMIC_RELAXED) == 0) ++res.n_short;
         }
       }
-      std::memcpy(lattice + (size_t)g * 9, p[7], 36);
+      if (part == 0) std::memcpy(lattice + (size_t)g * 9, p[7], 36);
     }
   };
 
-  // graphs are independent: contiguous ranges of graphs of about equal bytes per worker thread
+  // many graphs: contiguous ranges of whole graphs of about equal size per worker; few (large) graphs: every worker takes
+  // a slice of every array of every graph
   const int64_t total_items = N * 5 + Ed * 6 + Eu + A * 5;
   int n_thr = 1;
   if (total_items > (1 << 20)) {
     const unsigned hc = std::thread::hardware_concurrency();
     n_thr = (int)std::min<int64_t>(std::min<unsigned>(hc == 0 ? 4 : hc, 16), std::max<int64_t>(1, total_items >> 19));
-    n_thr = std::min(n_thr, n_graphs);
-    if (const char* e = std::getenv("CHG_PACK_THREADS")) n_thr = std::max(1, std::min(std::atoi(e), std::max(1, n_graphs)));
+    if (const char* e = std::getenv("CHG_PACK_THREADS")) n_thr = std::max(1, std::min(std::atoi(e), 64));
   }
+  const bool by_graph = n_graphs >= 4 * n_thr;
   std::vector<Partial> parts((size_t)n_thr);
   if (n_thr <= 1) {
-    pack_range(0, n_graphs, parts[0]);
-  } else {
+    pack_range(0, n_graphs, 0, 1, parts[0]);
+  } else if (by_graph) {
     auto weight = [&](int g) { return off[(size_t)g * 4] * 5 + off[(size_t)g * 4 + 1] * 6 + off[(size_t)g * 4 + 2] + off[(size_t)g * 4 + 3] * 5; };
     std::vector<int> cut((size_t)n_thr + 1, n_graphs);
     cut[0] = 0;
@@ -407,8 +411,14 @@ extern "C" int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts /* [B
     }
     std::vector<std::thread> pool;
     pool.reserve((size_t)n_thr - 1);
-    for (int t = 1; t < n_thr; ++t) pool.emplace_back(pack_range, cut[t], cut[t + 1], std::ref(parts[t]));
-    pack_range(cut[0], cut[1], parts[0]);
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(pack_range, cut[t], cut[t + 1], 0, 1, std::ref(parts[t]));
+    pack_range(cut[0], cut[1], 0, 1, parts[0]);
+    for (auto& th : pool) th.join();
+  } else {
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)n_thr - 1);
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(pack_range, 0, n_graphs, t, n_thr, std::ref(parts[t]));
+    pack_range(0, n_graphs, 0, n_thr, parts[0]);
     for (auto& th : pool) th.join();
   }
   bool edges_sorted = true, angles_sorted = true;

@@ -87,6 +87,8 @@ class _DeviceSystem:
         self.out: dict | None = None
         self.n_builds = 0
         self.n_steps = 0
+        self.n_captures = 0
+        self.t_rebuild = self.t_capture = 0.0  # host seconds spent rebuilding lists / capturing step graphs
         self._update_frac()
         self._rebuild()
         self._forward()
@@ -159,31 +161,51 @@ class DeviceMD(_DeviceSystem):
     def step(self) -> None:
         if self.use_cuda_graph:
             if self.graph is None:
-                # capture [kick + drift] -> chg_forward -> [kick] for this topology (a side stream, as CUDA requires)
-                self._capture_state = (self.x.clone(), self.v.clone(), self.f.clone(), self.max_disp2.clone())
-                self.model._get_native().reserve(self.batch, need_grad=True)  # never reallocate inside a capture
-                g = torch.cuda.CUDAGraph()
-                s = torch.cuda.Stream(self.dev)
-                s.wait_stream(torch.cuda.current_stream(self.dev))
-                with torch.cuda.stream(s):
-                    if not getattr(self, "_warmed", False):
-                        # once: a real step on the side stream (workspace growth, lazily set kernel attributes), undone
-                        self._step_body()
-                        s.synchronize()
-                        x0, v0, f0, d0 = self._capture_state
-                        self.x.copy_(x0), self.v.copy_(v0), self.f.copy_(f0), self.max_disp2.copy_(d0)
-                        self._warmed = True
-                    with torch.cuda.graph(g, stream=s):
-                        self._step_body()
-                torch.cuda.current_stream(self.dev).wait_stream(s)
-                # the capture itself executes nothing: state is still the pre-step state
-                self.graph = g
+                self._capture()
             self.graph.replay()
         else:
             self._step_body()
         self.n_steps += 1
         if self.needs_rebuild():
+            import time
+
+            t0 = time.perf_counter()
             self._rebuild()
+            self.t_rebuild += time.perf_counter() - t0
+
+    def _capture(self) -> None:
+        """Capture [kick + drift] -> chg_forward -> [kick] for the current topology.  Raw capture_begin / capture_end
+        on a side stream with one memory pool shared by all captures of this run (``torch.cuda.graph`` would run the
+        garbage collector and empty the allocator cache at every capture)."""
+        import time
+
+        t0 = time.perf_counter()
+        nat = self.model._get_native()
+        nat.reserve(self.batch, need_grad=True)  # never reallocate the workspace inside a capture
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.dev)
+            self._pool = torch.cuda.graph_pool_handle()
+        s = self._side
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            if not getattr(self, "_warmed", False):
+                # once: a real step on the side stream (lazily set kernel attributes, allocator warm-up), then undone
+                state = (self.x.clone(), self.v.clone(), self.f.clone(), self.max_disp2.clone())
+                self._step_body()
+                s.synchronize()
+                self.x.copy_(state[0]), self.v.copy_(state[1]), self.f.copy_(state[2]), self.max_disp2.copy_(state[3])
+                self._warmed = True
+            self.graph = None  # release the previous capture's buffers back to the shared pool first
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=self._pool)
+            try:
+                self._step_body()
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self.graph = g  # capturing executed nothing: the state is still the pre-step state
+        self.n_captures += 1
+        self.t_capture += time.perf_counter() - t0
 
     @property
     def kinetic_energy(self) -> float:
