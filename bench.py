@@ -291,10 +291,10 @@ def run_train(args, rank: int, world: int, local_rank: int, light: bool = False)
     peaks, peak_kind = measured_peaks()
     sc_ms, sc_bytes = time_scatter_kernel(K, batch)
     achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
-    roofline = {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "segment_sum_kernel<128> (AtomConv scatter-reduce of the reverse pass)", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth", "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "us_per_launch": round(sc_ms * 1e3, 2),
-                "algorithmic_bytes": sc_bytes, "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+                "algorithmic_bytes": sc_bytes, "bytes_formula": "512*E_d + 512*N + 4*(N+1)"}
     ek = EventKernels(K)
     from chgnet_b200.engine import Engine
 
@@ -501,11 +501,13 @@ class L2Flush:
         self.sink.copy_(self.r.sum())
 
 
-def time_scatter_kernel(K, batch, n_iter: int = 20):
-    """AtomConv scatter-reduce alone: CUDA events on the launching stream, L2 flushed."""
+def time_scatter_kernel(K, batch, n_iter: int = 20, width: int = 128):
+    """The AtomConv scatter-reduce alone: chg_segment_sum over centre-sorted rows, CUDA events on the launching stream, L2
+    flushed.  width = 128: the reverse-pass call (dE/dpre rows -> per-atom sums, the scatter that still runs as its own
+    kernel); width = 64: the forward message sum (now fused into gated_ws_fwd_kernel, kept for continuity with round 1)."""
     dev = batch.z.device
-    msg = torch.randn(batch.n_edges, 64, device=dev)
-    out = torch.empty(batch.n_atoms, 64, device=dev)
+    msg = torch.randn(batch.n_edges, width, device=dev)
+    out = torch.empty(batch.n_atoms, width, device=dev)
     flush = L2Flush(dev)
     for _ in range(3):
         K.segment_sum(msg, None, batch.ptr_c, 0, out)
@@ -519,7 +521,7 @@ def time_scatter_kernel(K, batch, n_iter: int = 20):
         e.synchronize()
         total += s.elapsed_time(e)
     ms = total / n_iter
-    alg_bytes = 256 * batch.n_edges + 256 * batch.n_atoms + 4 * (batch.n_atoms + 1)
+    alg_bytes = 4 * width * batch.n_edges + 4 * width * batch.n_atoms + 4 * (batch.n_atoms + 1)
     return ms, alg_bytes
 
 
@@ -668,18 +670,23 @@ def md_leg(model, dev, steps: int = 20) -> dict:
 def scatter_roofline(K, batch, workload: str, dev) -> dict:
     """Roofline record of the AtomConv scatter-reduce kernel at this batch's size."""
     peaks, peak_kind = measured_peaks()
-    sc_ms, sc_bytes = time_scatter_kernel(K, batch)
+    sc_ms, sc_bytes = time_scatter_kernel(K, batch, width=128)
     achieved = sc_bytes / (sc_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "scatter_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
         with open(tpath) as f:
-            traffic = json.load(f).get(workload, {}).get("dram_bytes_per_launch")
-    return {"kernel": "segment_sum_kernel<64> (AtomConv scatter-reduce)", "bound": "hbm",
+            traffic = json.load(f).get(workload + "_w128", {}).get("dram_bytes_per_launch")
+    ms64, b64 = time_scatter_kernel(K, batch, width=64)
+    return {"kernel": "segment_sum_kernel<128> (AtomConv scatter-reduce of the reverse pass: dE/dpre rows -> atoms)", "bound": "hbm",
             "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth",
             "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
             "us_per_launch": round(sc_ms * 1e3, 2), "algorithmic_bytes": sc_bytes,
-            "bytes_formula": "256*E_d + 256*N + 4*(N+1)"}
+            "bytes_formula": "512*E_d + 512*N + 4*(N+1)",
+            "forward_message_sum_w64": {"us_per_launch": round(ms64 * 1e3, 2), "algorithmic_bytes": b64,
+                                        "frac": round(b64 / (ms64 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                                        "note": "round-1 roofline kernel; in the default forward this sum is now fused into "
+                                                "gated_ws_fwd_kernel (the message never reaches HBM)"}}
 
 
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
@@ -743,15 +750,26 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             z = batch.z
             n_atoms, n_edges = 10000, 840000
             ptr_c = (torch.arange(10001, device=dev, dtype=torch.int32) * 84).contiguous()
-        ms10, b10 = time_scatter_kernel(K, _B)
+        ms10, b10 = time_scatter_kernel(K, _B, width=128)
         roofline["at_10k_atoms"] = {"us_per_launch": round(ms10 * 1e3, 2), "algorithmic_bytes": b10,
                                     "achieved": round(b10 / (ms10 * 1e-3) / 1e9, 1),
                                     "frac": round(b10 / (ms10 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                                    "input": "synthetic: 10,000 segments x 84 rows x 256 B"}
+                                    "input": "synthetic: 10,000 segments x 84 rows x 512 B"}
     # per-kernel shares (own events, outside the timed region)
     ek = EventKernels(K)
     Engine(engine.pw, ek).run(batch, need_grad=True)
     shares = ek.table()
+    fa = shares.get("atom_conv_fused")
+    if fa:
+        # the forward AtomConv scatter now lives inside the fused tile kernel: its compulsory traffic (SURVEY.md §8d "fully fused
+        # AtomConv": 268 E_d + 512 N) plus the 512 B / edge of p kept for the reverse pass, against the same HBM peak
+        us = fa["ms"] / fa["calls"] * 1e3
+        nb = (268 + 512) * c["directed_edges"] + 512 * c["atoms"]
+        roofline["fused_forward_atom_conv"] = {
+            "kernel": "gated_ws_fwd_kernel<ATOM> + seg_stitch_kernel (message + aggregation, tcgen05)", "us_per_launch": round(us, 2),
+            "compulsory_bytes": nb, "bytes_formula": "(268 + 512 saved p) * E_d + 512 * N",
+            "achieved": round(nb / (us * 1e-6) / 1e9, 1), "frac": round(nb / (us * 1e-6) / 1e9 / peaks["hbm_gbs"], 4),
+            "note": "latency-bound (gathers + MUFU), not bandwidth-bound: see profiles/ for tensor-pipe % and DRAM bytes"}
 
     # ---------------- the 10,000-atom cell (BASELINE configs[3]) as an extra key ----------------
     c4 = None

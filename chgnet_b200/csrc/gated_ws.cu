@@ -79,6 +79,8 @@ struct FusedArgs {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+// pull one 128-byte line towards L2 (no register, no dependency): issued one tile ahead of the gathers that read it
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // byte offset of 16-byte chunk c (0..15) of row r in a swizzled [128][64] fp32 tile
 __device__ __forceinline__ int swz(int r, int c) { return r * 256 + ((c ^ (r & 7)) << 4); }
 
@@ -214,6 +216,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
         gi[2 * TR + gt] = a.idx2[r];
       }
       tc::wg_barrier(1 + half, 128);  // indices visible; every thread of the group is done with the previous half-tile
+      {
+        // the rows of the NEXT tile that stream from HBM (p_b: per-bond products for AtomConv; p_c: per-angle products for
+        // BondConv): prefetch this group's half (2 lines of 128 B per row) towards L2 while this tile is gathered
+        const int nt = tile + gridDim.x;
+        if (nt < n_tiles) {
+          const int r = min(nt * TR + gt, a.n_rows - 1);
+          const float* row = MODE == BOND ? a.p_c + (size_t)r * 128 + half * 64 : a.p_b + (size_t)__ldg(a.idx2 + r) * 128 + half * 64;
+          prefetch_l2(row);
+          prefetch_l2(row + 32);
+        }
+      }
 #pragma unroll 1
       for (int b = 0; b < 4; ++b) {
         float4 v[4];
@@ -307,7 +320,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
           s_sa[t] = __ldg(a.ptr + seg);
           s_sb[t] = __ldg(a.ptr + seg + 1);
         } else {
-          s_wrow[t] = MODE == BOND ? a.idx1[r] : a.idx2[r];
+          const int wr = MODE == BOND ? a.idx1[r] : a.idx2[r];
+          s_wrow[t] = wr;
+          prefetch_l2(a.wgt + (size_t)wr * 64);  // the bond-weight row the strip reduction reads after the sweeps
+          prefetch_l2(a.wgt + (size_t)wr * 64 + 32);
         }
       }
       tc::mbar_wait(&bars.d_full[ds], (tl >> 1) & 1);
@@ -569,6 +585,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_bwd_kernel(const BwdAr
         if (MODE == ATOM) s_pidx[2 * TR + t] = a.idx2[r];
       }
       tc::wg_barrier(1, 256);  // indices visible; every thread has converted the previous tile
+      {
+        const int nt = tile + gridDim.x;  // next tile of this CTA: its saved p rows stream from HBM (4 lines of 128 B per row)
+        if (nt < n_tiles) {
+          const int r = min(nt * TR + (t & 127), a.n_rows - 1);
+          const float* row = a.save_p + (size_t)r * 128 + (t >> 7) * 64;
+          prefetch_l2(row);
+          prefetch_l2(row + 32);
+        }
+      }
       float4 g1, g2, b1, b2v;
       if (use_ln) {
         g1 = lds4(s_ln + c0);
@@ -729,6 +754,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_bwd_kernel(const BwdAr
         s_fidx[t] = a.idx0[r];
         s_fidx[TR + t] = a.idx1[r];
         s_fidx[2 * TR + t] = a.idx2[r];
+      }
+      {
+        // the rows this tile's silu' needs that stream from HBM: per-bond products (AtomConv) / saved pre (BondConv)
+        const int r = min(base + crow, a.n_rows - 1);
+        const float* row = MODE == ATOM ? a.p_b + (size_t)__ldg(a.idx2 + r) * 128 + chalf * 64 : a.save_pre + (size_t)r * 128 + chalf * 64;
+        prefetch_l2(row);
+        prefetch_l2(row + 32);
       }
       tc::mbar_wait(&bars.d_full[ds], (tl >> 1) & 1);
       tc::fence_after_sync();
