@@ -92,6 +92,7 @@ class _DeviceSystem:
         self._update_frac()
         self._rebuild()
         self._forward()
+        self._old_graph = None
 
     # ---- pieces ---------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -109,7 +110,7 @@ class _DeviceSystem:
         self.batch = batch
         self.x_ref.copy_(self.x)
         self.max_disp2.zero_()
-        self.graph = None
+        self._old_graph, self.graph = self.graph, None  # keep the pool's last user alive until the next capture
         self.n_builds += 1
 
     def _forward(self) -> None:
@@ -195,7 +196,7 @@ class DeviceMD(_DeviceSystem):
                 s.synchronize()
                 self.x.copy_(state[0]), self.v.copy_(state[1]), self.f.copy_(state[2]), self.max_disp2.copy_(state[3])
                 self._warmed = True
-            self.graph = None  # release the previous capture's buffers back to the shared pool first
+            # the previous capture stays alive until the new one exists: the shared pool must never drop to zero users
             g = torch.cuda.CUDAGraph()
             g.capture_begin(pool=self._pool)
             try:
@@ -203,6 +204,7 @@ class DeviceMD(_DeviceSystem):
             finally:
                 g.capture_end()
         torch.cuda.current_stream(self.dev).wait_stream(s)
+        self._old_graph = None
         self.graph = g  # capturing executed nothing: the state is still the pre-step state
         self.n_captures += 1
         self.t_capture += time.perf_counter() - t0

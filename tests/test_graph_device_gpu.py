@@ -117,3 +117,28 @@ def test_model_gives_the_same_answer_through_the_device_builder(builder):
     assert abs(e - float(host["e"])) < 1e-5
     assert np.abs(res["force"].float().cpu().numpy() - host["f"]).max() < 1e-4
     assert np.abs(res["magmom"].cpu().numpy() - host["m"]).max() < 1e-4
+
+
+def test_predict_structure_device_and_host_graph_paths_agree(monkeypatch):
+    """CHGNet.predict_structure builds the graph on the device by default; CHGNET_B200_GRAPH=host selects the host
+    converter.  Same graph bit for bit -> same numbers; isolated atoms raise like the reference's converter
+    (converter.py:160-174)."""
+    import os
+
+    from chgnet_b200.model import CHGNet
+
+    gold = os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz")
+    model = CHGNet.from_file(gold, version="0.3.0").to("cuda")
+    z, frac, lat = graphgen.random_structure(31, 9720)
+    dev = model.predict_structure((z, frac, lat), task="efsm", return_site_energies=True, return_crystal_feas=True)
+    monkeypatch.setenv("CHGNET_B200_GRAPH", "host")
+    host = model.predict_structure((z, frac, lat), task="efsm", return_site_energies=True, return_crystal_feas=True)
+    monkeypatch.delenv("CHGNET_B200_GRAPH")
+    assert set(dev) == set(host)
+    for k in host:
+        assert dev[k].shape == host[k].shape, k
+        assert np.abs(np.asarray(dev[k], np.float64) - np.asarray(host[k], np.float64)).max() < 1e-5, k
+    with pytest.raises(ValueError, match="isolated atom"):
+        model.predict_structure(([1, 1], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 20.0))
+    with pytest.raises(IndexError, match="index out of range"):
+        model.predict_structure(([3, 99], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 4.0))
