@@ -785,6 +785,28 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                       "api": "CHGNet.predict_graph(CrystalGraph on host, task='efs')"},
               "roofline": scatter_roofline(K, l4["batch"], "c4", dev), "clocks": l4["clocks"], "n_gpus": 1,
               "note": "one structure does not shard: rank 0 alone (replicas only, DESIGN.md §7)"}
+        try:  # the same structure through predict_structure: graph built ON THE DEVICE, only z / frac / lattice cross PCIe
+            from chgnet_b200 import graphgen as _gg
+
+            z4, f4, l4m = _gg.limno2_structure((10, 5, 25), 0.02, 4000)
+            for _ in range(2):
+                model.predict_structure((z4, f4, l4m), task="efs")
+            tt = 0.0
+            flush4 = L2Flush(dev)
+            for _ in range(5):
+                flush4()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                model.predict_structure((z4, f4, l4m), task="efs")
+                torch.cuda.synchronize()
+                tt += time.perf_counter() - t0
+            c4["e2e_from_structure"] = {"ms_per_step": round(tt / 5 * 1e3, 4), "atoms_per_s": round(c4c["atoms"] / (tt / 5), 1),
+                                        "over_kernel_path": round(tt / 5 * 1e3 / l4["ms_per_step"], 3),
+                                        "h2d_bytes_per_step": int(c4c["atoms"] * (4 + 24) + 72), "d2h_bytes_per_step": l4["d2h"],
+                                        "api": "CHGNet.predict_structure((Z, frac, lattice), task='efs'): chg_graph_build_device + "
+                                               "chg_build_csr + chg_forward"}
+        except Exception as exc:
+            c4["e2e_from_structure"] = {"unavailable": repr(exc)[:300]}
         if not args.no_md:
             try:
                 c4["md"] = md_leg(model, dev)
