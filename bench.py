@@ -639,29 +639,34 @@ def md_leg(model, dev, steps: int = 20) -> dict:
 
     z, frac, lat = graphgen.limno2_structure((10, 5, 25), 0.02, 4000)
     pos = frac @ lat
-    md = DeviceMD(model, z, pos, lat, timestep=2.0, skin=0.5)
-    md.set_temperature(300.0, seed=1)
-    md.run(5, log_every=0)
-    torch.cuda.synchronize()
-    md.t_rebuild = md.t_capture = 0.0
-    b0 = md.n_builds
-    t0 = time.perf_counter()
-    md.run(steps, log_every=0)
-    torch.cuda.synchronize()
-    dt_dev = (time.perf_counter() - t0) / steps
-    e_tot = md.potential_energy + md.kinetic_energy
+    def run_device(skin):
+        md = DeviceMD(model, z, pos, lat, timestep=2.0, skin=skin)
+        md.set_temperature(300.0, seed=1)
+        md.run(5, log_every=0)
+        torch.cuda.synchronize()
+        md.t_rebuild = md.t_capture = 0.0
+        b0 = md.n_builds
+        t0 = time.perf_counter()
+        md.run(steps, log_every=0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        return {"ms_per_step": round(dt * 1e3, 3), "steps_per_s": round(1.0 / dt, 2), "steps": steps, "skin_A": md.skin,
+                "graph_rebuilds": md.n_builds - b0, "model_edges": int(md.batch.n_edges), "model_angles": int(md.batch.n_angles),
+                "host_s_in_rebuilds": round(md.t_rebuild, 4), "host_s_in_captures": round(md.t_capture, 4),
+                "e_total_eV": md.potential_energy + md.kinetic_energy}
+
+    dev_exact = run_device(0.0)
+    dev_exact["what"] = ("DeviceMD(skin=0): kick+drift -> chg_graph_build_device + chg_build_csr (exact lists, every step) -> "
+                         "chg_forward -> kick; positions / velocities / forces never leave the device")
+    dev_skin = run_device(0.5)
+    dev_skin["what"] = "DeviceMD(skin=0.5): lists with cutoffs + 0.5 A reused until an atom moved 0.25 A; the step is one CUDA graph replay"
     host = VelocityVerlet(Atoms(z, pos, lat), CHGNetCalculator(model=model, on_isolated_atoms="ignore"), timestep=2.0)
     host.set_temperature(300.0, seed=1)
     host.run(2)
     t0 = time.perf_counter()
     host.run(5)
     dt_host = (time.perf_counter() - t0) / 5
-    return {"atoms": int(len(z)), "timestep_fs": 2.0, "temperature_K": 300.0,
-            "device_driver": {"ms_per_step": round(dt_dev * 1e3, 3), "steps_per_s": round(1.0 / dt_dev, 2), "steps": steps,
-                              "graph_rebuilds": md.n_builds - b0, "skin_A": 0.5, "model_edges_with_skin": int(md.batch.n_edges),
-                              "host_s_in_rebuilds": round(md.t_rebuild, 4), "host_s_in_captures": round(md.t_capture, 4),
-                              "what": "DeviceMD: kick+drift -> chg_forward -> kick as one CUDA graph per step, "
-                                      "chg_graph_build_device when an atom moved > skin/2", "e_total_eV": e_tot},
+    return {"atoms": int(len(z)), "timestep_fs": 2.0, "temperature_K": 300.0, "device_driver": dev_exact, "device_driver_skin": dev_skin,
             "host_driver": {"ms_per_step": round(dt_host * 1e3, 3), "steps_per_s": round(1.0 / dt_host, 2), "steps": 5,
                             "what": "CHGNetCalculator loop (the reference's structure, dynamics.py:129-181): host graph build "
                                     "(native C++), H2D, chg_forward, D2H, numpy integrator"}}

@@ -5,9 +5,12 @@ The reference's MD loop is ``ase.md`` driving ``CHGNetCalculator.calculate`` (re
 (dynamics.py:156-157), copies it to the GPU, runs the model and copies energy / forces / stress back.  Here positions,
 velocities and forces never leave the device:
 
-* ``DeviceGraphBuilder`` (csrc/graph_device.cu) rebuilds the neighbour list / bond graph on the GPU, with a Verlet
-  SKIN: the lists are built with cutoffs ``r + skin`` and reused until some atom has moved more than ``skin / 2`` since
-  the last build.  Pairs beyond the model's cutoffs contribute exactly zero - CHGNet's polynomial envelope and hence the
+* ``DeviceGraphBuilder`` (csrc/graph_device.cu) rebuilds the neighbour list / bond graph on the GPU.  Two policies:
+  ``skin = 0`` - rebuild every step between the drift and the model call, exact cutoffs (the right choice for large
+  cells: the build costs 0.5 ms for 10,000 atoms while a skin inflates the model's work, angles grow like (3 + skin)^6);
+  ``skin > 0`` - a Verlet SKIN: the lists are built with cutoffs ``r + skin`` and reused until some atom has moved more
+  than ``skin / 2`` since the last build, which lets the whole step be ONE CUDA graph replay (the right choice for small
+  cells, where the ~140 launches of a step cost more than the kernels).  ``skin=None`` picks by the number of atoms.  Pairs beyond the model's cutoffs contribute exactly zero - CHGNet's polynomial envelope and hence the
   bond weights w_ag / w_bg vanish for d >= r_c (reference basis.py:184-205, layers.py:118-126, 245-254) - so the skin
   changes no result (tests/test_dynamics_device_gpu.py compares against rebuilding every step);
 * between rebuilds the step = [half kick + drift] -> ``chg_forward`` -> [half kick] is ONE CUDA graph replay
@@ -54,7 +57,7 @@ def _check(rc: int, what: str) -> None:
 class _DeviceSystem:
     """Positions / velocities / forces on the device + the model evaluation with a skin-managed graph."""
 
-    def __init__(self, model, numbers, positions, cell, *, skin: float = 0.5, use_cuda_graph: bool = True) -> None:
+    def __init__(self, model, numbers, positions, cell, *, skin: float | None = 0.5, use_cuda_graph: bool = True) -> None:
         self.model = model.eval()
         self.dev = model.device
         if self.dev.type != "cuda":
@@ -75,13 +78,16 @@ class _DeviceSystem:
         self.x_ref = self.x.clone()
         self.max_disp2 = torch.zeros(1, **f64)
         self.e_kin = torch.zeros(1, **f64)
+        if skin is None:  # large cells: exact lists every step; small cells: skin + one CUDA graph per step
+            skin = 0.0 if self.n >= 2000 else 0.5
         self.skin = float(skin)
-        if self.skin <= 0.0:
-            raise ValueError("skin must be positive: the neighbour lists are reused until an atom has moved skin / 2")
+        if self.skin < 0.0:
+            raise ValueError("skin must be >= 0")
+        self.every_step = self.skin == 0.0
         gc = model.graph_converter
         self.builder = DeviceGraphBuilder(self.dev, float(gc.atom_graph_cutoff) + self.skin, float(gc.bond_graph_cutoff) + self.skin)
         self.compact = not model._arch.get("mlp_out_bias", False)
-        self.use_cuda_graph = use_cuda_graph
+        self.use_cuda_graph = use_cuda_graph and not self.every_step
         self.batch = None
         self.graph = None
         self.out: dict | None = None
@@ -133,7 +139,7 @@ class _DeviceSystem:
 class DeviceMD(_DeviceSystem):
     """Velocity-Verlet NVE with positions, velocities and forces resident on the device; ``timestep`` in fs."""
 
-    def __init__(self, model, numbers, positions, cell, *, timestep: float = 2.0, velocities=None, skin: float = 0.5,
+    def __init__(self, model, numbers, positions, cell, *, timestep: float = 2.0, velocities=None, skin: float | None = None,
                  use_cuda_graph: bool = True) -> None:
         super().__init__(model, numbers, positions, cell, skin=skin, use_cuda_graph=use_cuda_graph)
         self.dt = float(timestep) * FS
@@ -153,6 +159,8 @@ class DeviceMD(_DeviceSystem):
             _check(lib.chg_md_kick_drift(self.x.data_ptr(), self.v.data_ptr(), self.f.data_ptr(), self.inv_mass.data_ptr(), self.n, self.dt,
                                          self.inv_cell.ctypes.data, self.frac64.data_ptr(), self.frac32.data_ptr(),
                                          self.x_ref.data_ptr(), self.max_disp2.data_ptr(), st), "chg_md_kick_drift")
+        if self.every_step:  # exact neighbour lists for the new positions (0.5 ms for 10,000 atoms)
+            self._rebuild()
         self._forward()
         self.e_kin.zero_()
         with torch.cuda.device(self.dev):
@@ -167,7 +175,7 @@ class DeviceMD(_DeviceSystem):
         else:
             self._step_body()
         self.n_steps += 1
-        if self.needs_rebuild():
+        if not self.every_step and self.needs_rebuild():
             import time
 
             t0 = time.perf_counter()
@@ -231,7 +239,7 @@ class DeviceFIRE(_DeviceSystem):
     on the device; the host looks at the largest force every ``check_every`` steps."""
 
     def __init__(self, model, numbers, positions, cell, *, dt: float = 0.1, dt_max: float = 1.0, max_step: float = 0.2,
-                 skin: float = 0.5) -> None:
+                 skin: float | None = None) -> None:
         super().__init__(model, numbers, positions, cell, skin=skin, use_cuda_graph=False)
         self.dt_max, self.max_step = float(dt_max), float(max_step)
         self.state = torch.zeros(12, dtype=torch.float64, device=self.dev)
@@ -248,9 +256,12 @@ class DeviceFIRE(_DeviceSystem):
                                          self.inv_cell.ctypes.data, self.frac64.data_ptr(), self.frac32.data_ptr(), self.dt_max,
                                          self.max_step, self._stream()), "chg_fire_step")
             # skin test on the host side of the loop (positions moved by at most max_step)
-            d2 = float(((self.x - self.x_ref) ** 2).sum(dim=1).max().item())
-            if d2 > (0.5 * self.skin) ** 2:
+            if self.every_step:
                 self._rebuild()
+            else:
+                d2 = float(((self.x - self.x_ref) ** 2).sum(dim=1).max().item())
+                if d2 > (0.5 * self.skin) ** 2:
+                    self._rebuild()
             self._forward()
             it += 1
             if it % check_every == 0 or it == steps:

@@ -37,10 +37,14 @@ def test_device_trajectory_equals_the_host_driver_and_conserves_energy(model):
     v0 = host_atoms.velocities.copy()
     dev = DeviceMD(model, z, pos, cell, timestep=2.0, velocities=v0, skin=0.5)
     wide = DeviceMD(model, z, pos, cell, timestep=2.0, velocities=v0, skin=1.2, use_cuda_graph=False)  # different lists, same physics
+    exact = DeviceMD(model, z, pos, cell, timestep=2.0, velocities=v0, skin=0.0)  # exact lists rebuilt on the device every step
     e0 = host.potential_energy() + host.kinetic_energy()
     hlog = host.run(steps)
     dlog = dev.run(steps)
     wide.run(steps)
+    exact.run(steps)
+    de = np.abs(exact.positions() - host_atoms.positions).max()
+    assert de < 1e-4 and exact.n_builds == steps + 1, (de, exact.n_builds)
     dx = np.abs(dev.positions() - host_atoms.positions).max()
     dn = np.abs(dev.positions() - wide.positions()).max()
     print(f"50 steps: max |x_device - x_host (graph rebuilt every step)| = {dx:.2e} A, |x_skin0.5 - x_skin1.2| = {dn:.2e} A; "
