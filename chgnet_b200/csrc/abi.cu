@@ -40,7 +40,7 @@ namespace {
 // the warp-specialised tcgen05 kernel (linear_impl 3); the AtomConv / BondConv message + aggregation runs as the
 // fused warp-specialised tcgen05 kernel of gated_ws.cu (gated_impl 3) wherever the engine calls the fused entry
 // points; gated_impl 0..2 select the older unfused kernels (FFMA 4x8 / tcgen05 / FFMA 8x8) for A/B runs.
-std::atomic<int> g_linear_impl{-1}, g_gated_impl{-1};
+std::atomic<int> g_linear_impl{-1}, g_gated_impl{-1}, g_wgrad_impl{-1}, g_ws_min_rows{-1};
 int env_default(const char* name, int dflt) {
   const char* e = getenv(name);
   if (e == nullptr || e[0] == 0) return dflt;
@@ -51,6 +51,21 @@ int env_default(const char* name, int dflt) {
 int linear_impl() {
   int v = g_linear_impl.load();
   if (v < 0) { v = env_default("CHG_LINEAR_IMPL", 3); g_linear_impl.store(v); }
+  return v;
+}
+int ws_min_rows() {
+  int v = g_ws_min_rows.load();
+  if (v < 0) {
+    const char* e = getenv("CHG_WS_MIN_ROWS");
+    v = (e != nullptr && e[0] != 0) ? atoi(e) : 4096;
+    if (v < 0) v = 0;
+    g_ws_min_rows.store(v);
+  }
+  return v;
+}
+int wgrad_impl() {
+  int v = g_wgrad_impl.load();
+  if (v < 0) { v = env_default("CHG_WGRAD_IMPL", 1); g_wgrad_impl.store(v); }
   return v;
 }
 int gated_impl() {
@@ -64,6 +79,8 @@ extern "C" int chg_set_option(const char* name, int32_t value) {
   if (name == nullptr) return CHG_ERR_ARG;
   if (strcmp(name, "linear_impl") == 0) { chg::g_linear_impl.store(value < 0 ? 0 : (value > 3 ? 3 : value)); return CHG_OK; }
   if (strcmp(name, "gated_impl") == 0) { chg::g_gated_impl.store(value < 0 ? 0 : (value > 3 ? 3 : value)); return CHG_OK; }
+  if (strcmp(name, "ws_min_rows") == 0) { chg::g_ws_min_rows.store(value < 0 ? 0 : value); return CHG_OK; }
+  if (strcmp(name, "wgrad_impl") == 0) { chg::g_wgrad_impl.store(value != 0 ? 1 : 0); return CHG_OK; }
   chg::set_error("chg_set_option: unknown option %s", name);
   return CHG_ERR_ARG;
 }

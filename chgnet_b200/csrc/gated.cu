@@ -782,7 +782,7 @@ extern "C" int chg_atom_conv_bwd(const float* pcn, const float* pe, const float*
   CHG_CHECK_ARG(pcn && pe && wag && center && nbr && d2u && save_p && g_agg && w2 && g_pre && g_w, "null pointer");
   BwdArgs a{pcn, pe, wag, center, nbr, d2u, n_edges, nullptr, save_p, g_agg, w2, ln, g_pre, g_w, nullptr, g_p, g_ln};
   const bool train = g_p != nullptr || g_ln != nullptr;
-  if (gated_impl() == 3 && !train) return atom_conv_bwd_ws(a, as_stream(stream));  // warp-specialised tcgen05 (default)
+  if (gated_impl() == 3 && !train && n_edges >= ws_min_rows()) return atom_conv_bwd_ws(a, as_stream(stream));  // warp-specialised tcgen05 (default)
   if (gated_impl() == 1 && !train) return atom_conv_bwd_tc(a, as_stream(stream));
   if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;
@@ -817,7 +817,7 @@ extern "C" int chg_bond_conv_bwd(const float* save_pre, const float* save_p, con
   BwdArgs a{nullptr, nullptr, wbg, ang_i, ang_j, nullptr, n_angles, save_pre, save_p, g_agg, w2, ln,
             g_pre, gw_i, gw_j, g_p, g_ln};
   const bool train = g_p != nullptr || g_ln != nullptr;
-  if (gated_impl() == 3 && !train) return bond_conv_bwd_ws(a, as_stream(stream));  // warp-specialised tcgen05 (default)
+  if (gated_impl() == 3 && !train && n_angles >= ws_min_rows()) return bond_conv_bwd_ws(a, as_stream(stream));  // warp-specialised tcgen05 (default)
   if (gated_impl() == 1 && !train) return bond_conv_bwd_tc(a, as_stream(stream));
   if (gated_impl() == 2 && !train) {  // 8x8-tile variant (measured slower end to end; kept for A/B)
     static int slots = 0;

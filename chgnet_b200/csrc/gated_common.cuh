@@ -7,6 +7,11 @@ namespace gated {
 
 constexpr int HS = 132;    // smem stride of a 128-wide row
 constexpr float LN_EPS = 1e-5f;
+}  // namespace gated
+// below this many rows the warp-specialised tcgen05 kernels hand the call to the FFMA kernels (launch-bound regime);
+// chg_set_option("ws_min_rows", n) / env CHG_WS_MIN_ROWS, default 4096 (abi.cu)
+int ws_min_rows();
+namespace gated {
 
 enum Mode { ATOM = 0, BOND = 1, ANGLE = 2 };
 

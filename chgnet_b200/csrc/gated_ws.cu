@@ -472,7 +472,8 @@ extern "C" int chg_atom_conv_fused(const float* pcn, const float* pe, const floa
   if (n_atoms == 0) return CHG_OK;
   CHG_CHECK_ARG(ptr_c && agg, "null pointer");
   CHG_CHECK_ARG(n_edges == 0 || (pcn && pe && wag && center && nbr && d2u && w2t && b2 && work), "null pointer");
-  if (gated_impl() == 3)
+  // tiny inputs (a few tiles) are launch-bound: the persistent tcgen05 kernel's fixed cost (weight images, TMEM) loses there
+  if (gated_impl() == 3 && n_edges >= ws_min_rows())
     return gated::atom_conv_fused_ws(pcn, pe, wag, center, nbr, d2u, ptr_c, n_edges, n_atoms, w2t, b2, ln, agg, save_p, work,
                                      as_stream(stream));
   // A/B implementations 0..2: the unfused pair (message kernel -> segmented sum), the message in `work`
@@ -490,7 +491,7 @@ extern "C" int chg_bond_conv_fused(const float* pij, const float* px, const floa
   if (n_slots == 0) return CHG_OK;
   CHG_CHECK_ARG(ptr_i && agg, "null pointer");
   CHG_CHECK_ARG(n_angles == 0 || (pij && px && pa && wbg && ang_atom && ang_i && ang_j && w2t && b2 && work), "null pointer");
-  if (gated_impl() == 3)
+  if (gated_impl() == 3 && n_angles >= ws_min_rows())
     return gated::bond_conv_fused_ws(pij, px, pa, wbg, ang_atom, ang_i, ang_j, ptr_i, n_angles, n_slots, w2t, b2, ln, agg,
                                      save_pre, save_p, work, as_stream(stream));
   const int rc = chg_bond_conv_fwd(pij, px, pa, wbg, ang_atom, ang_i, ang_j, n_angles, w2t, b2, ln, work, save_pre, save_p, stream);

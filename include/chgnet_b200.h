@@ -51,7 +51,10 @@ int64_t chg_launch_count(void);
  *   "gated_impl" : 3 fused warp-specialised tcgen05 message + aggregation (default; chg_*_conv_fused),
  *                  0 FFMA 4x8 tiles, 1 tcgen05 (un-pipelined), 2 FFMA 8x8 tiles (all unfused; with 3 the
  *                  unfused entry points chg_*_conv_fwd / _bwd run the FFMA 4x8 kernels)
- * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3 set the defaults).                             */
+ *   "ws_min_rows": calls with fewer rows than this (default 4096) run the FFMA kernels even with gated_impl 3
+ *                  (launch-bound regime: the persistent tcgen05 kernels' fixed cost loses on a few tiles)
+ *   "wgrad_impl" : 1 tcgen05 3xTF32 for reductions over >= 4096 rows (default; csrc/wgrad_tc.cu), 0 FFMA
+ * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3, CHG_WGRAD_IMPL = 0..1 set the defaults).       */
 int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */

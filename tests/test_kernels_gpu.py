@@ -48,6 +48,7 @@ def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
     K = CudaKernels()
     K.set_option("linear_impl", linear_impl)
     K.set_option("gated_impl", gated_impl)
+    K.set_option("ws_min_rows", 0)  # the recorded graphs are small: run the tcgen05 kernels on them anyway
     try:
         seen = {}
         for name, snap, outs in recorded:
@@ -62,6 +63,7 @@ def test_every_kernel_matches_its_spec(recorded, linear_impl, gated_impl):
     finally:
         K.set_option("linear_impl", 3)
         K.set_option("gated_impl", 3)
+        K.set_option("ws_min_rows", 4096)
 
 
 def test_every_training_kernel_matches_its_spec(weights030):
@@ -218,3 +220,55 @@ def test_bad_arguments_are_reported():
         K.linear(x, torch.zeros(96, 64, device="cuda"), None, None, torch.zeros(4, 64, device="cuda"))
     with pytest.raises(ChgnetB200Error):
         K.linear(torch.zeros(4, 64), torch.zeros(64, 64), None, None, torch.zeros(4, 64))  # CPU tensors
+
+
+@pytest.mark.parametrize("wgrad_impl", [1, 0], ids=["tcgen05", "ffma"])
+def test_wgrad_large_reduction_matches_fp64(wgrad_impl):
+    """chg_wgrad at the sizes where the tensor-core kernel (csrc/wgrad_tc.cu, 3xTF32) takes over (>= 4096 rows): plain,
+    SiLU'd and tangent activations, row gathers on either operand, strided operands, column sums - against fp64."""
+    from chgnet_b200._lib import CudaKernels
+
+    K = CudaKernels()
+    K.set_option("wgrad_impl", wgrad_impl)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        m = 20011  # not a multiple of the 64-row stage
+        xs = torch.randn(m, 128, device="cuda", generator=gen)
+        x2 = torch.randn(m, 128, device="cuda", generator=gen)
+        gs = torch.randn(m, 256, device="cuda", generator=gen)
+        perm = torch.randperm(m, device="cuda", generator=gen).int()
+        sub = perm[:9000].contiguous()
+        silu, dsilu = torch.nn.functional.silu, (lambda t: torch.sigmoid(t) * (1 + t * (1 - torch.sigmoid(t))))
+        cases = [
+            dict(x=xs[:, :64], g=gs[:, :128], n=128),
+            dict(x=xs[:, 64:], g=gs[:, 64:128], n=64, x_silu=True, colsum=True),
+            dict(x=xs[:, :64], g=gs[:, 128:], n=128, x2=x2[:, :64]),
+            dict(x=xs[:, :64], g=gs[:, :128], n=128, x_rows=sub, colsum=True),
+            dict(x=xs[:, 64:], g=gs[:, :64], n=64, g_rows=sub),
+        ]
+        for c in cases:
+            n = c["n"]
+            out = torch.empty(64, n, device="cuda")
+            cs = torch.empty(n, device="cuda") if c.get("colsum") else None
+            K.wgrad(c["x"], c["g"], out, cs, c.get("x_rows"), c.get("g_rows"), c.get("x_silu", False), c.get("x2"))
+            torch.cuda.synchronize()
+            xr = c["x"].double() if c.get("x_rows") is None else c["x"].double()[c["x_rows"].long()]
+            gr = c["g"].double() if c.get("g_rows") is None else c["g"].double()[c["g_rows"].long()]
+            if c.get("g_rows") is not None and c.get("x_rows") is None:
+                xr = xr[: gr.shape[0]]
+            if c.get("x_rows") is not None and c.get("g_rows") is None:
+                gr = gr[: xr.shape[0]]
+            act = xr
+            if c.get("x_silu"):
+                act = silu(xr)
+            if c.get("x2") is not None:
+                act = dsilu(xr) * c["x2"].double()
+            want = act.T @ gr
+            scale = float(want.abs().max())
+            err = float((out.double() - want).abs().max())
+            assert err < 3e-5 * scale + 1e-5, (wgrad_impl, c.keys(), err, scale)
+            if cs is not None:
+                wc = gr.sum(dim=0)
+                assert float((cs.double() - wc).abs().max()) < 3e-5 * float(wc.abs().max()) + 1e-4
+    finally:
+        K.set_option("wgrad_impl", 1)

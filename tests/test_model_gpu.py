@@ -54,6 +54,7 @@ def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, lin
     K = CudaKernels()
     K.set_option("linear_impl", linear_impl)
     K.set_option("gated_impl", gated_impl)
+    K.set_option("ws_min_rows", 0)  # 8-atom cell: force the tcgen05 kernels where gated_impl asks for them
     try:
         out = model.predict_graph(limno2_graph)
         for k, tol in TOL.items():
@@ -61,6 +62,7 @@ def test_limno2_parity_for_every_implementation(model, limno2_graph, golden, lin
     finally:
         K.set_option("linear_impl", 3)
         K.set_option("gated_impl", 3)
+        K.set_option("ws_min_rows", 4096)
 
 
 def test_random_batch_vs_reference_golden(model, golden):
