@@ -192,7 +192,7 @@ def run_train(args, rank: int, world: int, local_rank: int, light: bool = False)
     def step_resident():
         engine = model._get_engine()  # re-packs the weights the previous Adam step changed
         report_, G = loss_and_grads(engine, batch, trainer.cfg, tg_dev, model.is_intensive, None)
-        fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
+        fg = trainer.flatten_packed_grads(G)
         if world > 1:
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
@@ -201,7 +201,7 @@ def run_train(args, rank: int, world: int, local_rank: int, light: bool = False)
             ar_events.append((a0, a1, fg.numel() * fg.element_size()))
         trainer.step_count += 1
         K.adam_step(trainer.flat, fg, trainer.exp_avg, trainer.exp_avg_sq, trainer.lr, 0.9, 0.999, 1e-8, 0.0, trainer.step_count)
-        model.mark_params_updated()
+        trainer.refresh_packed_weights()
         return report_
 
     n_steps = min(args.steps, 5) if light else args.steps
@@ -283,7 +283,7 @@ def run_train(args, rank: int, world: int, local_rank: int, light: bool = False)
     t4 = tick()
     G = engine.param_grads(o, (seeds["e"] / n_dev.float()).contiguous(), seeds["m"], seeds["f"], seeds["s"])
     t5 = tick()
-    fg = trainer.flatten_grads(unpack_grads(G, model.state_dict()))
+    fg = trainer.flatten_packed_grads(G)
     t6 = tick()
     breakdown = {"repack_weights_ms": (t1 - t0) * 1e3, "forward_ms": (t2 - t1) * 1e3, "force_pass_ms": (t3 - t2) * 1e3,
                  "loss_ms": (t4 - t3) * 1e3, "second_order_and_wgrads_ms": (t5 - t4) * 1e3,

@@ -381,6 +381,16 @@ class CHGNet(nn.Module):
             self._native_key = key
         return self._native
 
+    def _engine_cache_key(self) -> tuple:
+        sd = self.state_dict()
+        return (str(self.device), tuple(int(v._version) for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
+
+    def _mark_engine_current(self) -> None:
+        """The training engine's packed weights were refreshed in place (Trainer.refresh_packed_weights): keep the
+        Engine object, record that it matches the parameters as they are now."""
+        if self._engine is not None:
+            self._engine_key = self._engine_cache_key()
+
     def mark_params_updated(self) -> None:
         """Call after changing parameter storage in place from outside autograd (e.g. the fused Adam
         kernel): the packed kernel weights are rebuilt on the next forward."""

@@ -25,7 +25,7 @@ from dataclasses import dataclass
 import torch
 from torch import Tensor
 
-from chgnet_b200.weights import unpack_grads
+from chgnet_b200.weights import GradFlattenMap, RepackMap, unpack_grads
 
 _KIND = {"MSE": 0, "mse": 0, "MAE": 1, "mae": 1, "l1": 1, "Huber": 2}
 
@@ -165,6 +165,8 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         model.mark_params_updated()
+        self._repack: RepackMap | None = None  # in-place refresh of the packed kernel weights (built on first use)
+        self._gflat: GradFlattenMap | None = None  # packed-layout gradients -> flat buffer in one gather
 
     # ------------------------------------------------------------------
     def _targets(self, targets: dict, n_list: Sequence[int], device) -> dict[str, Tensor]:
@@ -189,6 +191,28 @@ class Trainer:
             self.flat_grad[o:o + sz] = grads[name].reshape(-1)
         return self.flat_grad
 
+    def flatten_packed_grads(self, G: dict) -> Tensor:
+        """``Engine.param_grads`` output -> ``self.flat_grad`` with one concatenation + one gather (the index map is
+        derived once from ``unpack_grads`` itself, so both routes agree element for element)."""
+        if self._gflat is None or not self._gflat.matches(G):
+            self._gflat = GradFlattenMap(G, self.model.state_dict(), self.names, self.offsets, self.sizes, self.flat.numel())
+        return self._gflat.flatten(G, self.flat_grad)
+
+    def refresh_packed_weights(self) -> None:
+        """After the fused Adam step changed the flat buffer: refresh the engine's packed weights in place (one gather)
+        instead of re-packing ~130 tensors in Python.  The inference-side packed blob (chg_forward) is dropped and rebuilt
+        on the next prediction."""
+        model = self.model
+        model._native_key = None
+        eng = model._engine
+        if eng is None:
+            model.mark_params_updated()
+            return
+        if self._repack is None or self._repack.pw is not eng.pw:
+            self._repack = RepackMap(eng.pw, model.state_dict(), model.model_args, self.names, self.offsets, self.flat)
+        self._repack.refresh(self.flat)
+        model._mark_engine_current()
+
     def grads_by_name(self) -> dict[str, Tensor]:
         """views of the (all-reduced) flat gradient buffer, one per parameter"""
         return {n: self.flat_grad[o:o + sz].view(sh) for n, o, sz, sh in zip(self.names, self.offsets, self.sizes, self.shapes)}
@@ -203,12 +227,12 @@ class Trainer:
         batch = build_batch(graphs, model.device, with_reverse=True, compact_bonds=compact)
         tg = self._targets(targets, batch.atoms_per_graph, model.device)
         report, G = loss_and_grads(engine, batch, self.cfg, tg, model.is_intensive, self.group)
-        flat_grad = self.flatten_grads(unpack_grads(G, model.state_dict()))
+        flat_grad = self.flatten_packed_grads(G)
         _all_reduce(flat_grad, self.group)  # the one collective of the step
         self.step_count += 1
         engine.K.adam_step(self.flat, flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0],
                            self.betas[1], self.eps, self.weight_decay, self.step_count)
-        model.mark_params_updated()
+        self.refresh_packed_weights()
         return report
 
     # ------------------------------------------------------------------ checkpoint / resume (trainer.py:614-688)

@@ -291,3 +291,115 @@ def unpack_grads(G: dict, state_dict: dict) -> dict[str, Tensor]:
         if name not in out and torch.is_floating_point(torch.as_tensor(v)):
             out[name] = torch.zeros(tuple(v.shape), dtype=any_g.dtype, device=any_g.device)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Index maps: pack_weights / unpack_grads are pure re-arrangements (slices, transposes, concatenations), so running them
+# ONCE on tensors that hold positions instead of values yields gather maps; afterwards the packed weights are refreshed
+# from the flat parameter buffer, and the packed gradients are flattened, with one gather each (no per-tensor Python).
+# ---------------------------------------------------------------------------------------------------------------------
+def packed_tensors(pw: PackedWeights) -> list[tuple[object, str | tuple]]:
+    """(owner, key) of every tensor of a PackedWeights in a fixed order; owner is the dataclass (attribute key) or an
+    ``extra`` dict (item key)."""
+    out: list[tuple[object, str | tuple]] = []
+    for name in ("emb", "freq_ag", "freq_bg", "freq_ang", "w3t", "w3", "wang_t", "wang", "readout_ln", "mlp_wt", "mlp_w", "mlp_b",
+                 "w_last", "w_mag", "atom_ref"):
+        if getattr(pw, name) is not None:
+            out.append((pw, name))
+    for packs in (pw.atom, pw.bond, pw.angle):
+        for gp in packs:
+            for name in ("w2t", "w2", "b2", "ln"):
+                if getattr(gp, name) is not None:
+                    out.append((gp, name))
+            for k in sorted(gp.extra):
+                if gp.extra[k] is not None:
+                    out.append((gp.extra, (k,)))
+    return out
+
+
+def _get(owner, key):
+    return owner[key[0]] if isinstance(key, tuple) else getattr(owner, key)
+
+
+def _set(owner, key, val) -> None:
+    if isinstance(key, tuple):
+        owner[key[0]] = val
+    else:
+        setattr(owner, key, val)
+
+
+class RepackMap:
+    """Refresh ``pw`` in place from the flat trainable-parameter buffer: ``pbuf[pos] = flat[src]`` (two launches).
+
+    ``offsets`` / ``names``: where every trainable parameter sits in ``flat`` (chgnet_b200.trainer.Trainer)."""
+
+    def __init__(self, pw: PackedWeights, state_dict: dict, model_args: dict | None, names, offsets, flat: Tensor) -> None:
+        dev = flat.device
+        where = dict(zip(names, offsets))
+        sd_idx = {}
+        for k, v in state_dict.items():
+            v = torch.as_tensor(v)
+            if not torch.is_floating_point(v):
+                continue
+            if k in where:
+                sd_idx[k] = (where[k] + 1 + torch.arange(v.numel(), dtype=torch.float64, device=dev)).reshape(v.shape)
+            else:  # frozen parameter / buffer: position 0 = "keep the packed value"
+                sd_idx[k] = torch.zeros(v.shape, dtype=torch.float64, device=dev)
+        pw_idx = pack_weights(sd_idx, model_args, device=dev, dtype=torch.float64)
+        real, idx = packed_tensors(pw), packed_tensors(pw_idx)
+        assert [k for _, k in real] == [k for _, k in idx]
+        sizes = [(_get(o, k).numel() + 15) // 16 * 16 for o, k in real]  # 64-byte aligned pieces
+        self.pbuf = torch.zeros(sum(sizes), dtype=flat.dtype, device=dev)
+        src = torch.zeros(sum(sizes), dtype=torch.int64, device=dev)
+        off = 0
+        for (o, k), (oi, ki), sz in zip(real, idx, sizes):
+            t = _get(o, k)
+            view = self.pbuf[off : off + t.numel()].view(t.shape)
+            view.copy_(t)
+            _set(o, k, view)  # the engine now reads the shared buffer
+            src[off : off + t.numel()] = _get(oi, ki).reshape(-1).long()
+            off += sz
+        self.pos = torch.nonzero(src > 0).view(-1)
+        self.src = (src[self.pos] - 1).contiguous()
+        self.scalars = torch.tensor([where.get(n, -1) for n in self._scalar_names(state_dict)], dtype=torch.int64, device=dev)
+        self.pw = pw
+
+    @staticmethod
+    def _scalar_names(sd) -> tuple[str, str]:
+        last = max(int(k.split(".")[2]) for k in sd if k.startswith("mlp.layers.") and k.endswith(".weight"))
+        return (f"mlp.layers.{last}.bias", "site_wise.bias")
+
+    def refresh(self, flat: Tensor) -> None:
+        self.pbuf.index_copy_(0, self.pos, flat.index_select(0, self.src))
+        if int(self.scalars.min()) >= 0:  # the two biases the kernels take by value
+            b_last, b_mag = flat.index_select(0, self.scalars).tolist()
+            self.pw.b_last, self.pw.b_mag = float(b_last), float(b_mag)
+
+
+class GradFlattenMap:
+    """``flat_grad = cat(0, G.values())[inv]``: the packed-layout gradients of ``Engine.param_grads`` -> the flat buffer in
+    the Trainer's layout (what ``unpack_grads`` + per-parameter copies did with ~300 small launches)."""
+
+    def __init__(self, G: dict, state_dict: dict, names, offsets, sizes, n_flat: int) -> None:
+        dev = G["emb"].device
+        self.signature = tuple((k, tuple(torch.as_tensor(v).shape)) for k, v in G.items())
+        g_idx, off = {}, 1  # position 0 of the concatenation is a zero
+        for k, v in G.items():
+            v = torch.as_tensor(v)
+            g_idx[k] = (off + torch.arange(v.numel(), dtype=torch.float64, device=dev)).reshape(v.shape)
+            off += v.numel()
+        by_name = unpack_grads(g_idx, state_dict)
+        inv = torch.zeros(n_flat, dtype=torch.int64, device=dev)
+        for n, o, sz in zip(names, offsets, sizes):
+            inv[o : o + sz] = by_name[n].reshape(-1).long()
+        self.inv = inv
+        self.zero = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def matches(self, G: dict) -> bool:
+        return self.signature == tuple((k, tuple(torch.as_tensor(v).shape)) for k, v in G.items())
+
+    def flatten(self, G: dict, out: Tensor) -> Tensor:
+        cat = torch.cat([self.zero] + [torch.as_tensor(v, dtype=torch.float32, device=out.device).reshape(-1) for v in G.values()])
+        torch.index_select(cat, 0, self.inv, out=out)
+        return out
+

@@ -292,7 +292,17 @@ def test_trainer_step_host_logic_with_spec_kernels(monkeypatch):
     want = dict(zip(names, torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)))
     assert report["loss"] == pytest.approx(float(loss.detach()), rel=1e-3)
     assert report["f_MAE_size"] == 3 * sum(g.atomic_number.shape[0] for i, g in enumerate(graphs) if i in keep)
-    got = trainer.grads_by_name()
+    got = {k: v.clone() for k, v in trainer.grads_by_name().items()}
+    # the one-gather flattening (weights.GradFlattenMap) is the same re-arrangement as unpack_grads + per-parameter copies
+    eng = model._get_engine()
+    b_chk = build_batch(graphs, "cpu")
+    from chgnet_b200.trainer import loss_and_grads
+
+    _, G_chk = loss_and_grads(eng, b_chk, trainer.cfg, trainer._targets(lab, b_chk.atoms_per_graph, "cpu"), model.is_intensive, False)
+    slow = {k: v.clone() for k, v in unpack_grads(G_chk, model.state_dict()).items()}
+    fast = trainer.flatten_packed_grads(G_chk).clone()
+    for n_, o_, sz_ in zip(trainer.names, trainer.offsets, trainer.sizes):
+        assert torch.equal(fast[o_:o_ + sz_], slow[n_].reshape(-1).float()), n_
     for k in names:
         wk = want[k] if want[k] is not None else torch.zeros_like(P[k])
         assert float((got[k].double() - wk).abs().max()) <= 2e-2 * float(wk.abs().max()) + 1e-5, k  # fp32 spec vs fp64
@@ -318,7 +328,16 @@ def test_trainer_step_host_logic_with_spec_kernels(monkeypatch):
     trainer.scheduler_step()
     trainer.save(ckpt)
     report2 = trainer.train_step(graphs, lab)
-    assert calls["n"] == n_before + 1 and report2["loss"] != report["loss"]  # new weights were re-packed and used
+    # the new weights were used, and WITHOUT another Python re-pack: the packed kernel weights are refreshed in place from
+    # the flat buffer (weights.RepackMap) and must equal a fresh pack of the current state_dict, tensor for tensor
+    assert calls["n"] == n_before and report2["loss"] != report["loss"]
+    from chgnet_b200.weights import packed_tensors, _get
+
+    fresh = pack_weights(model.state_dict(), model.model_args, device="cpu")
+    live = model._engine.pw
+    for (o1, k1), (o2, k2) in zip(packed_tensors(live), packed_tensors(fresh)):
+        assert k1 == k2 and torch.equal(_get(o1, k1), _get(o2, k2)), k1
+    assert live.b_last == pytest.approx(fresh.b_last, rel=1e-7) and live.b_mag == pytest.approx(fresh.b_mag, rel=1e-7)
     resumed = Trainer.load(ckpt, device="cpu")
     assert resumed.step_count == 1 and resumed.lr == pytest.approx(trainer.lr) and resumed.lr < 1e-3
     m2 = resumed.model
