@@ -30,8 +30,8 @@ constexpr int B_IMG = 64 * WT_K * 4;           // 16 KB: act(X)^T, hi or lo
 constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;   // 96 KB
 constexpr int WT_SMEM = 2 * STAGE + 2 * WT_K * 4 * 2 + 1024;
 
-// ACT: 0 x, 1 silu(x), 2 silu'(x) * x2
-template <int ACT>
+// ACT: 0 x, 1 silu(x), 2 silu'(x) * x2;  GG = 32-column groups of the G block (2: 64 columns, 4: 128 columns)
+template <int ACT, int GG>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int ldx, const int32_t* __restrict__ x_rows,
                 const float* __restrict__ g, int ldg, const int32_t* __restrict__ g_rows, int m, int n, int n_block,
@@ -85,31 +85,45 @@ wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int l
       s_gi[st * WT_K + tid] = g_rows != nullptr ? g_rows[row] : row;
     }
     __syncthreads();
-    // ---- transpose this stage into the operand images: a work item = (4 consecutive rows, 32 consecutive columns) ----
-    // G block: 16 row-quads x (n_block / 32) column groups; X: 16 row-quads x 2 feature groups
-    const int g_groups = n_block >> 5;
-    for (int item = warp; item < 16 * (g_groups + 2); item += 8) {
-      const int quad = item & 15, grp = item >> 4;
-      const bool is_g = grp < g_groups;
-      const int col = (is_g ? grp : grp - g_groups) * 32 + lane;  // column of G inside the block, or feature of X
-      float v[4];
+    // ---- transpose this stage into the operand images: a work item = (4 consecutive rows, 32 consecutive columns); a warp
+    // owns items warp + 8 t: row-quad warp + 8 (t & 1), column group t >> 1 (G block first, then the two feature groups of X).
+    // ALL loads of the stage are issued before the first use (2 (GG + 2) x 4 independent 4-byte loads per thread in flight).
+    constexpr int ITEMS = 2 * (GG + 2);
+    float v[ITEMS][4], w2[ACT == 2 ? 4 : 1][4];
+#pragma unroll
+    for (int t = 0; t < ITEMS; ++t) {
+      const int quad = warp + 8 * (t & 1), grp = t >> 1;
+      const bool is_g = grp < GG;
+      const int col = (is_g ? grp : grp - GG) * 32 + lane;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int k = quad * 4 + q;
         const bool live = base + k < m;
         if (is_g) {
-          v[q] = live ? __ldg(g + (size_t)s_gi[st * WT_K + k] * ldg + col_base + col) : 0.f;
+          v[t][q] = live ? __ldg(g + (size_t)s_gi[st * WT_K + k] * ldg + col_base + col) : 0.f;
         } else {
-          float xv = live ? __ldg(x + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
-          if (ACT == 1) xv = silu_f(xv);
-          if (ACT == 2) xv = live ? dsilu_f(xv) * __ldg(x2 + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
-          v[q] = xv;
+          v[t][q] = live ? __ldg(x + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
+          if (ACT == 2) w2[t - 2 * GG][q] = live ? __ldg(x2 + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
         }
       }
-      if (is_g) cs[grp] += (v[0] + v[1]) + (v[2] + v[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < ITEMS; ++t) {
+      const int quad = warp + 8 * (t & 1), grp = t >> 1;
+      const bool is_g = grp < GG;
+      const int col = (is_g ? grp : grp - GG) * 32 + lane;
+      if (is_g) {
+        cs[grp < 4 ? grp : 0] += (v[t][0] + v[t][1]) + (v[t][2] + v[t][3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (ACT == 1) v[t][q] = silu_f(v[t][q]);
+          if (ACT == 2) v[t][q] = dsilu_f(v[t][q]) * w2[t - 2 * GG][q];
+        }
+      }
       uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) tc::split_tf32(v[q], hi[q], lo[q]);
+      for (int q = 0; q < 4; ++q) tc::split_tf32(v[t][q], hi[q], lo[q]);
       const uint32_t off = tc::kmajor_offset(col, quad * 4, WT_K);  // 16 bytes: k = 4 quad .. 4 quad + 3 of row `col`
       *reinterpret_cast<uint4*>((is_g ? a_hi : b_hi) + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>((is_g ? a_lo : b_lo) + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -187,19 +201,25 @@ int wgrad_tc(const float* x, const float* x2, int ldx, const int32_t* x_rows, in
   float* partial = workspace;
   float* cs_partial = colsum != nullptr ? workspace + (size_t)n_chunks * 64 * n_out : nullptr;
   dim3 grid(n_chunks, col_blocks);
-#define CHG_WT(ACT_)                                                                                                    \
-  do {                                                                                                                  \
-    static bool attr = false;                                                                                           \
-    if (!attr) {                                                                                                        \
-      CHG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<ACT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));       \
-      attr = true;                                                                                                      \
-    }                                                                                                                   \
-    wgrad_tc_kernel<ACT_><<<grid, WT_THREADS, WT_SMEM, stream>>>(x, x2, ldx, x_rows, g, ldg, g_rows, m, n_out, n_block, partial, \
-                                                                 cs_partial);                                           \
+#define CHG_WT(ACT_, GG_)                                                                                                   \
+  do {                                                                                                                      \
+    static bool attr = false;                                                                                               \
+    if (!attr) {                                                                                                            \
+      CHG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<ACT_, GG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));      \
+      attr = true;                                                                                                          \
+    }                                                                                                                       \
+    wgrad_tc_kernel<ACT_, GG_><<<grid, WT_THREADS, WT_SMEM, stream>>>(x, x2, ldx, x_rows, g, ldg, g_rows, m, n_out, n_block, \
+                                                                      partial, cs_partial);                                 \
   } while (0)
-  if (x2 != nullptr) CHG_WT(2);
-  else if (x_silu) CHG_WT(1);
-  else CHG_WT(0);
+  if (n_block == 128) {
+    if (x2 != nullptr) CHG_WT(2, 4);
+    else if (x_silu) CHG_WT(1, 4);
+    else CHG_WT(0, 4);
+  } else {
+    if (x2 != nullptr) CHG_WT(2, 2);
+    else if (x_silu) CHG_WT(1, 2);
+    else CHG_WT(0, 2);
+  }
 #undef CHG_WT
   {
     cudaError_t e = cudaGetLastError();
