@@ -23,6 +23,7 @@ Segment structures (all int32, device):
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -200,6 +201,8 @@ def _pack_lib():
         lib = load_library()
         lib.chg_pack_batch_host.restype = ctypes.c_int32
         lib.chg_pack_batch_host.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5
+        lib.chg_pack_batch_wire.restype = ctypes.c_int32
+        lib.chg_pack_batch_wire.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 10
         lib.chg_build_csr_scratch_ints.restype = ctypes.c_int64
         lib.chg_build_csr_scratch_ints.argtypes = [ctypes.c_int32] * 4
         lib.chg_build_csr.restype = ctypes.c_int32
@@ -245,9 +248,15 @@ def _graphs_are_packable(graphs, ag_l, bg_l) -> bool:
 
 
 def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True,
-                compact_bonds: bool = True, native_pack: bool = True, native_csr: bool = True) -> DeviceBatch:
+                compact_bonds: bool = True, native_pack: bool = True, native_csr: bool = True,
+                wire: bool | None = None) -> DeviceBatch:
     """list[CrystalGraph] -> DeviceBatch.  ``native_pack`` / ``native_csr`` = False select the older torch
-    implementations of the host packing / the segment structures (kept as the checkers of the C paths)."""
+    implementations of the host packing / the segment structures (kept as the checkers of the C paths).
+    ``wire`` (default: on; env CHGNET_B200_WIRE=0 turns it off) ships the compact wire format of csrc/batch_wire.cu
+    (derivable bond-graph columns and fp32 images are re-created on the device, packing overlaps the copies) and falls
+    back to the full format for graphs that do not satisfy its (verified) assumptions."""
+    if wire is None:
+        wire = os.environ.get("CHGNET_B200_WIRE", "1") != "0"
     device = torch.device(device)
     B = len(graphs)
     # fast path: chgnet_b200.CrystalGraph caches its sizes and raw data pointers (graph.pack_info), so the per-graph
@@ -448,10 +457,67 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         return (z, owner, center, nbr, d2u, u2d, image.view(Ed, 3), frac.view(N, 3), lattice.view(B, 9), ang_atom, ang_i,
                 ang_di, ang_j, ang_dj, bool(flags[0]), bool(flags[1]), (n_int + n_flt) * 4 if device.type != "cpu" else 0)
 
+    def pack_wire():
+        """chg_pack_batch_wire: compact wire format, two-phase pack + copy overlap, expansion on the device.  Returns
+        None when some graph does not satisfy the format's assumptions (the caller then ships the full format)."""
+        import ctypes
+
+        lib = _pack_lib()
+        n_int_w, n_flt_w = 2 * N + 3 * Ed + Eu + 2 * A, 3 * N + 9 * B
+        cuda = device.type == "cuda"
+        ibuf_h = _staging_buffer(max(n_int_w, 1), torch.int32, cuda)
+        fbuf_h = _staging_buffer(max(n_flt_w, 1), torch.float32, cuda)
+        img_h = _staging_buffer(max(3 * Ed, 1), torch.int8, cuda)
+        if fast is not None:
+            counts, ptrs = np.ascontiguousarray(fast[0]), np.ascontiguousarray(fast[1])
+        else:
+            counts = np.ascontiguousarray(np.array([n_at, n_ed, n_eu, n_an], dtype=np.int64).T)
+            ptrs = np.fromiter((t.data_ptr() for g, ag, bg in zip(graphs, ag_l, bg_l)
+                                for t in (g.atomic_number, g.atom_frac_coord, ag, g.neighbor_image, g.directed2undirected,
+                                          g.undirected2directed, bg, g.lattice)), dtype=np.uint64, count=8 * B)
+        flags = (ctypes.c_int32 * 5)()
+        if cuda:
+            ibuf = torch.empty(n_int_w + 3 * A, dtype=torch.int32, device=device)
+            fbuf = torch.empty(n_flt_w + 3 * Ed, dtype=torch.float32, device=device)
+            img_d = torch.empty(max(3 * Ed, 1), dtype=torch.int8, device=device)
+            with torch.cuda.device(device):
+                rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(),
+                                             img_h.data_ptr(), ibuf.data_ptr(), fbuf.data_ptr(), img_d.data_ptr(), flags,
+                                             torch.cuda.current_stream(device).cuda_stream)
+        else:
+            rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(),
+                                         img_h.data_ptr(), None, None, None, flags, None)
+        if rc != 0:
+            raise RuntimeError(f"chg_pack_batch_wire failed: {lib.chg_last_error().decode()}")
+        if flags[2] >= 0:  # nn.Embedding(94, .) of the reference raises the same (tests/test_encoders.py:25-28)
+            raise IndexError(f"index out of range in self: atomic number {int(ibuf_h[flags[2]])} of atom {int(flags[2])} "
+                             f"is outside [1, {MAX_Z}]")
+        if flags[4] != 0:
+            return None
+        for dt in (torch.int32, torch.float32, torch.int8):
+            _mark_staging_in_flight(dt, cuda, device)
+        if cuda:
+            z, owner, center, nbr, d2u, u2d, ang_di, ang_dj, ang_atom, ang_i, ang_j = torch.split(
+                ibuf, (N, N, Ed, Ed, Ed, Eu, A, A, A, A, A))
+            frac, lattice, image = torch.split(fbuf, (3 * N, 9 * B, 3 * Ed))
+        else:  # CPU "device" (tests): expand on the host what the two device kernels re-create
+            z, owner, center, nbr, d2u, u2d, ang_di, ang_dj = (t.clone() for t in torch.split(
+                ibuf_h[:n_int_w], (N, N, Ed, Ed, Ed, Eu, A, A)))
+            frac, lattice = (t.clone() for t in torch.split(fbuf_h[:n_flt_w], (3 * N, 9 * B)))
+            image = img_h[: 3 * Ed].to(torch.float32)
+            ang_atom, ang_i, ang_j = center[ang_di.long()], d2u[ang_di.long()], d2u[ang_dj.long()]
+        nonlocal n_short_host
+        n_short_host = int(flags[3])
+        return (z, owner, center, nbr, d2u, u2d, image.view(Ed, 3), frac.view(N, 3), lattice.view(B, 9), ang_atom, ang_i,
+                ang_di, ang_j, ang_dj, bool(flags[0]), bool(flags[1]), (n_int_w + n_flt_w) * 4 + 3 * Ed if cuda else 0)
+
     n_short_host = -1  # number of bond-graph bonds, counted by the C packer (no device sync needed later)
     use_native = fast is not None or (native_pack and B > 0 and src_dev.type == "cpu" and _graphs_are_packable(graphs, ag_l, bg_l))
+    packed = pack_wire() if (use_native and wire) else None
+    if packed is None:
+        packed = pack_native() if use_native else pack_legacy()
     (z, owner, center, nbr, d2u, u2d, image, frac_t, lattice, ang_atom, ang_i, ang_di, ang_j, ang_dj, edges_sorted,
-     angles_sorted, h2d) = pack_native() if use_native else pack_legacy()
+     angles_sorted, h2d) = packed
 
     if not edges_sorted and Ed:
         # stable sort by center; remap everything that stores a directed index

@@ -7,7 +7,7 @@
 //   D[j][i] (+)= sum_k G[k][c0 + j] * act(X)[k][i]          A = G^T block (M = 128 columns of G, zero rows when the
 //                                                            block is 64 wide), B = act(X)^T (N = 64), K = rows
 //
-// as 3xTF32 tcgen05.mma.kind::tf32 (M=128, N=64, K=8) with BOTH operands in shared memory: every 64-row stage is
+// as 3xTF32 tcgen05.mma.kind::tf32 (M=128, N=64, K=8) with BOTH operands in shared memory: every 32-row stage is
 // transposed into the no-swizzle K-major operand images (hi and lo parts) by the 8 warps - lane <-> column, four rows
 // per 16-byte store, conflict-free - while the MMAs of the previous stage run (two stages, one mbarrier each).
 // Accumulator: 64 TMEM columns.  Each CTA owns a contiguous range of rows and one 128-column block and writes a
@@ -24,15 +24,16 @@ void wgrad_reduce_launch(const float* partial, const float* cs_partial, int n_ch
 namespace {
 
 constexpr int WT_THREADS = 256;
-constexpr int WT_K = 64;                       // rows per stage
-constexpr int A_IMG = 128 * WT_K * 4;          // 32 KB: G^T block, hi or lo
-constexpr int B_IMG = 64 * WT_K * 4;           // 16 KB: act(X)^T, hi or lo
-constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;   // 96 KB
+constexpr int WT_K = 32;                       // rows per stage
+constexpr int A_IMG = 128 * WT_K * 4;          // 16 KB: G^T block, hi or lo
+constexpr int B_IMG = 64 * WT_K * 4;           // 8 KB: act(X)^T, hi or lo
+constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;   // 48 KB: two stages per CTA, two CTAs per SM
+constexpr int WT_PER = WT_K / 32;              // row-quads per warp and column group (8 warps x 4 rows = 32 rows)
 constexpr int WT_SMEM = 2 * STAGE + 2 * WT_K * 4 * 2 + 1024;
 
 // ACT: 0 x, 1 silu(x), 2 silu'(x) * x2;  GG = 32-column groups of the G block (2: 64 columns, 4: 128 columns)
 template <int ACT, int GG>
-__global__ void __launch_bounds__(WT_THREADS, 1)
+__global__ void __launch_bounds__(WT_THREADS, 2)
 wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int ldx, const int32_t* __restrict__ x_rows,
                 const float* __restrict__ g, int ldg, const int32_t* __restrict__ g_rows, int m, int n, int n_block,
                 float* __restrict__ partial, float* __restrict__ cs_partial) {
@@ -86,13 +87,14 @@ wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int l
     }
     __syncthreads();
     // ---- transpose this stage into the operand images: a work item = (4 consecutive rows, 32 consecutive columns); a warp
-    // owns items warp + 8 t: row-quad warp + 8 (t & 1), column group t >> 1 (G block first, then the two feature groups of X).
-    // ALL loads of the stage are issued before the first use (2 (GG + 2) x 4 independent 4-byte loads per thread in flight).
-    constexpr int ITEMS = 2 * (GG + 2);
-    float v[ITEMS][4], w2[ACT == 2 ? 4 : 1][4];
+    // owns row-quad warp (+ 8 for the second quad of a 64-row stage) of every column group (G block first, then the two
+    // feature groups of X).  ALL loads of the stage are issued before the first use (WT_PER (GG + 2) x 4 independent 4-byte
+    // loads per thread in flight; two CTAs per SM alternate between loading and transposing).
+    constexpr int ITEMS = WT_PER * (GG + 2);
+    float v[ITEMS][4], w2[ACT == 2 ? 2 * WT_PER : 1][4];
 #pragma unroll
     for (int t = 0; t < ITEMS; ++t) {
-      const int quad = warp + 8 * (t & 1), grp = t >> 1;
+      const int quad = warp + 8 * (t % WT_PER), grp = t / WT_PER;
       const bool is_g = grp < GG;
       const int col = (is_g ? grp : grp - GG) * 32 + lane;
 #pragma unroll
@@ -103,13 +105,13 @@ wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int l
           v[t][q] = live ? __ldg(g + (size_t)s_gi[st * WT_K + k] * ldg + col_base + col) : 0.f;
         } else {
           v[t][q] = live ? __ldg(x + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
-          if (ACT == 2) w2[t - 2 * GG][q] = live ? __ldg(x2 + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
+          if (ACT == 2) w2[t - WT_PER * GG][q] = live ? __ldg(x2 + (size_t)s_xi[st * WT_K + k] * ldx + col) : 0.f;
         }
       }
     }
 #pragma unroll
     for (int t = 0; t < ITEMS; ++t) {
-      const int quad = warp + 8 * (t & 1), grp = t >> 1;
+      const int quad = warp + 8 * (t % WT_PER), grp = t / WT_PER;
       const bool is_g = grp < GG;
       const int col = (is_g ? grp : grp - GG) * 32 + lane;
       if (is_g) {
@@ -118,7 +120,7 @@ wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ x2, int l
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (ACT == 1) v[t][q] = silu_f(v[t][q]);
-          if (ACT == 2) v[t][q] = dsilu_f(v[t][q]) * w2[t - 2 * GG][q];
+          if (ACT == 2) v[t][q] = dsilu_f(v[t][q]) * w2[t - WT_PER * GG][q];
         }
       }
       uint32_t hi[4], lo[4];
@@ -196,7 +198,7 @@ int wgrad_tc(const float* x, const float* x2, int ldx, const int32_t* x_rows, in
   if (n_out % n_block != 0) return 1;
   const int col_blocks = n_out / n_block;
   const int steps = (m + WT_K - 1) / WT_K;
-  int n_chunks = sm_count() / col_blocks;
+  int n_chunks = 2 * sm_count() / col_blocks;  // two CTAs per SM
   n_chunks = max(1, min(min(n_chunks, steps), max_chunks));
   float* partial = workspace;
   float* cs_partial = colsum != nullptr ? workspace + (size_t)n_chunks * 64 * n_out : nullptr;

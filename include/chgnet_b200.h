@@ -372,6 +372,22 @@ int chg_bond_graph_count(const int32_t* ang_i, const int32_t* ang_j, int32_t n_a
 int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf,
                         float* fbuf, int32_t* flags_out);
 
+/* The same batch over a COMPACT wire format, packed by persistent worker threads and shipped in two phases whose
+ * copies overlap the packing (csrc/batch_wire.cu): the bond-graph columns that are functions of the two directed-edge
+ * columns (ang_atom = center[ang_di], ang_i = d2u[ang_di], ang_j = d2u[ang_dj]; graph.py:233-277) and the fp32 images
+ * (shipped as int8) are re-created on the device.  Both properties are VERIFIED per angle / image while packing:
+ * flags_out[4] != 0 (1 image not an integer in [-127, 127], 2 columns not derivable, 3 edge index out of range) means
+ * nothing usable was produced and the caller uses chg_pack_batch_host.  counts / ptrs / flags_out[0..3] as above.
+ *   host staging (pinned): ibuf_host [2N + 3Ed + Eu + 2A] = z owner center nbr d2u u2d ang_di ang_dj;
+ *                          fbuf_host [3N + 9B] = frac lattice;  img_host [3Ed] int8
+ *   device:                ibuf_dev [2N + 3Ed + Eu + 5A] = the host layout followed by ang_atom ang_i ang_j;
+ *                          fbuf_dev [3N + 9B + 3Ed] = frac lattice image;  img_dev [3Ed] scratch
+ * All three device pointers NULL: pack only (no CUDA call).  Copies and the two expansion kernels are enqueued on
+ * `stream`; the host buffers may be reused once an event recorded after the call has completed.                 */
+int chg_pack_batch_wire(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf_host,
+                        float* fbuf_host, int8_t* img_host, int32_t* ibuf_dev, float* fbuf_dev, int8_t* img_dev,
+                        int32_t* flags_out, void* stream);
+
 /* ======================= training (reference trainer.py:398-411, 779-869) =======================
  * The reverse pass over activations is the one above (seeded with the loss instead of 1); these
  * entry points add the parameter gradients, the loss terms and the optimizer step for losses on

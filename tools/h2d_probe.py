@@ -52,3 +52,27 @@ for wl in ("c3", "c4"):
         span.append(e0.elapsed_time(e1)); wall.append((t2 - t0) * 1e3); host.append((t1 - t0) * 1e3)
     span.sort(); wall.sort(); host.sort()
     print(f"{wl}: build_batch wall {wall[5]:.3f} ms, host part {host[5]:.3f} ms, first-to-last GPU event span {span[5]:.3f} ms, h2d bytes {b.h2d_bytes if hasattr(b, 'h2d_bytes') else '?'}")
+
+# write-combined vs default pinned memory (cudaHostAlloc through cuda-python), 19 MiB and 35 MiB
+try:
+    from cuda import cudart
+    for mb in (19, 35):
+        nbytes = mb * 2**20
+        d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        for label, flag in (("default", cudart.cudaHostAllocDefault), ("write-combined", cudart.cudaHostAllocWriteCombined)):
+            err, hp = cudart.cudaHostAlloc(nbytes, flag)
+            assert int(err) == 0, err
+            for _ in range(3):
+                cudart.cudaMemcpyAsync(d.data_ptr(), hp, nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, 0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                cudart.cudaMemcpyAsync(d.data_ptr(), hp, nbytes, cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, 0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"H2D cudaHostAlloc({label}) {mb} MiB: {ms:.3f} ms ({nbytes / ms / 1e6:.1f} GB/s)")
+            cudart.cudaFreeHost(hp)
+except Exception as exc:  # noqa: BLE001
+    print("cuda-python probe unavailable:", repr(exc))
