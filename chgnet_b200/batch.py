@@ -100,6 +100,39 @@ def _staging_buffer(n: int, dtype, pin: bool) -> Tensor:
     return slot[0][:n]
 
 
+_DEFAULT_STAGING = "pinned"  # "wc": write-combined staging for the wire packer (env CHGNET_B200_STAGING overrides)
+_WC_STAGING: dict = {}  # name -> [pointer, capacity in bytes, event of the last copy out of it]
+
+
+def _wc_staging(name: str, n_bytes: int) -> int:
+    """Grow-only WRITE-COMBINED pinned staging buffer (chg_host_alloc), returned as a raw pointer: the wire packer's
+    threads only write it and the copy engine reads it at full PCIe rate (ordinary pinned memory written by many
+    cores copies several times slower: its lines sit dirty in those cores' caches).  Waits for the previous batch's
+    copy out of the buffer before handing it out again."""
+    slot = _WC_STAGING.get(name)
+    if slot is not None and slot[2] is not None:
+        slot[2].synchronize()
+        slot[2] = None
+    if slot is None or slot[1] < n_bytes:
+        lib = _pack_lib()
+        cap = max(n_bytes, int(1.5 * slot[1]) if slot is not None else n_bytes, 4096)
+        ptr = ctypes.c_void_p()
+        if lib.chg_host_alloc(cap, 1, ctypes.byref(ptr)) != 0:
+            raise RuntimeError(f"chg_host_alloc failed: {lib.chg_last_error().decode()}")
+        if slot is not None:
+            lib.chg_host_free(ctypes.c_void_p(slot[0]))
+        slot = [ptr.value, cap, None]
+        _WC_STAGING[name] = slot
+    return slot[0]
+
+
+def _mark_wc_in_flight(device: torch.device) -> None:
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    for slot in _WC_STAGING.values():
+        slot[2] = ev
+
+
 def _mark_staging_in_flight(dtype, pin: bool, device: torch.device) -> None:
     if device.type == "cuda":
         ev = torch.cuda.Event()
@@ -203,6 +236,10 @@ def _pack_lib():
         lib.chg_pack_batch_host.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5
         lib.chg_pack_batch_wire.restype = ctypes.c_int32
         lib.chg_pack_batch_wire.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 10
+        lib.chg_host_alloc.restype = ctypes.c_int32
+        lib.chg_host_alloc.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]
+        lib.chg_host_free.restype = ctypes.c_int32
+        lib.chg_host_free.argtypes = [ctypes.c_void_p]
         lib.chg_build_csr_scratch_ints.restype = ctypes.c_int64
         lib.chg_build_csr_scratch_ints.argtypes = [ctypes.c_int32] * 4
         lib.chg_build_csr.restype = ctypes.c_int32
@@ -249,20 +286,24 @@ def _graphs_are_packable(graphs, ag_l, bg_l) -> bool:
 
 def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: bool = True,
                 compact_bonds: bool = True, native_pack: bool = True, native_csr: bool = True,
-                wire: bool | None = None) -> DeviceBatch:
+                wire: bool | None = None, packed: tuple | None = None) -> DeviceBatch:
     """list[CrystalGraph] -> DeviceBatch.  ``native_pack`` / ``native_csr`` = False select the older torch
     implementations of the host packing / the segment structures (kept as the checkers of the C paths).
     ``wire`` (default: on; env CHGNET_B200_WIRE=0 turns it off) ships the compact wire format of csrc/batch_wire.cu
     (derivable bond-graph columns and fp32 images are re-created on the device, packing overlaps the copies) and falls
-    back to the full format for graphs that do not satisfy its (verified) assumptions."""
+    back to the full format for graphs that do not satisfy its (verified) assumptions.
+    ``packed = (counts int64 [B][4], ptrs uint64 [B][8])`` (``graphs`` = None) batches graphs that exist only as host
+    arrays - the rows ``CrystalGraph.pack_info`` produces; used for the handles of ``chg_graph_build_many``."""
     if wire is None:
         wire = os.environ.get("CHGNET_B200_WIRE", "1") != "0"
     device = torch.device(device)
-    B = len(graphs)
+    B = len(graphs) if packed is None else int(packed[0].shape[0])
     # fast path: chgnet_b200.CrystalGraph caches its sizes and raw data pointers (graph.pack_info), so the per-graph
     # Python work is one attribute call; any other graph-like object goes through the generic reads below
     fast = None
-    if native_pack and B > 0:
+    if packed is not None:
+        fast = (np.ascontiguousarray(packed[0], dtype=np.int64), np.ascontiguousarray(packed[1], dtype=np.uint64))
+    elif native_pack and B > 0:
         infos = [g.pack_info() if hasattr(g, "pack_info") else False for g in graphs]
         if all(i is not False for i in infos):
             fast = (np.stack([i[0] for i in infos]), np.stack([i[1] for i in infos]))
@@ -271,7 +312,7 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         cnt = fast[0]
         n_at, n_ed, n_eu, n_an = (cnt[:, k].tolist() for k in range(4))
         bad = np.nonzero((cnt[:, 1] != 2 * cnt[:, 2]))[0]
-        if len(bad) or any(g.directed2undirected.shape[0] != e for g, e in zip(graphs, n_ed)):
+        if len(bad) or (packed is None and any(g.directed2undirected.shape[0] != e for g, e in zip(graphs, n_ed))):
             raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
     else:
         # per-graph Python work is kept to attribute reads (no reshape / detach calls per tensor)
@@ -292,7 +333,7 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
                 raise ValueError("CrystalGraph invariant violated: n_directed != 2 * n_undirected")
     N, Ed, Eu, A = sum(n_at), sum(n_ed), sum(n_eu), sum(n_an)
 
-    src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
+    src_dev = graphs[0].atomic_number.device if (B and packed is None) else torch.device("cpu")
 
     def pack_legacy():
         src_dev = graphs[0].atomic_number.device if B else torch.device("cpu")
@@ -465,9 +506,15 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
         lib = _pack_lib()
         n_int_w, n_flt_w = 2 * N + 3 * Ed + Eu + 2 * A, 3 * N + 9 * B
         cuda = device.type == "cuda"
-        ibuf_h = _staging_buffer(max(n_int_w, 1), torch.int32, cuda)
-        fbuf_h = _staging_buffer(max(n_flt_w, 1), torch.float32, cuda)
-        img_h = _staging_buffer(max(3 * Ed, 1), torch.int8, cuda)
+        wc = cuda and os.environ.get("CHGNET_B200_STAGING", _DEFAULT_STAGING) == "wc"
+        if wc:  # write-combined pinned staging: raw pointers, never read on the CPU
+            ip, fp, gp = (_wc_staging("int", 4 * max(n_int_w, 1)), _wc_staging("flt", 4 * max(n_flt_w, 1)),
+                          _wc_staging("img", max(3 * Ed, 1)))
+        else:
+            ibuf_h = _staging_buffer(max(n_int_w, 1), torch.int32, cuda)
+            fbuf_h = _staging_buffer(max(n_flt_w, 1), torch.float32, cuda)
+            img_h = _staging_buffer(max(3 * Ed, 1), torch.int8, cuda)
+            ip, fp, gp = ibuf_h.data_ptr(), fbuf_h.data_ptr(), img_h.data_ptr()
         if fast is not None:
             counts, ptrs = np.ascontiguousarray(fast[0]), np.ascontiguousarray(fast[1])
         else:
@@ -481,21 +528,24 @@ def build_batch(graphs: Sequence, device: torch.device | str, *, with_reverse: b
             fbuf = torch.empty(n_flt_w + 3 * Ed, dtype=torch.float32, device=device)
             img_d = torch.empty(max(3 * Ed, 1), dtype=torch.int8, device=device)
             with torch.cuda.device(device):
-                rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(),
-                                             img_h.data_ptr(), ibuf.data_ptr(), fbuf.data_ptr(), img_d.data_ptr(), flags,
+                rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ip, fp, gp, ibuf.data_ptr(),
+                                             fbuf.data_ptr(), img_d.data_ptr(), flags,
                                              torch.cuda.current_stream(device).cuda_stream)
+            if wc:
+                _mark_wc_in_flight(device)
+            else:
+                for dt in (torch.int32, torch.float32, torch.int8):
+                    _mark_staging_in_flight(dt, True, device)
         else:
-            rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ibuf_h.data_ptr(), fbuf_h.data_ptr(),
-                                         img_h.data_ptr(), None, None, None, flags, None)
+            rc = lib.chg_pack_batch_wire(B, counts.ctypes.data, ptrs.ctypes.data, ip, fp, gp, None, None, None, flags, None)
         if rc != 0:
             raise RuntimeError(f"chg_pack_batch_wire failed: {lib.chg_last_error().decode()}")
         if flags[2] >= 0:  # nn.Embedding(94, .) of the reference raises the same (tests/test_encoders.py:25-28)
-            raise IndexError(f"index out of range in self: atomic number {int(ibuf_h[flags[2]])} of atom {int(flags[2])} "
+            bad = ctypes.c_int32.from_address(ip + 4 * int(flags[2])).value
+            raise IndexError(f"index out of range in self: atomic number {bad} of atom {int(flags[2])} "
                              f"is outside [1, {MAX_Z}]")
         if flags[4] != 0:
             return None
-        for dt in (torch.int32, torch.float32, torch.int8):
-            _mark_staging_in_flight(dt, cuda, device)
         if cuda:
             z, owner, center, nbr, d2u, u2d, ang_di, ang_dj, ang_atom, ang_i, ang_j = torch.split(
                 ibuf, (N, N, Ed, Ed, Ed, Eu, A, A, A, A, A))

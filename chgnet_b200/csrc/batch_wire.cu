@@ -30,6 +30,7 @@
 #include <unistd.h>
 
 #include "common.cuh"
+#include "worker_pool.h"
 
 #define CHG_LAUNCH_CHECK(what)                                                      \
   do {                                                                              \
@@ -43,77 +44,6 @@
 
 namespace chg {
 namespace {
-
-// ---- persistent workers ------------------------------------------------------------------------------------------
-class WorkerPool {
- public:
-  explicit WorkerPool(int n_workers) : pid_(getpid()) {
-    for (int i = 0; i < n_workers; ++i) std::thread(&WorkerPool::loop, this, i + 1).detach();
-    n_workers_ = n_workers;
-  }
-  pid_t pid() const { return pid_; }
-  int size() const { return n_workers_ + 1; }
-  // fn(k) for k in [0, n): k = 0 on the calling thread, the rest on the workers; returns when all are done
-  void run(int n, const std::function<void(int)>& fn) {
-    n = std::max(1, std::min(n, size()));
-    if (n > 1) {
-      std::lock_guard<std::mutex> lk(m_);
-      job_ = &fn;
-      job_n_ = n;
-      pending_.store(n - 1, std::memory_order_relaxed);
-      ++generation_;
-    }
-    if (n > 1) start_.notify_all();
-    fn(0);
-    if (n > 1) {
-      std::unique_lock<std::mutex> lk(m_);
-      done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
-      job_ = nullptr;
-    }
-  }
-
- private:
-  void loop(int index) {
-    uint64_t seen = 0;
-    for (;;) {
-      const std::function<void(int)>* job = nullptr;
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        start_.wait(lk, [&] { return generation_ != seen; });
-        seen = generation_;
-        if (index < job_n_) job = job_;
-      }
-      if (job != nullptr) {
-        (*job)(index);
-        if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-          std::lock_guard<std::mutex> lk(m_);
-          done_.notify_one();
-        }
-      }
-    }
-  }
-  std::mutex m_;
-  std::condition_variable start_, done_;
-  const std::function<void(int)>* job_ = nullptr;
-  int job_n_ = 0, n_workers_ = 0;
-  uint64_t generation_ = 0;
-  std::atomic<int> pending_{0};
-  pid_t pid_;
-};
-
-// never destroyed (detached workers may be parked in it at exit); re-created in a forked child, whose threads are gone
-WorkerPool& pool() {
-  static std::mutex m;
-  static WorkerPool* p = nullptr;
-  std::lock_guard<std::mutex> lk(m);
-  if (p == nullptr || p->pid() != getpid()) {
-    const unsigned hc = std::thread::hardware_concurrency();
-    int n = (int)std::min<unsigned>(hc == 0 ? 4 : hc, 16);
-    if (const char* e = std::getenv("CHG_PACK_THREADS")) n = std::max(1, std::min(std::atoi(e), 64));
-    p = new WorkerPool(n - 1);
-  }
-  return *p;
-}
 
 // ---- device side: re-create what was not shipped -------------------------------------------------------------------
 __global__ void expand_image_kernel(const int8_t* __restrict__ img8, float* __restrict__ image, int64_t n) {
@@ -137,6 +67,21 @@ __global__ void derive_angle_columns_kernel(const int32_t* __restrict__ center, 
 }  // namespace chg
 
 using namespace chg;
+
+// Pinned staging memory for the packers.  write_combined != 0: cudaHostAllocWriteCombined - the packer's worker threads
+// only WRITE it (streaming stores, no cache lines left dirty in many cores' caches), and the copy engine reads it at
+// full PCIe rate: on the B200 hosts of this pool a 19 MiB buffer freshly written by 8 threads copies at 54 GB/s from
+// write-combined memory and at 8 GB/s from ordinary pinned memory (profiles/SUMMARY_r2.md).  Never read it on the CPU.
+extern "C" int chg_host_alloc(int64_t bytes, int32_t write_combined, void** out) {
+  CHG_CHECK_ARG(bytes > 0 && out != nullptr, "bad size or null pointer");
+  CHG_CUDA(cudaHostAlloc(out, (size_t)bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return CHG_OK;
+}
+
+extern "C" int chg_host_free(void* p) {
+  if (p != nullptr) CHG_CUDA(cudaFreeHost(p));
+  return CHG_OK;
+}
 
 // counts [B][4] = atoms, directed edges, bonds, angles per graph; ptrs [B][8] = z (int32), frac (fp32 [n][3]),
 // atom_graph (int32 [ed][2]), image (fp32 [ed][3]), d2u, u2d (int32), bond_graph (int32 [an][5]), lattice (fp32 [9]).
@@ -223,39 +168,44 @@ extern "C" int chg_pack_batch_wire(int32_t n_graphs, const int64_t* counts, cons
             if ((zs[i] < 1 || zs[i] > CHG_MAX_Z) && res.bad_z < 0) res.bad_z = a_off + i;
           }
         }
+        // one output array per loop: the staging buffer may be write-combined memory, which only combines stores into full
+        // lines while a core writes ONE stream at a time (the sources stay in L1 / L2 between the loops)
         const float* im = static_cast<const float*>(p[3]);
-        for (int64_t e = lo(ed); e < hi(ed); ++e) {
+        const int64_t e0 = lo(ed), e1 = hi(ed);
+        for (int64_t e = e0; e < e1; ++e) {
           center[e_off + e] = ag[2 * e] + (int32_t)a_off;
-          nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
-          d2u[e_off + e] = du[e] + (int32_t)u_off;
           if (e > 0 && ag[2 * e] < ag[2 * e - 2]) res.edges_sorted = false;
-          for (int k = 0; k < 3; ++k) {
-            const float v = im[3 * e + k];
-            const int8_t q = (v >= -127.f && v <= 127.f) ? (int8_t)v : (int8_t)0;
-            if ((float)q != v) res.reject = 1;
-            img_host[(e_off + e) * 3 + k] = q;
-          }
+        }
+        for (int64_t e = e0; e < e1; ++e) nbr[e_off + e] = ag[2 * e + 1] + (int32_t)a_off;
+        for (int64_t e = e0; e < e1; ++e) d2u[e_off + e] = du[e] + (int32_t)u_off;
+        for (int64_t i = 3 * e0; i < 3 * e1; ++i) {
+          const float v = im[i];
+          const int8_t q = (v >= -127.f && v <= 127.f) ? (int8_t)v : (int8_t)0;
+          if ((float)q != v) res.reject = 1;
+          img_host[e_off * 3 + i] = q;
         }
         const int32_t* ud = static_cast<const int32_t*>(p[5]);
         for (int64_t u = lo(eu); u < hi(eu); ++u) u2d[u_off + u] = ud[u] + (int32_t)e_off;
         if (part == 0) std::memcpy(lattice + (size_t)g * 9, p[7], 36);
       } else {
         const int32_t* bg = static_cast<const int32_t*>(p[6]);
-        for (int64_t a = lo(an); a < hi(an); ++a) {
+        const int64_t a0 = lo(an), a1 = hi(an);
+        for (int64_t a = a0; a < a1; ++a) {
           const int64_t di = bg[5 * a + 2], dj = bg[5 * a + 4];
           if (di < 0 || di >= ed || dj < 0 || dj >= ed) {
             res.reject = 3;
+            ang_di[g_off + a] = 0;
             continue;
           }
           if (bg[5 * a] != ag[2 * di] || bg[5 * a + 1] != du[di] || bg[5 * a + 3] != du[dj]) res.reject = 2;
           ang_di[g_off + a] = (int32_t)(di + e_off);
-          ang_dj[g_off + a] = (int32_t)(dj + e_off);
           if (a > 0 && bg[5 * a + 1] < bg[5 * a - 4]) res.angles_sorted = false;
           for (int which_bond = 1; which_bond <= 3; which_bond += 2) {
             const int64_t ul = bg[5 * a + which_bond];
             if (ul >= 0 && ul < eu && __atomic_exchange_n(&bg_flag[u_off + ul], (uint8_t)1, __ATOMIC_RELAXED) == 0) ++res.n_short;
           }
         }
+        for (int64_t a = a0; a < a1; ++a) ang_dj[g_off + a] = bg[5 * a + 4] + (int32_t)e_off;
       }
     }
   };

@@ -15,6 +15,7 @@
 // Pure host code (no device work): a uniform grid over the replicated images makes the search
 // O(N * neighbours), single-threaded (0.5 ms for 50 atoms, ~100 ms for 10 000).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <chrono>
@@ -26,12 +27,14 @@
 #include <vector>
 
 #include "common.cuh"
+#include "worker_pool.h"
 
 struct chg_graph {
   std::vector<int32_t> atom_graph;  // [Ed][2]
   std::vector<float> image;         // [Ed][3]
   std::vector<int32_t> d2u, u2d;    // [Ed], [Eu]
   std::vector<int32_t> bond_graph;  // [A][5]
+  int32_t n_isolated = 0;           // atoms without any neighbour inside r_atom
 };
 
 namespace chg {
@@ -187,6 +190,7 @@ extern "C" int chg_graph_build(const double* frac, const double* lattice, int32_
       dist.push_back(h.d);
     }
     first_edge[c + 1] = (int64_t)keys.size();
+    if (first_edge[c + 1] == first_edge[c]) ++G->n_isolated;
   }
   lap("search");
   const size_t n_dir = keys.size();
@@ -294,6 +298,64 @@ extern "C" int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* 
 }
 
 extern "C" void chg_graph_free(chg_graph* g) { delete g; }
+
+// ---- many structures at once (the converter loop of the reference's predict_structure, model.py:578-583) ----------
+// chg_graph_build for n structures on the persistent worker threads (one structure per task, dynamic assignment).
+// out[i] is always a handle to free (possibly of an empty graph); the return code is the first failure's, and its
+// message is re-created on the calling thread.
+extern "C" int chg_graph_build_many(int32_t n, const double* const* frac, const double* const* lattice, const int32_t* n_atoms,
+                                    double r_atom, double r_bond, chg_graph** out) {
+  CHG_CHECK_ARG(n >= 0, "negative size");
+  CHG_CHECK_ARG(n == 0 || (frac != nullptr && lattice != nullptr && n_atoms != nullptr && out != nullptr), "null pointer");
+  for (int i = 0; i < n; ++i) out[i] = nullptr;
+  std::atomic<int> next{0};
+  std::atomic<int> first_bad{INT32_MAX};
+  WorkerPool& wp = pool();
+  wp.run(std::min(wp.size(), std::max(1, n)), [&](int) {
+    for (;;) {
+      const int i = next.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n) break;
+      if (chg_graph_build(frac[i], lattice[i], n_atoms[i], r_atom, r_bond, &out[i]) != CHG_OK) {
+        int cur = first_bad.load();
+        while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {
+        }
+      }
+    }
+  });
+  const int bad = first_bad.load();
+  if (bad == INT32_MAX) return CHG_OK;
+  chg_graph* again = nullptr;  // the error text is per thread: repeat the failing build here
+  const int rc = chg_graph_build(frac[bad], lattice[bad], n_atoms[bad], r_atom, r_bond, &again);
+  delete again;
+  return rc != CHG_OK ? rc : CHG_ERR_ARG;
+}
+
+// counts [n][3] = directed edges, bonds, angles; ptrs [n][5] = atom_graph, image, d2u, u2d, bond_graph (host pointers
+// into the handles, valid until they are freed: what chg_pack_batch_wire / chg_pack_batch_host take); n_isolated [n].
+extern "C" int chg_graph_views(int32_t n, chg_graph* const* graphs, int64_t* counts, uint64_t* ptrs, int32_t* n_isolated) {
+  CHG_CHECK_ARG(n >= 0 && (n == 0 || (graphs != nullptr && counts != nullptr && ptrs != nullptr)), "bad size or null pointer");
+  for (int i = 0; i < n; ++i) {
+    const chg_graph* g = graphs[i];
+    CHG_CHECK_ARG(g != nullptr, "null graph");
+    counts[3 * i] = (int64_t)g->d2u.size();
+    counts[3 * i + 1] = (int64_t)g->u2d.size();
+    counts[3 * i + 2] = (int64_t)g->bond_graph.size() / 5;
+    ptrs[5 * i] = (uint64_t)(uintptr_t)g->atom_graph.data();
+    ptrs[5 * i + 1] = (uint64_t)(uintptr_t)g->image.data();
+    ptrs[5 * i + 2] = (uint64_t)(uintptr_t)g->d2u.data();
+    ptrs[5 * i + 3] = (uint64_t)(uintptr_t)g->u2d.data();
+    ptrs[5 * i + 4] = (uint64_t)(uintptr_t)g->bond_graph.data();
+    if (n_isolated != nullptr) n_isolated[i] = g->n_isolated;
+  }
+  return CHG_OK;
+}
+
+extern "C" void chg_graph_free_many(int32_t n, chg_graph** graphs) {
+  for (int i = 0; i < n; ++i) {
+    delete graphs[i];
+    graphs[i] = nullptr;
+  }
+}
 
 // =====================================================================================
 // Host batch packer: list of CrystalGraphs -> the concatenated, offset-adjusted SoA of

@@ -236,6 +236,21 @@ class GraphConverter:
                 print(msg, file=sys.stderr)
         return g
 
+    def convert_many(self, structures, n_threads: int | None = None) -> list[CrystalGraph]:
+        """Graphs of many structures, built concurrently: the native builder (csrc/graph_builder.cu, entered through
+        ctypes, which releases the GIL) runs on a thread pool, one structure per task.  Same graphs, same order and the
+        same isolated-atom handling as calling the converter in a loop (what the reference's ``predict_structure`` does,
+        model.py:578-583)."""
+        structures = list(structures)
+        if n_threads is None:
+            n_threads = min(16, os.cpu_count() or 1)
+        if n_threads <= 1 or len(structures) < 4:
+            return [self(s) for s in structures]
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(n_threads, len(structures))) as ex:
+            return list(ex.map(self, structures))
+
     def __repr__(self) -> str:
         return (f"GraphConverter(atom_graph_cutoff={self.atom_graph_cutoff}, "
                 f"bond_graph_cutoff={self.bond_graph_cutoff})")
@@ -498,10 +513,118 @@ class CHGNet(nn.Module):
                 and os.environ.get("CHGNET_B200_GRAPH", "device") == "device"):
             return self._predict_structure_device(structure, task, return_site_energies, return_atom_feas, return_crystal_feas)
         structures = [structure] if single else structure
-        graphs = [self.graph_converter(s) for s in structures]
+        if (not single and isinstance(self.graph_converter, GraphConverter)
+                and os.environ.get("CHGNET_B200_GRAPH", "device") != "python"):
+            return self._predict_structures_native(list(structures), task, return_site_energies, return_atom_feas,
+                                                   return_crystal_feas, batch_size)
+        convert_many = getattr(self.graph_converter, "convert_many", None)
+        graphs = convert_many(structures) if convert_many is not None else [self.graph_converter(s) for s in structures]
         return self.predict_graph(graphs[0] if single else graphs, task=task,
                                   return_site_energies=return_site_energies, return_atom_feas=return_atom_feas,
                                   return_crystal_feas=return_crystal_feas, batch_size=batch_size)
+
+    @staticmethod
+    def _structure_arrays(structure):
+        if isinstance(structure, tuple):
+            z, frac, lat = structure
+        else:
+            z = getattr(structure, "atomic_numbers", None)
+            if z is None:
+                z = [site.specie.Z for site in structure]
+            frac = structure.frac_coords
+            lat = structure.lattice.matrix if hasattr(structure.lattice, "matrix") else structure.lattice
+        return (np.ascontiguousarray(z, dtype=np.int32).reshape(-1), np.ascontiguousarray(frac, dtype=np.float64).reshape(-1, 3),
+                np.ascontiguousarray(lat, dtype=np.float64).reshape(3, 3))
+
+    def structures_to_batch(self, structures, *, with_reverse: bool = True):
+        """``list[structure] -> DeviceBatch`` without per-structure Python objects: the graphs are built concurrently by
+        the library's worker threads (``chg_graph_build_many``) and packed straight out of the builder's memory
+        (``chg_graph_views`` -> ``chg_pack_batch_wire``).  Identical to converting every structure with the
+        ``GraphConverter`` and batching the CrystalGraphs (tests/test_graph_builder.py)."""
+        import ctypes
+
+        from chgnet_b200._lib import ChgnetB200Error, load_library
+        from chgnet_b200.batch import build_batch
+
+        lib = load_library()
+        if not getattr(lib, "_graph_many_bound", False):
+            vp = ctypes.c_void_p
+            lib.chg_graph_build_many.restype = ctypes.c_int32
+            lib.chg_graph_build_many.argtypes = [ctypes.c_int32, vp, vp, vp, ctypes.c_double, ctypes.c_double, vp]
+            lib.chg_graph_views.restype = ctypes.c_int32
+            lib.chg_graph_views.argtypes = [ctypes.c_int32, vp, vp, vp, vp]
+            lib.chg_graph_free_many.restype = None
+            lib.chg_graph_free_many.argtypes = [ctypes.c_int32, vp]
+            lib._graph_many_bound = True
+        gc = self.graph_converter
+        arrays = [self._structure_arrays(s) for s in structures]
+        n = len(arrays)
+        n_at = np.array([len(a[0]) for a in arrays], dtype=np.int32)
+        frac_p = np.array([a[1].ctypes.data for a in arrays], dtype=np.uint64)
+        lat_p = np.array([a[2].ctypes.data for a in arrays], dtype=np.uint64)
+        handles = np.zeros(max(n, 1), dtype=np.uint64)
+        rc = lib.chg_graph_build_many(n, frac_p.ctypes.data, lat_p.ctypes.data, n_at.ctypes.data, float(gc.atom_graph_cutoff),
+                                      float(gc.bond_graph_cutoff), handles.ctypes.data)
+        try:
+            if rc != 0:
+                msg = lib.chg_last_error().decode()
+                raise (ValueError if "not complete" in msg else ChgnetB200Error)(msg)
+            counts3, ptrs5 = np.empty((n, 3), dtype=np.int64), np.empty((n, 5), dtype=np.uint64)
+            n_iso = np.zeros(max(n, 1), dtype=np.int32)
+            lib.chg_graph_views(n, handles.ctypes.data, counts3.ctypes.data, ptrs5.ctypes.data, n_iso.ctypes.data)
+            if gc.on_isolated_atoms != "ignore" and n_iso.any():
+                for i in np.nonzero(n_iso)[0]:
+                    n_isolated_atoms, atom_graph_cutoff, graph_id = int(n_iso[i]), gc.atom_graph_cutoff, None
+                    msg = (f"Structure {graph_id=} has {n_isolated_atoms} isolated atom(s) with "
+                           f"{atom_graph_cutoff=}. CHGNet calculation will likely go wrong")
+                    if gc.on_isolated_atoms == "error":
+                        raise ValueError(msg)
+                    import sys
+
+                    print(msg, file=sys.stderr)
+            # fp32 / int32 copies of the per-atom and per-structure inputs, one array each, addressed by offsets
+            z_all = np.concatenate([a[0] for a in arrays]) if n else np.zeros(0, np.int32)
+            frac_all = np.concatenate([a[1] for a in arrays]).astype(np.float32) if n else np.zeros((0, 3), np.float32)
+            lat_all = np.stack([a[2] for a in arrays]).astype(np.float32).reshape(n, 9) if n else np.zeros((0, 9), np.float32)
+            a_off = np.concatenate([[0], np.cumsum(n_at[:-1], dtype=np.int64)]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+            counts = np.empty((n, 4), dtype=np.int64)
+            counts[:, 0], counts[:, 1:] = n_at, counts3
+            ptrs = np.empty((n, 8), dtype=np.uint64)
+            ptrs[:, 0] = np.uint64(z_all.ctypes.data) + a_off * np.uint64(4)
+            ptrs[:, 1] = np.uint64(frac_all.ctypes.data) + a_off * np.uint64(12)
+            for k in range(5):
+                ptrs[:, 2 + k] = ptrs5[:, k]
+            ptrs[:, 7] = np.uint64(lat_all.ctypes.data) + np.arange(n, dtype=np.uint64) * np.uint64(36)
+            # both packers copy into their staging buffers before they return: the handles can be freed right after
+            return build_batch(None, self.device, with_reverse=with_reverse,
+                               compact_bonds=not self._arch.get("mlp_out_bias", False), packed=(counts, ptrs))
+        finally:
+            lib.chg_graph_free_many(n, handles.ctypes.data)
+
+    def _predict_structures_native(self, structures, task, return_site_energies, return_atom_feas, return_crystal_feas,
+                                   batch_size):
+        """``predict_structure`` of a list: chunks of ``batch_size`` structures through ``structures_to_batch``; same
+        graphs, chunking and outputs as converting every structure and calling ``predict_graph`` (reference
+        model.py:544-591)."""
+        valid_tasks = get_args(PredTask)
+        if task not in valid_tasks:
+            raise ValueError(f"Invalid {task=}. Must be one of {valid_tasks}.")
+        self.eval()
+        need_grad = "f" in task or "s" in task
+        predictions: list[dict[str, np.ndarray]] = [{} for _ in structures]
+        for start in range(0, len(structures), batch_size):
+            batch = self.structures_to_batch(structures[start : start + batch_size], with_reverse=need_grad)
+            n = batch.n_graphs
+            raw = self._run(None, task, return_site_energies, return_atom_feas, return_crystal_feas, batch=batch)
+            bounds = np.cumsum(batch.atoms_per_graph)[:-1]
+            for key in ("e", "f", "s", "m", "site_energies", "atom_fea", "crystal_fea"):
+                if key not in raw:
+                    continue
+                host = raw[key].cpu().numpy()
+                parts = np.split(host, bounds) if key in self._PER_ATOM else [host[i] for i in range(n)]
+                for i, part in enumerate(parts):
+                    predictions[start + i][key] = np.asarray(part)
+        return predictions
 
     def _predict_structure_device(self, structure, task, return_site_energies, return_atom_feas, return_crystal_feas):
         """One structure, graph built ON THE DEVICE (chgnet_b200.graph_device: the same edges / angles as the host

@@ -305,6 +305,16 @@ int chg_graph_export(const chg_graph* g, int32_t* atom_graph, float* image, int3
                      int32_t* bond_graph);
 void chg_graph_free(chg_graph* g);
 
+/* Many structures at once (the converter loop of the reference's predict_structure, model.py:578-583): chg_graph_build
+ * for n structures on the library's persistent worker threads; out[i] is always a handle to free; returns the first
+ * failure's code (message in chg_last_error).  chg_graph_views: counts [n][3] = directed edges, bonds, angles; ptrs
+ * [n][5] = host pointers to atom_graph, image, d2u, u2d, bond_graph inside the handles (valid until freed; exactly what
+ * chg_pack_batch_wire / chg_pack_batch_host take); n_isolated [n] (or NULL) = atoms without a neighbour.         */
+int chg_graph_build_many(int32_t n, const double* const* frac, const double* const* lattice, const int32_t* n_atoms,
+                         double r_atom, double r_bond, chg_graph** out);
+int chg_graph_views(int32_t n, chg_graph* const* graphs, int64_t* counts, uint64_t* ptrs, int32_t* n_isolated);
+void chg_graph_free_many(int32_t n, chg_graph** graphs);
+
 /* ---- device graph builder (one structure): fractional coordinates -> the edge / angle arrays of chg_batch, on the device
  * (csrc/graph_device.cu).  Replaces the host-side neighbour list + create_graph.c / cygraph.pyx + line graph
  * (converter.py:102-190, graph.py:132-328, fast_converter_libraries/create_graph.c:100-219) that the reference
@@ -371,6 +381,11 @@ int chg_bond_graph_count(const int32_t* ang_i, const int32_t* ang_j, int32_t n_a
  * flags_out[3] = number of distinct bonds that occur in angles (n_short of chg_build_csr: no device sync). */
 int chg_pack_batch_host(int32_t n_graphs, const int64_t* counts, const void* const* ptrs, int32_t* ibuf,
                         float* fbuf, int32_t* flags_out);
+
+/* Pinned staging memory for the two packers (cudaHostAlloc; write_combined != 0: write-combined - written by the
+ * packer's threads with streaming stores and read only by the copy engine; never read it on the CPU). */
+int chg_host_alloc(int64_t bytes, int32_t write_combined, void** out);
+int chg_host_free(void* p);
 
 /* The same batch over a COMPACT wire format, packed by persistent worker threads and shipped in two phases whose
  * copies overlap the packing (csrc/batch_wire.cu): the bond-graph columns that are functions of the two directed-edge

@@ -38,7 +38,8 @@ def test_binding_table_matches_header(lib):
                                    "chg_wgrad_workspace_floats", "chg_gated_fused_workspace_floats", "chg_packed_floats", "chg_pack_weights_host",
                                    "chg_forward_plan", "chg_forward",
                                    "chg_graph_build", "chg_graph_sizes", "chg_graph_export", "chg_graph_free",
-                                   "chg_pack_batch_host", "chg_pack_batch_wire", "chg_build_csr", "chg_build_csr_scratch_ints", "chg_bond_graph_count",
+                                   "chg_graph_build_many", "chg_graph_views", "chg_graph_free_many",
+                                   "chg_pack_batch_host", "chg_pack_batch_wire", "chg_host_alloc", "chg_host_free", "chg_build_csr", "chg_build_csr_scratch_ints", "chg_bond_graph_count",
                                    "chg_graph_build_device", "chg_graph_device_scratch_bytes", "chg_md_kick_drift", "chg_md_kick",
                                    "chg_fire_step"}
     assert declared == set(_lib.SIGNATURES)

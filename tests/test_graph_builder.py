@@ -55,3 +55,57 @@ def test_bad_input_is_reported():
 
     with pytest.raises(ChgnetB200Error):
         graphgen.native_graph_arrays(np.zeros((1, 3)), np.zeros((3, 3)), 6.0, 3.0)  # singular lattice
+
+
+def _random_structures(n, seed, lo=5, hi=40):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        k = int(rng.integers(lo, hi + 1))
+        a = (k / 0.1) ** (1 / 3)
+        out.append((rng.integers(1, 90, k), rng.random((k, 3)), np.eye(3) * a + rng.normal(0, 0.05, (3, 3))))
+    return out
+
+
+def test_many_structures_at_once_equal_the_converter_loop():
+    """chg_graph_build_many + chg_graph_views + the batch packers reading the builder's memory directly
+    (CHGNet.structures_to_batch) against converting every structure (converter.py:102-190) and batching the
+    CrystalGraphs: every field of the batch descriptor."""
+    import dataclasses
+
+    from chgnet_b200.batch import build_batch
+    from chgnet_b200.model import CHGNet
+
+    model = CHGNet.from_file("tests/golden/chgnet_0.3.0_weights.npz", version="0.3.0")
+    model.graph_converter.on_isolated_atoms = "ignore"
+    structs = _random_structures(37, 3) + [([3], np.zeros((1, 3)), np.eye(3) * 20.0)]  # + one isolated atom, no edges
+    a = model.structures_to_batch(structs)
+    b = build_batch([model.graph_converter(s) for s in structs], "cpu")
+    n = 0
+    for f in dataclasses.fields(a):
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        if isinstance(x, torch.Tensor):
+            assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y), f.name
+            n += 1
+        elif f.name != "h2d_bytes":
+            assert x == y, f.name
+    assert n >= 30 and a.n_graphs == 38
+    # isolated atoms are reported like the converter does (converter.py:160-174)
+    model.graph_converter.on_isolated_atoms = "error"
+    with pytest.raises(ValueError, match="isolated atom"):
+        model.structures_to_batch(structs)
+    # a failing structure fails the call with the builder's message
+    from chgnet_b200._lib import ChgnetB200Error
+
+    with pytest.raises(ChgnetB200Error, match="singular lattice"):
+        model.structures_to_batch(structs[:3] + [([3], np.zeros((1, 3)), np.zeros((3, 3)))])
+
+
+def test_convert_many_equals_the_loop():
+    from chgnet_b200.model import GraphConverter
+
+    gc = GraphConverter()
+    structs = _random_structures(12, 5, lo=12)
+    for x, y in zip(gc.convert_many(structs, n_threads=4), [gc(s) for s in structs]):
+        assert torch.equal(x.atom_graph, y.atom_graph) and torch.equal(x.bond_graph, y.bond_graph)
+        assert torch.equal(x.neighbor_image, y.neighbor_image) and torch.equal(x.undirected2directed, y.undirected2directed)

@@ -142,3 +142,29 @@ def test_predict_structure_device_and_host_graph_paths_agree(monkeypatch):
         model.predict_structure(([1, 1], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 20.0))
     with pytest.raises(IndexError, match="index out of range"):
         model.predict_structure(([3, 99], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 4.0))
+
+
+def test_predict_structure_of_a_list_native_builder_equals_converter_loop(monkeypatch):
+    """predict_structure(list) builds the graphs of a chunk concurrently in the library and packs them out of the
+    builder's memory (CHGNet.structures_to_batch); CHGNET_B200_GRAPH=python converts structure by structure like the
+    reference (model.py:578-583).  Same batches -> same numbers, per structure, in order; chunking by batch_size."""
+    import os
+
+    from chgnet_b200.model import CHGNet
+
+    gold = os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz")
+    model = CHGNet.from_file(gold, version="0.3.0").to("cuda")
+    structs = [graphgen.random_structure(n, 9800 + n) for n in (7, 31, 18, 40, 12, 25, 9)]
+    native = model.predict_structure(structs, task="efsm", return_site_energies=True, batch_size=3)
+    monkeypatch.setenv("CHGNET_B200_GRAPH", "python")
+    loop = model.predict_structure(structs, task="efsm", return_site_energies=True, batch_size=3)
+    monkeypatch.delenv("CHGNET_B200_GRAPH")
+    assert len(native) == len(loop) == len(structs)
+    for a, b, s in zip(native, loop, structs):
+        assert set(a) == set(b)
+        assert a["f"].shape == (len(s[0]), 3)
+        for k in b:
+            assert a[k].shape == b[k].shape, k
+            assert np.abs(np.asarray(a[k], np.float64) - np.asarray(b[k], np.float64)).max() < 1e-6, k
+    with pytest.raises(ValueError, match="isolated atom"):
+        model.predict_structure(structs[:2] + [([1, 1], np.array([[0.0, 0, 0], [0.5, 0.5, 0.5]]), np.eye(3) * 20.0)])
