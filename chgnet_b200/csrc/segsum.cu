@@ -173,6 +173,9 @@ extern "C" int chg_segment_sum(const float* data, int32_t width, const int32_t* 
   int S = 1;
   // grow S while segments stay long enough AND all CTAs still fit in a single wave
   while (S < 8 && avg >= 16 * S && ((long long)n_rows * (2 * S) + groups - 1) / groups <= resident) S *= 2;
+  // long segments with one lane-group each leave a latency-bound tail (the last, longest segments stream with 4 loads
+  // in flight): two groups per row even when that takes more than one wave (c3: 67.5 -> 64.3 us, c4: 75.7 -> 71.8 us)
+  if (S == 1 && avg >= 32) S = 2;
   if (segsum_force_s() > 0) S = segsum_force_s();
   const bool u8 = segsum_unroll() == 8;
   cudaStream_t st = as_stream(stream);

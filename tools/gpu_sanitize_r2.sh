@@ -25,6 +25,19 @@ md2.set_temperature(300.0, seed=1)
 md2.run(2, log_every=0)
 torch.cuda.synchronize()
 print("md ok", md.potential_energy, md2.potential_energy)
+# list of structures: chg_graph_build_many -> chg_pack_batch_wire (two-phase copies, expand_image / derive_angle_columns)
+structs = [graphgen.random_structure(n, 9400 + n) for n in (9, 14, 11)]
+ps = m.predict_structure(structs, task="efs", batch_size=2)
+print("predict_structure (list)", [float(p["e"]) for p in ps])
+# one training step whose angle-level weight gradients take the tcgen05 wgrad kernel (>= 4096 reduction rows)
+from chgnet_b200.trainer import Trainer
+graphs = graphgen.random_graphs(2, 20, 24, 4243)
+base = m.predict_graph(graphs, task="efsm", batch_size=2)
+lab = {"e": torch.tensor([float(p["e"]) + 0.05 for p in base]), "f": [torch.as_tensor(p["f"]) + 0.02 for p in base],
+       "s": [torch.as_tensor(p["s"]) - 0.05 for p in base], "m": [torch.as_tensor(p["m"]) + 0.03 for p in base]}
+tr = Trainer(m, targets="efsm", criterion="MSE", learning_rate=1e-5)
+print("train_step", tr.train_step(graphs, lab), "angles", sum(int(g.bond_graph.shape[0]) for g in graphs))
+torch.cuda.synchronize()
 PY
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 3 python /tmp/san2.py > gpurun_out/sanitizer_memcheck_r2.log 2>&1
 echo "memcheck rc=$?" | tee -a gpurun_out/sanitizer_memcheck_r2.log
