@@ -1,6 +1,7 @@
 // Persistent host worker threads shared by the batch packer (batch_wire.cu) and the many-structure graph builder
 // (graph_builder.cu): parked on a condition variable between jobs, never joined.
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -24,6 +25,7 @@ class WorkerPool {
   int size() const { return n_workers_ + 1; }
   // fn(k) for k in [0, n): k = 0 on the calling thread, the rest on the workers; returns when all are done
   void run(int n, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> one_job(run_m_);  // callers on different threads take turns
     n = std::max(1, std::min(n, size()));
     if (n > 1) {
       std::lock_guard<std::mutex> lk(m_);
@@ -61,7 +63,7 @@ class WorkerPool {
       }
     }
   }
-  std::mutex m_;
+  std::mutex m_, run_m_;
   std::condition_variable start_, done_;
   const std::function<void(int)>* job_ = nullptr;
   int job_n_ = 0, n_workers_ = 0;

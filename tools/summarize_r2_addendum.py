@@ -14,6 +14,44 @@ def sh(*args):
 lines = ["# Profiles r2 - addendum", "",
          "Everything here was measured on one B200 of the pool after `SUMMARY_r2.md` was written (tools/gpu_r16..r2x.sh). "
          "ncu per-launch times are cold-cache and serialised: compare SHARES and bytes; throughput numbers come from bench.py.", ""]
+# ---- validation of the final tree (tools/gpu_r24.sh / gpu_r25.sh): bench lines, test / sanitizer / smoke verdicts ----
+lines += ["## Final tree: bench lines (`profiles/r2_bench_*.json`), tests, sanitizer", "",
+          "| record | workload | kernel path ms/step | value | e2e ms/step | e2e value | roofline frac | parity ok | launches |", "|---|---|---|---|---|---|---|---|---|"]
+for name in ("r2_bench_c3_default.json", "r2_bench_c2.json", "r2_bench_c1.json", "r2_bench_c5.json", "r2_bench_c3_2gpu.json"):
+    p = os.path.join(PROF, name)
+    if not os.path.exists(p):
+        continue
+    try:
+        d = json.load(open(p))
+    except ValueError:
+        d = json.loads([l for l in open(p) if l.startswith("{")][0])
+    lines.append(f"| `{name}` | {d['config']['workload'][:40]} ({d['n_gpus']} GPU) | {d['ms_per_step']:.3f} | {d['value']:.1f} {d['unit']} | "
+                 f"{d['e2e']['ms_per_step']:.3f} | {d['e2e']['value']:.1f} | {(d.get('roofline') or {}).get('frac')} | "
+                 f"{(d.get('parity') or {}).get('ok')} | {d.get('gpu_launches')} |")
+    c4 = d.get("c4") or {}
+    if c4:
+        md = c4.get("md") or {}
+        lines.append(f"| &nbsp;&nbsp;`c4` key of the same line | 10 000-atom cell | {c4.get('ms_per_step')} | {c4.get('atoms_per_s')} atoms/s | "
+                     f"{(c4.get('e2e') or {}).get('ms_per_step')} (graph) / {(c4.get('e2e_from_structure') or {}).get('ms_per_step')} (structure) | | "
+                     f"{(c4.get('roofline') or {}).get('frac')} | | MD ms/step: device {(md.get('device_driver') or {}).get('ms_per_step')}, "
+                     f"device+skin {(md.get('device_driver_skin') or {}).get('ms_per_step')}, host loop {(md.get('host_driver') or {}).get('ms_per_step')} |")
+lines.append("")
+for name, what in (("r2_pytest_gpu.log", "`pytest tests -m gpu`"), ("r2_smoke.log", "`__graft_entry__.smoke()`"), ("sanitizer_memcheck_r2.log", "`compute-sanitizer --tool memcheck` (tools/gpu_sanitize_r2.sh)"),
+                   ("r2_predict_structure_list.log", "structures -> graphs -> E/F/sigma for a list of 256 structures (tools/time_convert_many.py)")):
+    p = os.path.join(PROF, name)
+    if os.path.exists(p):
+        tail = [l.rstrip() for l in open(p) if l.strip() and "Warning" not in l and "Consider using" not in l][-6:]
+        lines += [f"* {what} -> `profiles/{name}`:", "", "```"] + [t[:220] for t in tail] + ["```", ""]
+p = os.path.join(OUT, "md_small_r2.json")
+if os.path.exists(p):
+    import shutil
+    shutil.copy(p, os.path.join(PROF, "md_small_r2.json"))
+    lines += ["## MD steps/s of small cells (tools/time_md_small.py; NVE, 2 fs, 300 K, LiMnO2 supercells)", "",
+              "| atoms | device driver, 0.5 A skin, CUDA-graph replay | device driver, lists rebuilt every step | host calculator loop |", "|---|---|---|---|"]
+    for r in json.load(open(p)):
+        f = lambda k: f"{r[k]['ms_per_step']} ms ({r[k]['steps_per_s']} steps/s)"
+        lines.append(f"| {r['atoms']} | {f('device_skin0.5_cuda_graph')} | {f('device_skin0_rebuild_every_step')} | {f('host_calculator_loop')} |")
+    lines.append("")
 for wl in ("c3", "c4"):
     p = os.path.join(PROF, f"launches_{wl}_r2.csv")
     if os.path.exists(p):
