@@ -459,8 +459,11 @@ def run_reference(args, rank: int, world: int) -> None:
                f"the full batch would exceed {REF_BUDGET_S:.0f} s for {args.steps}+{args.warmup} steps at {1.0 / per_graph:.1f} structures/s")
         desc_s = ("the full batch per step" if n == len(graphs) else
                   f"first {n} of {len(graphs)} graphs per step ({n / len(graphs):.3f} of the batch: {why})")
-    desc_s += f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep, best of 3 per candidate)"
-    bs = min(len(sample), 64)  # predict_graph's batching loop (model.py:634-645); 64 per forward (reference default 16)
+    desc_s += (f"; {threads} of {os.cpu_count()} host threads (fastest of a 4..all sweep, best of 3 per candidate); "
+               "16 graphs per forward (the reference's default batch_size)")
+    # predict_graph's batching loop (model.py:634-645) at the reference's own default batch_size = 16 (model.py:601): the CPU
+    # path is FASTEST there (measured on the pool's hosts: 17 structures/s at 8-16 graphs per forward, 5 at 64)
+    bs = min(len(sample), 16)
     for _ in range(args.warmup):
         orc.predict_graph(w, sample, "efs", batch_size=bs)
     t0 = time.perf_counter()
@@ -557,7 +560,7 @@ class EventKernels:
                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
 
 
-def infer_leg(model, graphs, dev, local_rank: int, world: int, steps: int, warmup: int) -> dict:
+def infer_leg(model, graphs, dev, local_rank: int, world: int, steps: int, warmup: int, replay: bool = False) -> dict:
     """Times one workload two ways: the kernel path on a resident batch descriptor (CUDA events per step, L2
     flushed between steps) and `CHGNet.predict_graph` from host CrystalGraphs (wall clock per step, device
     synchronised on both sides; host packing, H2D, CSR build, kernels, D2H inside).  Max over ranks."""
@@ -578,7 +581,8 @@ def infer_leg(model, graphs, dev, local_rank: int, world: int, steps: int, warmu
     native = model._get_native()  # the product's inference path: ONE chg_forward call per step
 
     def step_resident():
-        out = native(batch, need_grad=True)
+        # replay: the resident descriptor is evaluated through NativeForward.replay (one captured CUDA graph of chg_forward)
+        out = native.replay(batch, need_grad=True) if replay else native(batch, need_grad=True)
         scale = EV_A3_TO_GPA / batch.volume.to(torch.float64)
         stress = (out["virial"].view(-1, 3, 3) * scale[:, None, None]).to(torch.float32)
         return out["energy"], out["force"].to(torch.float32), stress
@@ -719,7 +723,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         print(json.dumps({"scatter_only": True, "us_per_launch": ms * 1e3, "algorithmic_bytes": nbytes}))
         return
 
-    leg = infer_leg(model, graphs, dev, local_rank, world, args.steps, args.warmup)
+    leg = infer_leg(model, graphs, dev, local_rank, world, args.steps, args.warmup, replay=args.graph_replay)
     batch = leg["batch"]
     ms_per_step, e2e_ms_per_step = leg["ms_per_step"], leg["e2e_ms_per_step"]
 
@@ -909,6 +913,7 @@ def main() -> None:
     ap.add_argument("--no-c4", action="store_true", help="skip the 10,000-atom extra leg of a c2 / c3 run")
     ap.add_argument("--no-collective", action="store_true", help="N > 1: skip the c5 all-reduce leg")
     ap.add_argument("--no-md", action="store_true", help="skip the MD sub-leg of the c4 extra leg")
+    ap.add_argument("--graph-replay", action="store_true", help="kernel-path leg: replay one captured CUDA graph of chg_forward per step")
     ap.add_argument("--scatter-only", action="store_true", help="run only the AtomConv scatter kernel timing (ncu target)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -172,6 +172,9 @@ class NativeForward:
         if "composition_model.fc.weight" in state_dict:
             self.atom_ref = state_dict["composition_model.fc.weight"].detach().reshape(-1).to(device=device, dtype=torch.float32)
         self.calls = 0
+        self._ws_version = 0          # bumped whenever the workspace is reallocated (captured graphs point into it)
+        self._graphs: dict = {}       # (id(batch), flags) -> captured CUDA graph of one chg_forward
+        self._seen: dict = {}
 
     def reserve(self, b: DeviceBatch, *, need_grad: bool = True) -> None:
         """Grow the workspace for this batch NOW (e.g. before a CUDA-graph capture, where it must not be reallocated)."""
@@ -179,6 +182,38 @@ class NativeForward:
         need, _ = plan(self.hps, batch_struct(b, None), outs)
         if self.workspace.numel() < need + 256:
             self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            self._ws_version += 1
+
+    def replay(self, b: DeviceBatch, *, need_grad: bool, need_magmom: bool = False, need_atom_fea: bool = False) -> dict[str, Tensor]:
+        """``chg_forward`` for a batch descriptor that is evaluated again and again (same ``DeviceBatch`` object: fixed
+        topology, coordinates / lattice updated in place): the second call captures the launches of one forward into a
+        CUDA graph, later calls replay it (one graph launch instead of ~130 kernel launches - small systems are
+        launch-bound).  The returned tensors are REUSED by every replay: consume them before the next call."""
+        flags = (bool(need_grad), bool(need_magmom), bool(need_atom_fea))
+        key = (id(b), flags)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["batch"] is b and ent["ws"] == self._ws_version:
+            ent["graph"].replay()
+            self.calls += 1
+            return ent["res"]
+        kw = dict(need_grad=need_grad, need_magmom=need_magmom, need_atom_fea=need_atom_fea)
+        res = self(b, **kw)  # eager: sizes the workspace, sets the kernels' one-time attributes
+        seen = self._seen.get(key)
+        if seen is None or seen[0] is not b:
+            self._seen = {key: (b, 1)}  # one candidate at a time
+            return res
+        dev = self.device
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.graph(graph, stream=side):
+            captured = self(b, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if len(self._graphs) >= 8:  # small cache: drop the oldest entry
+            self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = {"graph": graph, "res": captured, "batch": b, "ws": self._ws_version}
+        self._seen = {}
+        return res
 
     def __call__(self, b: DeviceBatch, *, need_grad: bool, need_magmom: bool = False, need_atom_fea: bool = False,
                  need_crystal_fea: bool = False) -> dict[str, Tensor]:
@@ -201,6 +236,7 @@ class NativeForward:
         need, _ = plan(self.hps, bs, outs)
         if self.workspace.numel() < need + 256:
             self.workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=dev)
+            self._ws_version += 1
         base = (self.workspace.data_ptr() + 255) // 256 * 256
         room = self.workspace.numel() - (base - self.workspace.data_ptr())
         with torch.cuda.device(dev):  # launches go to the model's device and its current stream

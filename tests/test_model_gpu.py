@@ -234,3 +234,33 @@ def test_native_forward_equals_python_schedule(model, monkeypatch):
     rc = n.lib.chg_forward(ctypes.byref(n.hps), n.weights.data_ptr(), ctypes.byref(bs), ctypes.byref(outs), base, 1 << 15,
                            torch.cuda.current_stream().cuda_stream)
     assert rc != 0 and b"workspace too small" in n.lib.chg_last_error()
+
+
+def test_static_evaluator_replays_one_cuda_graph():
+    """CHGNet.static_evaluator: fixed topology, coordinates updated in place, chg_forward replayed as a CUDA graph
+    (NativeForward.replay).  Same numbers as predict_graph on the re-built graph of the displaced structure, call after
+    call (eager -> capture -> replays), for a single graph and for a list."""
+    from chgnet_b200.model import CHGNet
+
+    gold = os.path.join(os.path.dirname(__file__), "golden", "chgnet_0.3.0_weights.npz")
+    model = CHGNet.from_file(gold, version="0.3.0").to("cuda")
+    rng = np.random.default_rng(5)
+    structs = [graphgen.random_structure(n, 4100 + n) for n in (12, 17)]
+    graphs = [graphgen.make_crystal_graph(*s) for s in structs]
+    ev = model.static_evaluator(graphs, task="efsm")
+    base = model.predict_graph(graphs, task="efsm", batch_size=2)
+    calls_before = model._get_native().calls
+    for it in range(5):
+        new = [(z, f + (0.0015 * rng.standard_normal(f.shape) if it else 0.0), lat) for z, f, lat in structs]
+        ev.update(frac=np.concatenate([f for _, f, _ in new]))
+        got = ev()
+        want = model.predict_graph([graphgen.make_crystal_graph(*s) for s in new], task="efsm", batch_size=2) if it else base
+        for a, b in zip(got, want):
+            assert set(a) == set(b)
+            for k in b:
+                assert np.abs(np.asarray(a[k], np.float64) - np.asarray(b[k], np.float64)).max() < 3e-5, (it, k)
+    native = model._get_native()
+    assert len(native._graphs) == 1 and native.calls > calls_before
+    one = model.static_evaluator(graphs[0], task="ef")
+    r = [one() for _ in range(3)]
+    assert set(r[0]) == {"e", "f"} and np.allclose(r[0]["f"], r[2]["f"]) and np.allclose(r[0]["f"], base[0]["f"], atol=1e-6)
