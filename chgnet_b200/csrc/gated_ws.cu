@@ -40,6 +40,16 @@ constexpr int TR = 128;          // rows per tile
 constexpr int HALF_BYTES = TR * 64 * 4;
 constexpr int IMG_BYTES = 64 * 64 * 4;
 constexpr int STRIP = 16;        // rows per reduction strip (one half-warp)
+#ifndef CHG_WS_REGSPLIT
+// 1: setmaxnreg in the forward kernel - 20 warps launched with 96 registers, then 144 for the producer warps (24 instead of 12
+// independent 16-byte gathers in flight per thread), 72 for the epilogue warps, 40 for the MMA warp's warpgroup (3 of its 4 warps
+// exist only to donate registers; the pool of a CTA is what it was launched with).  Measured on B200 (c3): AtomConv 1.53 -> 1.47 ms,
+// BondConv 1.55 -> 1.51 ms per step, i.e. the gathers' memory-level parallelism is NOT what bounds the kernel: left off.
+#define CHG_WS_REGSPLIT 0
+#endif
+constexpr int PB = CHG_WS_REGSPLIT ? 8 : 4;  // rows gathered per producer batch (x 3-4 loads each in flight)
+// register pool of the CTA = what it was launched with: 20 warps x 96; after the reallocation 8 x 72 + 8 x 144 + 4 x 40 = 1888 <= 1920
+constexpr int WS_FWD_THREADS = CHG_WS_REGSPLIT ? 640 : WS_THREADS;
 
 struct WsSmem {
   static constexpr int IMG_OFF = 0;                          // Bc_hi, Bc_lo, Bg_hi, Bg_lo
@@ -87,7 +97,7 @@ __device__ __forceinline__ int swz(int r, int c) { return r * 256 + ((c ^ (r & 7
 // image element (n, kk) = src[kk * ld + col0 + n]   (64 x 64, K-major, no swizzle), all threads of the CTA
 __device__ __forceinline__ void build_image_ws(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int ld, int col0,
                                                int tid) {
-  for (int i = tid; i < 4096; i += WS_THREADS) {
+  for (int i = tid; i < 4096; i += (int)blockDim.x) {
     const int kk = i >> 6, n = i & 63;
     uint32_t h, l;
     tc::split_tf32(__ldg(src + (size_t)kk * ld + col0 + n), h, l);
@@ -157,7 +167,7 @@ __device__ __forceinline__ void epilogue_half(uint32_t d_addr, const float* s_b2
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const FusedArgs a) {
+__global__ void __launch_bounds__(WS_FWD_THREADS, 1) gated_ws_fwd_kernel(const FusedArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* s_img = smem_raw + WsSmem::IMG_OFF;
   uint8_t* s_hs = smem_raw + WsSmem::HS_OFF;
@@ -198,6 +208,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
 
   if (warp >= 8 && warp < 16) {
     // ============================ producer groups (gather -> SiLU -> A operand) ============================
+#if CHG_WS_REGSPLIT
+    // the gathers are what the kernel waits for: take registers from the epilogue warps (which give up 24 each) so that a
+    // producer thread keeps 24 instead of 12 independent 16-byte loads in flight
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+#endif
     const int half = (warp - 8) >> 2;            // 0: core columns, 1: gate columns
     const int gt = tid - 256 - half * 128;       // 0..127 inside the group; also this thread's tile row / TMEM lane
     const int tx = gt & 15, ty = gt >> 4;        // 16 lanes per row, 8 rows per pass
@@ -228,11 +243,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
         }
       }
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        float4 v[4];
+      for (int b = 0; b < 16 / PB; ++b) {
+        float4 v[PB];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = ty + 8 * (b * 4 + i);
+        for (int i = 0; i < PB; ++i) {
+          const int row = ty + 8 * (b * PB + i);
           const float* s0 = a.p_a + (size_t)gi[row] * 256 + col;
           const float* s1 = a.p_a + (size_t)gi[TR + row] * 256 + 128 + col;
           const float* s2 = a.p_b + (size_t)gi[2 * TR + row] * 128 + col;
@@ -240,8 +255,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
           if (MODE == BOND) v[i] = v[i] + ldg4(a.p_c + (size_t)min(base + row, a.n_rows - 1) * 128 + col);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = ty + 8 * (b * 4 + i);
+        for (int i = 0; i < PB; ++i) {
+          const int row = ty + 8 * (b * PB + i);
           if (a.save_pre != nullptr && base + row < a.n_rows) stg4(a.save_pre + (size_t)(base + row) * 128 + col, v[i]);
           *reinterpret_cast<float4*>(stage + swz(row, tx)) =
               make_float4(silu_f(v[i].x), silu_f(v[i].y), silu_f(v[i].z), silu_f(v[i].w));
@@ -268,9 +283,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
       tc::fence_before_sync();
       mbar_arrive(&bars.a_full[half]);
     }
-  } else if (warp == 16) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
+  } else if (warp >= 16) {
+    // ============================ MMA issuer (warp 16; warps 17-19 only donate registers) ============================
+#if CHG_WS_REGSPLIT
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+    if (warp == 16 && lane == 0) {
       const uint32_t idesc = tc::idesc_tf32(128, 64);
       const uint32_t img = tc::smem_u32(s_img);
       int tl = 0;
@@ -299,6 +317,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gated_ws_fwd_kernel(const Fused
     }
   } else if (warp < 8) {
     // ============================ epilogue: warps 0-3 core half, warps 4-7 gate half ============================
+#if CHG_WS_REGSPLIT
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+#endif
     const int eh = warp >> 2;        // 0: core, 1: gate
     const int t = tid & 127;         // tile row == TMEM lane
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
@@ -423,7 +444,7 @@ int launch_fused(const FusedArgs& a, cudaStream_t stream) {
       attr_set = true;
     }
     const int n_tiles = (a.n_rows + TR - 1) / TR;
-    gated_ws_fwd_kernel<MODE><<<min(n_tiles, sm_count()), WS_THREADS, WsSmem::TOTAL, stream>>>(a);
+    gated_ws_fwd_kernel<MODE><<<min(n_tiles, sm_count()), WS_FWD_THREADS, WsSmem::TOTAL, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("gated_ws_fwd_kernel: launch failed: %s", cudaGetErrorString(e));

@@ -80,6 +80,11 @@ inline WorkerPool& pool() {
   if (p == nullptr || p->pid() != getpid()) {
     const unsigned hc = std::thread::hardware_concurrency();
     int n = (int)std::min<unsigned>(hc == 0 ? 4 : hc, 16);
+    // one process per GPU (torchrun sets LOCAL_WORLD_SIZE): share the physical cores (2 hardware threads each) between the ranks
+    if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) {
+      const int ranks = std::atoi(e);
+      if (ranks > 1 && hc > 0) n = std::max(2, std::min(n, (int)(hc / 2) / ranks));
+    }
     if (const char* e = std::getenv("CHG_PACK_THREADS")) n = std::max(1, std::min(std::atoi(e), 64));
     p = new WorkerPool(n - 1);
   }
