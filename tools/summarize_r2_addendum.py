@@ -82,5 +82,13 @@ for p in sorted(glob.glob(os.path.join(OUT, "r18_bench_*_w*.json")) + glob.glob(
 if rows:
     lines += ["## Wire format A/B (`w1` compact wire format, `w0` full format; r2x = wire format + write-combined staging)", "",
               "| run | kernel path ms | e2e ms | H2D bytes | pack+H2D+CSR ms | c4 kernel ms | c4 e2e ms |", "|---|---|---|---|---|---|---|"] + rows + [""]
+lines += ["## Kernel A/B experiments of the last hours (bench.py c3 unless noted; CUDA events, one B200)", "",
+          "| experiment | result | kept? |", "|---|---|---|",
+          "| `segment_sum<128>`: rows in flight per lane-group 4 / 8, lane-groups per row 1 / 2 / 4 (tools/gpu_r23.sh) | c3 by-centre sum 67.5 us (4 rows, 1 group) -> 63.9 (8, 1) / 64.3 (4, 2) / 63.5 (8, 4); c4 75.7 -> 76.3 / 71.8 / 73.7 | 2 groups per row for segments >= 32 rows: roofline 0.82 -> 0.87 (c3), 0.88 -> 0.93 (c4) |",
+          "| `wgrad_tc_kernel`: 64-row stages, 4 loads in flight per thread -> all 48 loads of a stage up front -> 32-row stages, 2 CTAs / SM | 23.9 -> 7.8 -> 6.4 ms per c5 step (FFMA kernel: 8.7) | yes |",
+          "| `gated_ws_bwd_kernel`: load loops unrolled 4 instead of 2 (tools/gpu_r28.sh) | atom 2.14 -> 2.12 ms, bond 2.05 -> 2.09 ms per step: no change | no |",
+          "| `gated_ws_fwd_kernel`: setmaxnreg register split, 24 instead of 12 gathers in flight per producer thread (tools/gpu_r29.sh) | AtomConv 1.53 -> 1.47 ms, BondConv 1.55 -> 1.51 ms per step; 31 GPU tests pass | no (`CHG_WS_REGSPLIT=0`): the gathers' parallelism is not the limiter |",
+          "| write-combined pinned staging for the batch packer (tools/gpu_r21.sh) | packing 1.1 -> 10.6 ms (write-combining is very slow on these hosts) although the copy itself would run at 54 GB/s | no (`CHGNET_B200_STAGING=wc` selects it) |",
+          "| `chg_forward` replayed as one CUDA graph (tools/gpu_r27.sh) | c1 1.204 -> 0.960 ms, c2 7.69 -> 7.37, c3 16.18 -> 15.87 | as `NativeForward.replay` / `CHGNet.static_evaluator` / bench key `graph_replay`; the headline `value` stays the eager path |", ""]
 open(os.path.join(PROF, "SUMMARY_r2_addendum.md"), "w").write("\n".join(lines) + "\n")
 print("wrote profiles/SUMMARY_r2_addendum.md", len(lines))
