@@ -698,6 +698,33 @@ def scatter_roofline(K, batch, workload: str, dev) -> dict:
                                                 "gated_ws_fwd_kernel (the message never reaches HBM)"}}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU: keep this process (and the packer's worker threads it creates later) on the CPUs NVML reports as
+    local to its GPU, so that the pinned staging buffers and the threads that fill them sit on the GPU's NUMA node (what
+    `numactl --cpunodebind` does in a deployment).  Returns (previous mask, description) or (None, why not); the CPU-baseline
+    leg restores the previous mask.  CHGNET_BENCH_BIND=0 disables it."""
+    if os.environ.get("CHGNET_BENCH_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None, "disabled"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus or cpus == prev:
+            return None, f"NVML reports no narrower CPU set for GPU {index} ({len(prev)} CPUs allowed)"
+        os.sched_setaffinity(0, cpus)
+        return prev, f"{len(cpus)} of {len(prev)} CPUs (local to GPU {index}: {min(cpus)}..{max(cpus)})"
+    except Exception as exc:  # noqa: BLE001  (no NVML / no permission: run unbound)
+        return None, f"unavailable: {exc!r}"[:160]
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import contextlib
     import io
@@ -710,6 +737,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    prev_affinity, binding = bind_to_gpu_numa_node(local_rank)
     with contextlib.redirect_stdout(io.StringIO()):
         model = CHGNet.from_file(WEIGHTS, version="0.3.0").to(dev).eval()
     graphs, desc, whole = sharded_workload(args.workload, rank, world)
@@ -852,6 +880,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     if not args.no_cpu_baseline:
         from oracle import chgnet_oracle as orc
 
+        if prev_affinity is not None:  # the CPU baseline may use every core of the host
+            os.sched_setaffinity(0, prev_affinity)
         w = orc.load_weights_npz(WEIGHTS)
         n_s = min(len(graphs), args.cpu_sample if args.cpu_sample > 0 else 8)
         if args.workload == "c4":
@@ -909,7 +939,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         "atoms_per_s": whole["atoms"] / (ms_per_step * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": cfg, "rank0_share": c,
+        "config": cfg, "rank0_share": c, "cpu_binding": binding,
         "engine": "native chg_forward (one C call per step); kernel_shares via the Python schedule of the same kernels",
         "e2e": {"value": total_graphs / (e2e_ms_per_step * 1e-3), "unit": "structures/s",
                 "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": leg["h2d"], "d2h_bytes_per_step": leg["d2h"],

@@ -7,6 +7,9 @@ from chgnet_b200 import graphgen
 from chgnet_b200 import batch as B
 
 dev = torch.device("cuda")
+if os.environ.get("PROBE_BIND") == "1":
+    import bench
+    print("cpu binding:", bench.bind_to_gpu_numa_node(0)[1])
 for mb in (1, 8, 35, 128):
     h = torch.empty(mb * 2**20 // 4, dtype=torch.int32).pin_memory()
     d = torch.empty_like(h, device=dev)
