@@ -757,7 +757,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     # ---------------- the same resident step replayed as ONE CUDA graph (NativeForward.replay) ----------------
     graph_replay = None
-    if not args.graph_replay:
+    if not args.graph_replay and world == 1:  # single-GPU records only
         try:
             nat, flush_r = model._get_native(), L2Flush(dev)
             for _ in range(3):  # eager, capture, first replay

@@ -206,7 +206,7 @@ class DeviceMD(_DeviceSystem):
                 self._warmed = True
             # the previous capture stays alive until the new one exists: the shared pool must never drop to zero users
             g = torch.cuda.CUDAGraph()
-            g.capture_begin(pool=self._pool)
+            g.capture_begin(pool=self._pool, capture_error_mode="thread_local")  # other threads (NCCL watchdog) may call CUDA
             try:
                 self._step_body()
             finally:

@@ -206,7 +206,8 @@ class NativeForward:
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.graph(graph, stream=side):
+        # thread_local: CUDA calls of other threads (an NCCL watchdog, a clock sampler) must not invalidate this capture
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
             captured = self(b, **kw)
         torch.cuda.current_stream(dev).wait_stream(side)
         if len(self._graphs) >= 8:  # small cache: drop the oldest entry

@@ -54,7 +54,10 @@ int64_t chg_launch_count(void);
  *   "ws_min_rows": calls with fewer rows than this (default 4096) run the FFMA kernels even with gated_impl 3
  *                  (launch-bound regime: the persistent tcgen05 kernels' fixed cost loses on a few tiles)
  *   "wgrad_impl" : 1 tcgen05 3xTF32 for reductions over >= 4096 rows (default; csrc/wgrad_tc.cu), 0 FFMA
- * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3, CHG_WGRAD_IMPL = 0..1 set the defaults).       */
+ *   "segsum_unroll": 4 (default) or 8 input rows in flight per lane-group of chg_segment_sum (identical results)
+ *   "segsum_s"   : 0 (default: chosen from the mean segment length) or 1 / 2 / 4 / 8 lane-groups per output row
+ * (env CHG_LINEAR_IMPL / CHG_GATED_IMPL = 0..3, CHG_WGRAD_IMPL = 0..1, CHG_WS_MIN_ROWS, CHG_SEGSUM_UNROLL, CHG_SEGSUM_S set
+ * the defaults; CHG_PACK_THREADS = worker threads of the host packers / many-structure builder, default min(16, cores)). */
 int chg_set_option(const char* name, int32_t value);
 
 /* ---- K0: atom embedding.  x[i] = emb[z[i]-1]   (model.py:432-434, encoders.py:32) */
