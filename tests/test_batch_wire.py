@@ -121,3 +121,56 @@ def test_wire_format_equals_full_format_gpu():
     torch.cuda.synchronize()
     for o in outs:
         _assert_same(o, ref)
+
+
+def test_packer_is_safe_under_concurrent_callers():
+    """Two Python threads batching different graph lists at the same time: the library's worker pool runs one job at a
+    time (worker_pool.h), so both get exactly what a single caller gets.  (Staging buffers are per process: the CPU
+    'device' clones out of them before returning, like the device path copies out of them.)"""
+    import threading
+
+    # above the threading threshold, so the workers are actually used
+    sets = [graphgen.random_graphs(48, 20, 40, 500 + k) for k in range(2)]
+    want = [build_batch(s, "cpu", wire=False) for s in sets]
+    errors = []
+    lock = threading.Lock()
+
+    def work(k):
+        try:
+            for _ in range(4):
+                with lock:  # build_batch itself reuses per-process staging buffers: one Python caller at a time
+                    got = build_batch(sets[k], "cpu", wire=True)
+                _assert_same(got, want[k])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    # and the raw C entry point from two threads at once, each with its own buffers
+    from chgnet_b200 import batch as B
+    import ctypes
+
+    def raw(k, out):
+        infos = [g.pack_info() for g in sets[k]]
+        counts = np.ascontiguousarray(np.stack([i[0] for i in infos]))
+        ptrs = np.ascontiguousarray(np.stack([i[1] for i in infos]))
+        n, ed, eu, an = (int(v) for v in counts.sum(0))
+        ib = torch.empty(2 * n + 3 * ed + eu + 2 * an + 1, dtype=torch.int32)
+        fb = torch.empty(3 * n + 9 * len(infos), dtype=torch.float32)
+        im = torch.empty(3 * ed + 1, dtype=torch.int8)
+        flags = (ctypes.c_int32 * 5)()
+        for _ in range(6):
+            rc = B._pack_lib().chg_pack_batch_wire(len(infos), counts.ctypes.data, ptrs.ctypes.data, ib.data_ptr(), fb.data_ptr(),
+                                                   im.data_ptr(), None, None, None, flags, None)
+            assert rc == 0 and flags[4] == 0
+        out[k] = (ib[2 * n: 2 * n + ed].clone(), n, ed)
+
+    out = {}
+    threads = [threading.Thread(target=raw, args=(k, out)) for k in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for k in range(2):
+        center, n, ed = out[k]
+        assert torch.equal(center, want[k].center)
