@@ -165,7 +165,6 @@ def run_train(args, rank: int, world: int, local_rank: int, light: bool = False)
     from chgnet_b200.batch import build_batch
     from chgnet_b200.model import CHGNet
     from chgnet_b200.trainer import Trainer, loss_and_grads
-    from chgnet_b200.weights import unpack_grads
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
