@@ -109,3 +109,40 @@ def test_convert_many_equals_the_loop():
     for x, y in zip(gc.convert_many(structs, n_threads=4), [gc(s) for s in structs]):
         assert torch.equal(x.atom_graph, y.atom_graph) and torch.equal(x.bond_graph, y.bond_graph)
         assert torch.equal(x.neighbor_image, y.neighbor_image) and torch.equal(x.undirected2directed, y.undirected2directed)
+
+
+# ---- known answers of the reference's own converter tests (tests/test_crystal_graph.py; cutoffs 5 A / 3 A) -------------
+_KNOWN = [
+    # strain per lattice vector (pymatgen apply_strain), (edges, angles, bonds), {(column, atom): count} for atom_graph
+    ((0.0, 0.0, 0.0), (384, 744, 192), {(0, 0): 48, (1, 0): 48, (0, 4): 48, (0, 7): 48}),     # :22-42
+    ((0.1, 0.1, 0.1), (264, 288, 132), {(0, 3): 34, (1, 3): 34, (0, 7): 32}),                 # :174-211
+    ((0.2, -0.3, 0.5), (336, 256, 168), {(0, 3): 42, (1, 3): 42, (0, 7): 42}),                # :214-253
+]
+
+
+@pytest.mark.parametrize("backend", ["native", "numpy"])
+@pytest.mark.parametrize("strain,sizes,counts", _KNOWN)
+def test_reference_known_answers_strained_cells(backend, strain, sizes, counts):
+    z, frac, lat = graphgen.limno2_structure()
+    cell = lat * (1.0 + np.asarray(strain))[:, None]  # apply_strain scales lattice vector i by 1 + strain_i
+    g = graphgen.make_crystal_graph(z, frac, cell, atom_graph_cutoff=5.0, bond_graph_cutoff=3.0, backend=backend)
+    assert g.atomic_number.tolist() == [3, 3, 25, 25, 8, 8, 8, 8]
+    assert (len(g.atom_graph), len(g.bond_graph), len(g.undirected2directed)) == sizes
+    assert len(g.directed2undirected) == sizes[0] and list(g.lattice.shape) == [3, 3] and list(g.atom_frac_coord.shape) == [8, 3]
+    for (col, atom), want in counts.items():
+        assert int((g.atom_graph[:, col] == atom).sum()) == want, (col, atom)
+    if strain == (0.0, 0.0, 0.0):
+        assert int((g.bond_graph[:, 0] == 1).sum()) == 72  # :36
+
+
+def test_reference_stability_invariants_under_large_perturbations():
+    """tests/test_crystal_graph.py:306-335: 2x2x2 supercells with every atom displaced by 0.5 A still give complete
+    undirected bonds (the reference's converter falls back to the legacy algorithm when they do not)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(20):
+        z, frac, lat = graphgen.limno2_structure((2, 2, 2), 0.0, 0)
+        step = rng.standard_normal((len(z), 3))
+        step *= 0.5 / np.linalg.norm(step, axis=1, keepdims=True)  # Structure.perturb(distance=0.5)
+        g = _same(z, frac + step @ np.linalg.inv(lat), lat, atom_graph_cutoff=5.0, bond_graph_cutoff=3.0)
+        assert g.directed2undirected.shape[0] == 2 * g.undirected2directed.shape[0]
+        assert g.atom_graph.shape[0] == g.directed2undirected.shape[0]
