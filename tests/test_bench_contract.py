@@ -38,3 +38,13 @@ def test_default_arm_needs_cuda():
         return
     res = _run("--steps", "1", "--warmup", "1")
     assert res.returncode != 0 and "no CUDA device" in (res.stderr + res.stdout)
+
+
+def test_reference_arm_under_torchrun_only_rank0_works():
+    """N > 1: the driver launches the reference arm like the product arm (one process per GPU); rank 0 alone runs and prints,
+    the other ranks exit 0 without work and without output."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stderr[-500:]
+    assert not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
