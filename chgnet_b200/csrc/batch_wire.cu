@@ -131,24 +131,27 @@ extern "C" int chg_pack_batch_wire(int32_t n_graphs, const int64_t* counts, cons
   WorkerPool& wp = pool();
   int n_thr = 1;
   if (total_items > (1 << 18)) n_thr = (int)std::min<int64_t>(wp.size(), std::max<int64_t>(1, total_items >> 17));
+  // work units: 4 per worker, taken from a shared counter, so that a worker the host deschedules for a while (busy box)
+  // delays one small unit, not a sixteenth of the batch.  Many graphs: unit t = the graphs cut[t] .. cut[t+1]-1, whole;
+  // few (large) graphs: unit t = slice t of every array of every graph.
   const bool by_graph = n_graphs >= 4 * n_thr;
-  // by_graph: worker t owns the graphs cut[t] .. cut[t+1]-1 whole; else every worker owns slice t of every array of every graph
-  std::vector<int> cut((size_t)n_thr + 1, n_graphs);
+  const int n_units = n_thr == 1 ? 1 : (by_graph ? (int)std::min<int64_t>(n_graphs, 4 * n_thr) : 4 * n_thr);
+  std::vector<int> cut((size_t)n_units + 1, n_graphs);
   cut[0] = 0;
   if (by_graph) {
     auto weight = [&](int g) { return off[(size_t)g * 4] * 5 + off[(size_t)g * 4 + 1] * 6 + off[(size_t)g * 4 + 2] + off[(size_t)g * 4 + 3] * 5; };
-    for (int t = 1, g = 0; t < n_thr; ++t) {
-      const int64_t target = total_items * t / n_thr;
+    for (int t = 1, g = 0; t < n_units; ++t) {
+      const int64_t target = total_items * t / n_units;
       while (g < n_graphs && weight(g) < target) ++g;
       cut[t] = g;
     }
   }
-  std::vector<Partial> parts((size_t)n_thr);
+  std::vector<Partial> parts((size_t)n_units);
 
   auto phase = [&](int which, int t) {
     Partial& res = parts[t];
     const int g0 = by_graph ? cut[t] : 0, g1 = by_graph ? cut[t + 1] : n_graphs;
-    const int part = by_graph ? 0 : t, nparts = by_graph ? 1 : n_thr;
+    const int part = by_graph ? 0 : t, nparts = by_graph ? 1 : n_units;
     for (int g = g0; g < g1; ++g) {
       const int64_t n = counts[4 * g], ed = counts[4 * g + 1], eu = counts[4 * g + 2], an = counts[4 * g + 3];
       const int64_t a_off = off[(size_t)g * 4], e_off = off[(size_t)g * 4 + 1], u_off = off[(size_t)g * 4 + 2], g_off = off[(size_t)g * 4 + 3];
@@ -230,7 +233,13 @@ extern "C" int chg_pack_batch_wire(int32_t n_graphs, const int64_t* counts, cons
   };
 
   // ---- phase 1: atoms, edges, bonds -> three copies in flight while the angles are packed -------------------------
-  wp.run(n_thr, [&](int t) { phase(0, t); });
+  auto run_phase = [&](int which) {
+    std::atomic<int> next{0};
+    wp.run(n_thr, [&](int) {
+      for (int u = next.fetch_add(1, std::memory_order_relaxed); u < n_units; u = next.fetch_add(1, std::memory_order_relaxed)) phase(which, u);
+    });
+  };
+  run_phase(0);
   if (reduce_flags() != 0 || flags_out[2] >= 0) return CHG_OK;  // compact format rejected / bad Z: nothing shipped
   if (ship) {
     if (n_int_1 > 0) CHG_CUDA(cudaMemcpyAsync(ibuf_dev, ibuf_host, (size_t)n_int_1 * 4, cudaMemcpyHostToDevice, stream));
@@ -243,7 +252,7 @@ extern "C" int chg_pack_batch_wire(int32_t n_graphs, const int64_t* counts, cons
     }
   }
   // ---- phase 2: angles ---------------------------------------------------------------------------------------------
-  if (A > 0) wp.run(n_thr, [&](int t) { phase(1, t); });
+  if (A > 0) run_phase(1);
   if (reduce_flags() != 0) {
     if (ship) cudaStreamSynchronize(stream);  // the caller re-packs into the same staging buffers
     return CHG_OK;
